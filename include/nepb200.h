@@ -1,0 +1,116 @@
+/*
+ * nepb200.h -- C ABI of libnepb200.so: the B200-native (sm_100a) hot path for NEP-PACK
+ * (NonlinearEigenproblems.jl v1.1.1).  Reference citations are relative to the reference repo.
+ *
+ * The reference has no FFI on this path today (it is 100 % Julia, multiple dispatch); these entry
+ * points are what a Julia shim `ccall`s from new methods of the reference's own plugin interfaces
+ * (see INTEGRATION.md and nonlineareigenproblems.jl_b200/julia/NEPB200.jl):
+ *
+ *   compute_Mder / compute_Mlincomb[!] / compute_MM   src/NEPCore.jl:89,113-160,192
+ *   AbstractSPMF, get_Av / get_fv, SPMF_NEP           src/NEPTypes.jl:96-113,162-237
+ *   LinSolver / lin_solve                             src/LinSolvers.jl:100,135-137,157-159
+ *   LinSolverCreator / create_linsolver               src/LinSolverCreators.jl:11,35,107
+ *   integrate_interval(MatrixTrapezoidal, ...)        src/method_contour_common.jl:61-94
+ *   orthogonalize_and_normalize!(V,w,h,DGKS())        call sites src/method_iar.jl:107, method_tiar.jl:128
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (NEPB_E_*); nepb_last_error() gives the
+ *     message of the last failure on the calling thread.  There is no CPU fallback: without a
+ *     CUDA device every compute entry point fails with NEPB_E_CUDA.
+ *   - host pointers unless the name ends in _dev; host dense arrays are column-major (Julia layout),
+ *     complex = interleaved (re,im) doubles (layout of Julia ComplexF64 / C99 double _Complex).
+ *   - sparse input is Julia's SparseMatrixCSC: int64 colptr[n+1], int64 rowval[nnz], index_base 1
+ *     (0 accepted for C callers), row indices ascending within a column.
+ *   - functions f_i never cross the ABI: the caller evaluates them (scalars or small matrix
+ *     functions, exactly as src/NEPTypes.jl:993-1004 does) and passes coefficient blocks.
+ */
+#ifndef NEPB200_H
+#define NEPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEPB_OK 0
+#define NEPB_E_INVALID (-1)   /* bad argument / inconsistent sizes (reference: error("...")) */
+#define NEPB_E_CUDA (-2)      /* CUDA runtime failure, or no device */
+#define NEPB_E_SINGULAR (-3)  /* zero / non-finite pivot (reference: LinearAlgebra.SingularException) */
+#define NEPB_E_NOMEM (-4)
+#define NEPB_E_UNSUPPORTED (-5)
+
+/* coefficient modes of nepb_spmf_apply*: Z(n x q) = sum_i A_i * (V(n x k) * C_i(k x q)) */
+#define NEPB_COEF_SCALAR 0  /* C_i = c_i*I, q == k;          C = c[p]                              */
+#define NEPB_COEF_DIAG 1    /* C_i = diag(c_i[0..k-1]), q==k; C = p x k column-major (C[i + p*s])  */
+#define NEPB_COEF_GENERAL 2 /* C_i dense k x q;              C = p blocks, block i column-major    */
+
+typedef struct nepb_spmf nepb_spmf;   /* SPMF operator resident in HBM (union-pattern CSR)        */
+typedef struct nepb_block nepb_block; /* dense n x k complex block resident in HBM (row-major)    */
+
+/* ---- runtime ------------------------------------------------------------------------------- */
+const char* nepb_version(void);
+const char* nepb_last_error(void);
+int nepb_device_count(int* count);
+int nepb_set_device(int device);
+/* All work of the calling process is enqueued on one stream; by default a stream the library owns.
+ * Pass a cudaStream_t (e.g. torch's current stream) to time with external events. */
+int nepb_set_stream(void* cuda_stream);
+int nepb_synchronize(void);
+/* CUDA-event timer on the library stream: start / stop return elapsed milliseconds. */
+int nepb_timer_start(void);
+int nepb_timer_stop(float* ms);
+/* number of kernels this library launched since process start (bench.py "gpu_launches") */
+int64_t nepb_launch_count(void);
+
+/* ---- a1: SPMF operator (src/NEPTypes.jl:162-237; alignment :244-274) -------------------------- */
+/* Builds the union sparsity pattern of the p matrices (what form_aligned_sparsity_patterns does),
+ * converts CSC -> CSR, int64 -> int32 (overflow checked) and uploads one int32 column index per
+ * union nonzero plus p interleaved values.  nzval[i] is double[nnz_i] (val_is_complex=0) or
+ * interleaved complex (val_is_complex=1). */
+int nepb_spmf_create(int64_t n, int p, const int64_t* const* colptr, const int64_t* const* rowval,
+                     const void* const* nzval, int val_is_complex, int index_base, nepb_spmf** out);
+int nepb_spmf_destroy(nepb_spmf* h);
+int nepb_spmf_info(const nepb_spmf* h, int64_t* n, int* p, int64_t* nnz_union, int* val_is_complex);
+/* union pattern, CSC, in the index base given at creation: colptr[n+1], rowval[nnz_union] */
+int nepb_spmf_pattern(const nepb_spmf* h, int64_t* colptr, int64_t* rowval);
+/* the same pattern as the device sees it: CSR, 0-based int32, plus csr_of_csc[nnz] (position in CSR
+ * order of the j-th CSC nonzero) -- exposed so the integer work can be checked bit-exactly */
+int nepb_spmf_pattern_csr(const nepb_spmf* h, int32_t* rowptr, int32_t* colind, int32_t* csr_of_csc);
+
+/* ---- a5: compute_Mder for SPMF (src/NEPTypes.jl:336-367) ---------------------------------------- */
+/* nzval_out[nnz_union] (complex, CSC order of nepb_spmf_pattern) = sum_i coef[i] * A_i.nzval */
+int nepb_spmf_mder(const nepb_spmf* h, const double* coef /* p complex */, double* nzval_out);
+
+/* ---- a2,a3,a4,a12,a13: the fused multi-term SpMM ------------------------------------------------ */
+/* Z = sum_i A_i (V C_i); V is n x k, Z is n x q, host column-major with leading dimensions ldv, ldz
+ * (in complex elements).  Covers compute_MM with diagonal S (NEPTypes.jl:299-311), M(lambda)*V,
+ * batched residuals (errmeasure.jl:128-130) and, through NEPB_COEF_GENERAL, compute_Mlincomb
+ * (NEPTypes.jl:972-1011,1130-1160) and the nleigs stacked product (method_nleigs.jl:456-472). */
+int nepb_spmf_apply(const nepb_spmf* h, int mode, int k, int q, const double* V, int64_t ldv,
+                    const double* C, double* Z, int64_t ldz);
+
+/* ---- device-resident dense blocks (Krylov bases, probe matrices stay in HBM) ------------------- */
+int nepb_block_create(int64_t n, int k, nepb_block** out);
+int nepb_block_destroy(nepb_block* b);
+/* copy columns [k0, k0+kc) from/to a host column-major array (ld in complex elements) */
+int nepb_block_upload(nepb_block* b, int k0, int kc, const double* host, int64_t ld);
+int nepb_block_download(const nepb_block* b, int k0, int kc, double* host, int64_t ld);
+/* raw device pointer of the row-major n x k storage (complex interleaved) */
+void* nepb_block_dev_ptr(nepb_block* b);
+/* same product with operands already in HBM: no host traffic, asynchronous on the library stream */
+int nepb_spmf_apply_block(const nepb_spmf* h, int mode, const nepb_block* V, int q, const double* C,
+                          nepb_block* Z);
+/* algorithmic HBM bytes of one nepb_spmf_apply_block call (SURVEY.md 8(d) formula) */
+int64_t nepb_spmf_apply_bytes(const nepb_spmf* h, int mode, int k, int q);
+
+/* ---- deterministic synthetic data (bench / tests): Middle-Square-Weyl stream ------------------- */
+/* state = {x_lo,x_hi,w_lo,w_hi,s_lo,s_hi}; fills out[count] with uniform doubles in [0,1) exactly as
+ * gen_rng_float of src/gallery_extra/basic_random_examples.jl:86-95 and advances the state. */
+int nepb_msws_init(uint64_t seed_lo, uint64_t seed_hi, uint64_t state[6]);
+int nepb_msws_fill(uint64_t state[6], int64_t count, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEPB200_H */

@@ -1,0 +1,785 @@
+// Fused multi-term CSR SpMM for SPMF operators on sm_100a, and the C ABI around it.
+//
+//   Z(n x q) = sum_{i<p} A_i * (V(n x k) * C_i(k x q))
+//
+// All p matrices share one union pattern: one int32 column index per nonzero and the p values
+// interleaved right behind each other (vals[nz][p]), so the kernel walks every A_i in ONE pass over
+// the pattern and the coefficient combine happens in registers.  V / Z live in HBM row-major
+// (k*16 contiguous bytes per row) so a gathered row V[col,:] is one coalesced read.
+//
+// Replaces (reference, relative to src/): NEPTypes.jl:276-319 (compute_MM), :322-367 (compute_Mder),
+// :972-1011 and :1130-1160 (compute_Mlincomb), types_poly.jl:44-76, method_nleigs.jl:456-472 (BBCC*z),
+// errmeasure.jl:128-130 (one SpMV per Ritz pair -> one multi-lambda SpMM).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.h"
+#include "spmf_host.h"
+
+namespace nepb {
+
+// ---------------------------------------------------------------------------------------------
+// load helpers: matrix stream bypasses L1 (read once), V gathers allocate in L1 (stencil reuse)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ld_stream_f64x2(const double* p) {
+    double2 r;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double ld_stream_f64(const double* p) {
+    double r;
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int ld_stream_s32(const int* p) {
+    int r;
+    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+template <int VW>
+__device__ __forceinline__ void load_vals(const double* __restrict__ vals, size_t idx, double (&v)[VW]) {
+    const double* p = vals + idx * VW;
+    if constexpr (VW % 2 == 0) {
+#pragma unroll
+        for (int t = 0; t < VW; t += 2) {
+            double2 x = ld_stream_f64x2(p + t);
+            v[t] = x.x;
+            v[t + 1] = x.y;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < VW; ++t) v[t] = ld_stream_f64(p + t);
+    }
+}
+
+constexpr int MAXP = 16;
+struct CoefP {
+    double2 c[MAXP];
+};
+
+__device__ __forceinline__ void cfma(double2& acc, const double2 a, const double2 b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+
+// m = sum_i c_i * val_i for one nonzero; CA: values complex (VW = 2p) else real (VW = p)
+template <int VW, bool CA, class CF>
+__device__ __forceinline__ double2 combine(const double (&v)[VW], CF&& cf) {
+    double2 m = make_double2(0.0, 0.0);
+    if constexpr (CA) {
+#pragma unroll
+        for (int i = 0; i < VW / 2; ++i) cfma(m, cf(i), make_double2(v[2 * i], v[2 * i + 1]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < VW; ++i) {
+            double2 c = cf(i);
+            m.x = fma(c.x, v[i], m.x);
+            m.y = fma(c.y, v[i], m.y);
+        }
+    }
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1/K2: SCALAR (C_i = c_i I) and DIAG (C_i = diag c_i[.]) modes.
+// A row is owned by G = GC*GN lanes: GC lanes split the dense columns (cyclically, CPT each, so one
+// gather instruction reads GC*16 contiguous bytes), GN lanes split the row's nonzeros (U-deep
+// unrolled so U*GN independent loads are in flight per row) and are reduced with warp shuffles.
+// ---------------------------------------------------------------------------------------------
+template <int VW, bool CA, bool DIAG, int GC, int GN, int CPT, int U>
+__global__ void __launch_bounds__(256) spmm_fused_kernel(int n, int kt, int ldv, int ldz, const int* __restrict__ rowptr,
+                                                         const int* __restrict__ colind, const double* __restrict__ vals,
+                                                         const double2* __restrict__ V, double2* __restrict__ Z,
+                                                         const CoefP cp, const double2* __restrict__ cdiag, int p) {
+    constexpr int G = GC * GN;
+    constexpr int ROWS = 256 / G;
+    const int tid = threadIdx.x;
+    const int g = tid % G;
+    const int gc = g % GC;
+    const int gn = g / GC;
+    const int row = blockIdx.x * ROWS + tid / G;
+
+    // DIAG: per-column coefficients of this lane's CPT columns, kept in registers
+    double2 cd[DIAG ? CPT : 1][DIAG ? (CA ? VW / 2 : VW) : 1];
+    if constexpr (DIAG) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int c = gc + j * GC;
+#pragma unroll
+            for (int i = 0; i < (CA ? VW / 2 : VW); ++i) cd[j][i] = (c < kt) ? cdiag[i + p * c] : make_double2(0.0, 0.0);
+        }
+    }
+
+    double2 acc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[j] = make_double2(0.0, 0.0);
+
+    int start = 0, end = 0;
+    if (row < n) {
+        start = rowptr[row];
+        end = rowptr[row + 1];
+    }
+    for (int base = start; base < end; base += GN * U) {
+        int col[U];
+        double v[U][VW];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = base + u * GN + gn;
+            ok[u] = idx < end;
+            col[u] = 0;
+            if (ok[u]) {
+                col[u] = ld_stream_s32(colind + idx);
+                load_vals<VW>(vals, (size_t)idx, v[u]);
+            }
+        }
+        double2 x[U][CPT];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int c = gc + j * GC;
+                x[u][j] = make_double2(0.0, 0.0);
+                if (ok[u] && c < kt) x[u][j] = __ldg(V + (size_t)col[u] * ldv + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (ok[u]) {
+                if constexpr (!DIAG) {
+                    const double2 m = combine<VW, CA>(v[u], [&](int i) { return cp.c[i]; });
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) cfma(acc[j], m, x[u][j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) {
+                        const double2 m = combine<VW, CA>(v[u], [&](int i) { return cd[j][i]; });
+                        cfma(acc[j], m, x[u][j]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = GC; off < G; off <<= 1) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, off);
+            acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, off);
+        }
+    }
+    if (row < n && gn == 0) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int c = gc + j * GC;
+            if (c < kt) Z[(size_t)row * ldz + c] = acc[j];
+        }
+    }
+}
+
+// runtime-p fallback (any p <= MAXP, real or complex values); same row ownership with GC=4, GN=2
+template <bool DIAG>
+__global__ void __launch_bounds__(256) spmm_fused_generic_kernel(int n, int kt, int ldv, int ldz, const int* __restrict__ rowptr,
+                                                                 const int* __restrict__ colind, const double* __restrict__ vals,
+                                                                 const double2* __restrict__ V, double2* __restrict__ Z,
+                                                                 const CoefP cp, const double2* __restrict__ cdiag, int p, int ca) {
+    constexpr int GC = 4, GN = 2, G = 8, ROWS = 256 / G, CPT = 8;
+    const int tid = threadIdx.x;
+    const int g = tid % G, gc = g % GC, gn = g / GC;
+    const int row = blockIdx.x * ROWS + tid / G;
+    const int vw = ca ? 2 * p : p;
+    double2 acc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[j] = make_double2(0.0, 0.0);
+    int start = 0, end = 0;
+    if (row < n) {
+        start = rowptr[row];
+        end = rowptr[row + 1];
+    }
+    for (int idx = start + gn; idx < end; idx += GN) {
+        const int col = colind[idx];
+        const double* v = vals + (size_t)idx * vw;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int c = gc + j * GC;
+            if (c < kt) {
+                double2 m = make_double2(0.0, 0.0);
+                for (int i = 0; i < p; ++i) {
+                    const double2 ci = DIAG ? cdiag[i + p * c] : cp.c[i];
+                    const double2 a = ca ? make_double2(v[2 * i], v[2 * i + 1]) : make_double2(v[i], 0.0);
+                    cfma(m, ci, a);
+                }
+                cfma(acc[j], m, __ldg(V + (size_t)col * ldv + c));
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, GC);
+        acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, GC);
+    }
+    if (row < n && gn == 0) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int c = gc + j * GC;
+            if (c < kt) Z[(size_t)row * ldz + c] = acc[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: GENERAL mode, second stage.  X = V * [C_1 .. C_p] was formed by the panel kernel below with
+// layout X[row][c][i] (the p terms of output column c contiguous), then
+//   Z[row, c] = sum_nz sum_i val_i(nz) * X[col(nz), c, i].
+// ---------------------------------------------------------------------------------------------
+template <int VW, bool CA, int GC, int GN, int U>
+__global__ void __launch_bounds__(256) spmm_stacked_kernel(int n, int q, const int* __restrict__ rowptr,
+                                                           const int* __restrict__ colind, const double* __restrict__ vals,
+                                                           const double2* __restrict__ X, double2* __restrict__ Z, int ldz) {
+    constexpr int P = CA ? VW / 2 : VW;
+    constexpr int G = GC * GN;
+    constexpr int ROWS = 256 / G;
+    const int tid = threadIdx.x;
+    const int g = tid % G, gc = g % GC, gn = g / GC;
+    const int row = blockIdx.x * ROWS + tid / G;
+    int start = 0, end = 0;
+    if (row < n) {
+        start = rowptr[row];
+        end = rowptr[row + 1];
+    }
+    for (int c0 = 0; c0 < q; c0 += GC) {  // uniform trip count for the whole grid
+        const int c = c0 + gc;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int base = start; base < end; base += GN * U) {
+            int col[U];
+            double v[U][VW];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = base + u * GN + gn;
+                ok[u] = idx < end && c < q;
+                col[u] = 0;
+                if (ok[u]) {
+                    col[u] = ld_stream_s32(colind + idx);
+                    load_vals<VW>(vals, (size_t)idx, v[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (ok[u]) {
+                    const double2* xp = X + ((size_t)col[u] * q + c) * P;
+#pragma unroll
+                    for (int i = 0; i < P; ++i) {
+                        const double2 x = __ldg(xp + i);
+                        if constexpr (CA) {
+                            cfma(acc, make_double2(v[u][2 * i], v[u][2 * i + 1]), x);
+                        } else {
+                            acc.x = fma(v[u][i], x.x, acc.x);
+                            acc.y = fma(v[u][i], x.y, acc.y);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int off = GC; off < G; off <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        }
+        if (row < n && gn == 0 && c < q) Z[(size_t)row * ldz + c] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) spmm_stacked_generic_kernel(int n, int q, int p, int ca, const int* __restrict__ rowptr,
+                                                                   const int* __restrict__ colind, const double* __restrict__ vals,
+                                                                   const double2* __restrict__ X, double2* __restrict__ Z, int ldz) {
+    constexpr int G = 8, ROWS = 256 / G;
+    const int tid = threadIdx.x;
+    const int gn = tid % G;
+    const int row = blockIdx.x * ROWS + tid / G;
+    const int vw = ca ? 2 * p : p;
+    int start = 0, end = 0;
+    if (row < n) {
+        start = rowptr[row];
+        end = rowptr[row + 1];
+    }
+    for (int c = 0; c < q; ++c) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int idx = start + gn; idx < end; idx += G) {
+            const int col = colind[idx];
+            const double* v = vals + (size_t)idx * vw;
+            const double2* xp = X + ((size_t)col * q + c) * p;
+            for (int i = 0; i < p; ++i) {
+                const double2 a = ca ? make_double2(v[2 * i], v[2 * i + 1]) : make_double2(v[i], 0.0);
+                cfma(acc, a, __ldg(xp + i));
+            }
+        }
+#pragma unroll
+        for (int off = 1; off < G; off <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        }
+        if (row < n && gn == 0) Z[(size_t)row * ldz + c] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0: tall-skinny panel product X(n x w) = V(n x k) * Cs(k x w), all row-major complex.
+// 32 rows x 32 k-chunk tile of V staged in shared memory with coalesced loads; bandwidth-bound on V.
+// ---------------------------------------------------------------------------------------------
+constexpr int PANEL_R = 32, PANEL_K = 32, PANEL_W = 8;  // block computes 32 rows x (8 outputs per pass)
+__global__ void __launch_bounds__(256) panel_gemm_kernel(int n, int k, int w, const double2* __restrict__ V, int ldv,
+                                                         const double2* __restrict__ Cs, double2* __restrict__ X) {
+    __shared__ double2 sV[PANEL_R][PANEL_K + 1];
+    __shared__ double2 sC[PANEL_K][PANEL_W];
+    const int tid = threadIdx.x;
+    const int r = tid / PANEL_W;  // 0..31
+    const int cw = tid % PANEL_W;
+    const int row0 = blockIdx.x * PANEL_R;
+    for (int w0 = 0; w0 < w; w0 += PANEL_W) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int k0 = 0; k0 < k; k0 += PANEL_K) {
+            __syncthreads();
+            for (int t = tid; t < PANEL_R * PANEL_K; t += 256) {
+                const int rr = t / PANEL_K, kk = t % PANEL_K;
+                double2 val = make_double2(0.0, 0.0);
+                if (row0 + rr < n && k0 + kk < k) val = V[(size_t)(row0 + rr) * ldv + k0 + kk];
+                sV[rr][kk] = val;
+            }
+            {
+                const int kk = tid / PANEL_W, ww = tid % PANEL_W;
+                double2 val = make_double2(0.0, 0.0);
+                if (k0 + kk < k && w0 + ww < w) val = Cs[(size_t)(k0 + kk) * w + w0 + ww];
+                sC[kk][ww] = val;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int kk = 0; kk < PANEL_K; ++kk) cfma(acc, sV[r][kk], sC[kk][cw]);
+        }
+        if (row0 + r < n && w0 + cw < w) X[(size_t)(row0 + r) * w + w0 + cw] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mder values: out[e] (CSC order) = sum_i c_i * vals[csr_of_csc[e]][i]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mder_kernel(int64_t nnz, int p, int ca, const int* __restrict__ csr_of_csc,
+                                                   const double* __restrict__ vals, const CoefP cp, double2* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const int vw = ca ? 2 * p : p;
+    const double* v = vals + (size_t)csr_of_csc[e] * vw;
+    double2 m = make_double2(0.0, 0.0);
+    for (int i = 0; i < p; ++i) {
+        const double2 a = ca ? make_double2(v[2 * i], v[2 * i + 1]) : make_double2(v[i], 0.0);
+        cfma(m, cp.c[i], a);
+    }
+    out[e] = m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout changes: host column-major (ld) <-> device row-major (k), complex elements
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colmajor_to_rowmajor_kernel(int64_t n, int kc, const double2* __restrict__ src, int64_t lds,
+                                                                   double2* __restrict__ dst, int ldd, int k0) {
+    __shared__ double2 tile[32][33];
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;  // 32 x 8
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int j = ty; j < 32; j += 8)
+        if (r0 + tx < n && c0 + j < kc) tile[j][tx] = src[(size_t)(c0 + j) * lds + r0 + tx];
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8)
+        if (r0 + j < n && c0 + tx < kc) dst[(size_t)(r0 + j) * ldd + k0 + c0 + tx] = tile[tx][j];
+}
+
+__global__ void __launch_bounds__(256) rowmajor_to_colmajor_kernel(int64_t n, int kc, const double2* __restrict__ src, int lds, int k0,
+                                                                   double2* __restrict__ dst, int64_t ldd) {
+    __shared__ double2 tile[32][33];
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int j = ty; j < 32; j += 8)
+        if (r0 + j < n && c0 + tx < kc) tile[j][tx] = src[(size_t)(r0 + j) * lds + k0 + c0 + tx];
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8)
+        if (r0 + tx < n && c0 + j < kc) dst[(size_t)(c0 + j) * ldd + r0 + tx] = tile[tx][j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------------------------
+struct TileCfg {
+    int gc, gn, cpt, u;
+};
+
+static bool env_cfg(TileCfg& c) {
+    const char* s = getenv("NEPB_SPMM_CFG");
+    if (!s) return false;
+    return sscanf(s, "%d,%d,%d,%d", &c.gc, &c.gn, &c.cpt, &c.u) == 4;
+}
+
+static TileCfg default_cfg(int kt) {
+    if (kt <= 1) return {1, 8, 1, 4};
+    if (kt <= 2) return {2, 4, 1, 4};
+    if (kt <= 4) return {4, 2, 1, 4};
+    if (kt <= 8) return {4, 2, 2, 4};
+    if (kt <= 16) return {4, 2, 4, 2};
+    if (kt <= 20) return {4, 2, 5, 2};
+    return {8, 1, 4, 4};
+}
+
+#define NEPB_TILE_LIST(X) \
+    X(1, 8, 1, 4) X(2, 4, 1, 4) X(4, 2, 1, 4) X(4, 2, 2, 4) X(4, 2, 4, 2) X(4, 2, 5, 2) X(8, 1, 4, 4)
+// extra shapes kept for on-device tuning of the benchmark case (p=4 real, SCALAR)
+#define NEPB_TUNE_LIST(X)                                                                              \
+    X(1, 4, 1, 6) X(1, 8, 1, 3) X(1, 16, 1, 2) X(1, 32, 1, 1) X(1, 4, 1, 8) X(8, 1, 1, 4) X(8, 2, 1, 4) \
+    X(4, 4, 2, 2) X(8, 1, 1, 8) X(4, 1, 5, 4) X(4, 4, 5, 1) X(4, 2, 5, 4) X(8, 1, 3, 4) X(8, 2, 3, 2) X(2, 4, 10, 2)
+
+template <int VW, bool CA, bool DIAG>
+static int launch_fused_vw(const nepb_spmf* h, TileCfg cfg, int kt, int ldv, int ldz, const double2* V, double2* Z,
+                           const CoefP& cp, const double2* cdiag, bool allow_tune) {
+    const int n = (int)h->n;
+#define NEPB_TRY(GC_, GN_, CPT_, U_)                                                                           \
+    if (cfg.gc == GC_ && cfg.gn == GN_ && cfg.cpt == CPT_ && cfg.u == U_) {                                     \
+        const int rows = 256 / (GC_ * GN_);                                                                     \
+        NEPB_LAUNCH((spmm_fused_kernel<VW, CA, DIAG, GC_, GN_, CPT_, U_>), (n + rows - 1) / rows, 256, 0, n, kt, \
+                    ldv, ldz, h->d_rowptr.p, h->d_colind.p, h->d_vals.p, V, Z, cp, cdiag, h->p);                \
+        return 1;                                                                                               \
+    }
+    NEPB_TILE_LIST(NEPB_TRY)
+    if constexpr (VW == 4 && !CA && !DIAG) {
+        if (allow_tune) {
+            NEPB_TUNE_LIST(NEPB_TRY)
+        }
+    }
+#undef NEPB_TRY
+    return 0;
+}
+
+// one column tile (<= 32 columns) of the SCALAR / DIAG product
+static int launch_fused(const nepb_spmf* h, bool diag, int kt, int ldv, int ldz, const double2* V, double2* Z,
+                        const CoefP& cp, const double2* cdiag) {
+    TileCfg cfg = default_cfg(kt), ecfg;
+    bool tuned = false;
+    if (env_cfg(ecfg) && ecfg.gc * ecfg.cpt >= kt) {
+        cfg = ecfg;
+        tuned = true;
+    }
+    const int vw = h->vw;
+    const bool ca = h->is_complex;
+    int done = 0;
+#define NEPB_VW_CASE(VW_, CA_)                                                                              \
+    if (!done && vw == VW_ && ca == CA_) {                                                                   \
+        done = diag ? launch_fused_vw<VW_, CA_, true>(h, cfg, kt, ldv, ldz, V, Z, cp, cdiag, tuned)          \
+                    : launch_fused_vw<VW_, CA_, false>(h, cfg, kt, ldv, ldz, V, Z, cp, cdiag, tuned);        \
+        if (!done && tuned) {                                                                                \
+            cfg = default_cfg(kt);                                                                           \
+            done = diag ? launch_fused_vw<VW_, CA_, true>(h, cfg, kt, ldv, ldz, V, Z, cp, cdiag, false)      \
+                        : launch_fused_vw<VW_, CA_, false>(h, cfg, kt, ldv, ldz, V, Z, cp, cdiag, false);    \
+        }                                                                                                    \
+    }
+    NEPB_VW_CASE(2, false)
+    NEPB_VW_CASE(3, false)
+    NEPB_VW_CASE(4, false)
+    NEPB_VW_CASE(4, true)
+    NEPB_VW_CASE(8, true)
+#undef NEPB_VW_CASE
+    if (!done) {
+        const int n = (int)h->n;
+        if (diag)
+            NEPB_LAUNCH((spmm_fused_generic_kernel<true>), (n + 31) / 32, 256, 0, n, kt, ldv, ldz, h->d_rowptr.p,
+                        h->d_colind.p, h->d_vals.p, V, Z, cp, cdiag, h->p, h->is_complex);
+        else
+            NEPB_LAUNCH((spmm_fused_generic_kernel<false>), (n + 31) / 32, 256, 0, n, kt, ldv, ldz, h->d_rowptr.p,
+                        h->d_colind.p, h->d_vals.p, V, Z, cp, cdiag, h->p, h->is_complex);
+    }
+    NEPB_LAUNCH_CHECK();
+    return NEPB_OK;
+}
+
+static int launch_stacked(const nepb_spmf* h, int q, const double2* X, double2* Z, int ldz) {
+    const int n = (int)h->n;
+    const int vw = h->vw;
+    const bool ca = h->is_complex;
+    bool done = false;
+#define NEPB_ST_CASE(VW_, CA_)                                                                                      \
+    if (!done && vw == VW_ && ca == CA_) {                                                                           \
+        if (q == 1)                                                                                                  \
+            NEPB_LAUNCH((spmm_stacked_kernel<VW_, CA_, 1, 8, 4>), (n + 31) / 32, 256, 0, n, q, h->d_rowptr.p,         \
+                        h->d_colind.p, h->d_vals.p, X, Z, ldz);                                                      \
+        else                                                                                                         \
+            NEPB_LAUNCH((spmm_stacked_kernel<VW_, CA_, 4, 2, 4>), (n + 31) / 32, 256, 0, n, q, h->d_rowptr.p,         \
+                        h->d_colind.p, h->d_vals.p, X, Z, ldz);                                                      \
+        done = true;                                                                                                 \
+    }
+    NEPB_ST_CASE(2, false)
+    NEPB_ST_CASE(3, false)
+    NEPB_ST_CASE(4, false)
+    NEPB_ST_CASE(4, true)
+    NEPB_ST_CASE(8, true)
+#undef NEPB_ST_CASE
+    if (!done)
+        NEPB_LAUNCH(spmm_stacked_generic_kernel, (n + 31) / 32, 256, 0, n, q, h->p, h->is_complex, h->d_rowptr.p,
+                    h->d_colind.p, h->d_vals.p, X, Z, ldz);
+    NEPB_LAUNCH_CHECK();
+    return NEPB_OK;
+}
+
+// Z = sum_i A_i (V C_i) with device row-major operands (dV: n x k, ld k ; dZ: n x q, ld q)
+int spmf_apply_device(const nepb_spmf* h, int mode, int k, int q, const double2* dV, const double* C, double2* dZ) {
+    NEPB_CHECK_ARG(h && dV && dZ && C, "NULL argument");
+    NEPB_CHECK_ARG(k >= 1 && q >= 1, "k and q must be positive (k=%d q=%d)", k, q);
+    const int p = h->p;
+    if (mode == NEPB_COEF_SCALAR || mode == NEPB_COEF_DIAG) {
+        NEPB_CHECK_ARG(q == k, "SCALAR/DIAG coefficient modes need q == k (k=%d q=%d)", k, q);
+        NEPB_CHECK_ARG(p <= MAXP, "p=%d exceeds the %d terms supported by the fused kernel", p, MAXP);
+        CoefP cp;
+        memset(&cp, 0, sizeof(cp));
+        const double2* cdiag = nullptr;
+        if (mode == NEPB_COEF_SCALAR) {
+            for (int i = 0; i < p; ++i) cp.c[i] = make_double2(C[2 * i], C[2 * i + 1]);
+        } else {
+            NEPB_CUDA(h->d_coef.reserve((size_t)2 * p * k));
+            NEPB_CUDA(cudaMemcpyAsync(h->d_coef.p, C, sizeof(double) * 2 * p * k, cudaMemcpyHostToDevice, stream()));
+            cdiag = (const double2*)h->d_coef.p;
+        }
+        for (int k0 = 0; k0 < k; k0 += 32) {
+            const int kt = std::min(32, k - k0);
+            int rc = launch_fused(h, mode == NEPB_COEF_DIAG, kt, k, k, dV + k0, dZ + k0, cp, cdiag ? cdiag + (size_t)p * k0 : nullptr);
+            if (rc) return rc;
+        }
+        return NEPB_OK;
+    }
+    NEPB_CHECK_ARG(mode == NEPB_COEF_GENERAL, "unknown coefficient mode %d", mode);
+    // stage 1: Cs[kk][c*p + i] = C_i[kk, c]  (host re-pack, k*q*p complex), X = V * Cs
+    const int w = p * q;
+    std::vector<double> cs((size_t)2 * k * w);
+    for (int i = 0; i < p; ++i)
+        for (int c = 0; c < q; ++c)
+            for (int kk = 0; kk < k; ++kk) {
+                const double* s = C + 2 * ((size_t)i * k * q + (size_t)c * k + kk);
+                double* d = cs.data() + 2 * ((size_t)kk * w + (size_t)c * p + i);
+                d[0] = s[0];
+                d[1] = s[1];
+            }
+    NEPB_CUDA(h->d_coef.reserve(cs.size()));
+    NEPB_CUDA(cudaMemcpyAsync(h->d_coef.p, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice, stream()));
+    NEPB_CUDA(cudaStreamSynchronize(stream()));  // cs is a local buffer
+    NEPB_CUDA(h->d_tmp_x.reserve((size_t)2 * h->n * w));
+    NEPB_LAUNCH(panel_gemm_kernel, (int)((h->n + PANEL_R - 1) / PANEL_R), 256, 0, (int)h->n, k, w, dV, k,
+                (const double2*)h->d_coef.p, (double2*)h->d_tmp_x.p);
+    NEPB_LAUNCH_CHECK();
+    return launch_stacked(h, q, (const double2*)h->d_tmp_x.p, dZ, q);
+}
+
+int upload_colmajor(int64_t n, int kc, const double* host, int64_t ld, DevBuf<double>& stage, double* dst, int ldd, int k0) {
+    // host column-major -> staging (column-major, ld = n) -> row-major
+    NEPB_CUDA(stage.reserve((size_t)2 * n * kc));
+    NEPB_CUDA(cudaMemcpy2DAsync(stage.p, (size_t)n * 16, host, (size_t)ld * 16, (size_t)n * 16, kc, cudaMemcpyHostToDevice, stream()));
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((kc + 31) / 32));
+    NEPB_LAUNCH(colmajor_to_rowmajor_kernel, grid, 256, 0, n, kc, (const double2*)stage.p, n, (double2*)dst, ldd, k0);
+    NEPB_LAUNCH_CHECK();
+    return NEPB_OK;
+}
+
+int download_colmajor(int64_t n, int kc, const double* src, int lds, int k0, DevBuf<double>& stage, double* host, int64_t ld) {
+    NEPB_CUDA(stage.reserve((size_t)2 * n * kc));
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((kc + 31) / 32));
+    NEPB_LAUNCH(rowmajor_to_colmajor_kernel, grid, 256, 0, n, kc, (const double2*)src, lds, k0, (double2*)stage.p, n);
+    NEPB_LAUNCH_CHECK();
+    NEPB_CUDA(cudaMemcpy2DAsync(host, (size_t)ld * 16, stage.p, (size_t)n * 16, (size_t)n * 16, kc, cudaMemcpyDeviceToHost, stream()));
+    NEPB_CUDA(cudaStreamSynchronize(stream()));
+    return NEPB_OK;
+}
+
+}  // namespace nepb
+
+nepb_spmf::~nepb_spmf() {
+    free(h_colptr);
+    free(h_rowval);
+    free(h_rowptr);
+    free(h_colind);
+    free(h_csr_of_csc);
+}
+
+using namespace nepb;
+
+namespace nepb {
+void lu_symbolic_release(void* p);
+}
+
+extern "C" {
+
+int nepb_spmf_create(int64_t n, int p, const int64_t* const* colptr, const int64_t* const* rowval,
+                     const void* const* nzval, int val_is_complex, int index_base, nepb_spmf** out) {
+    NEPB_CHECK_ARG(out, "out is NULL");
+    *out = nullptr;
+    NEPB_CHECK_ARG(n >= 1, "n must be positive (n=%lld)", (long long)n);
+    NEPB_CHECK_ARG(p >= 1, "an SPMF needs at least one term (p=%d)", p);
+    NEPB_CHECK_ARG(index_base == 0 || index_base == 1, "index_base must be 0 or 1");
+    NEPB_CHECK_ARG(colptr && rowval && nzval, "NULL array of arrays");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: libnepb200 has no CPU fallback");
+        return NEPB_E_CUDA;
+    }
+    UnionCSR u;
+    int rc = build_union_csr(n, p, colptr, rowval, nzval, val_is_complex, index_base, u);
+    if (rc) return rc;
+    nepb_spmf* h = new nepb_spmf();
+    h->n = n;
+    h->p = p;
+    h->nnz = u.nnz;
+    h->is_complex = val_is_complex ? 1 : 0;
+    h->index_base = index_base;
+    h->vw = u.vw;
+    auto dup = [](const void* src, size_t bytes) {
+        void* d = malloc(bytes ? bytes : 1);
+        if (d && bytes) memcpy(d, src, bytes);
+        return d;
+    };
+    h->h_colptr = (int64_t*)dup(u.colptr.data(), sizeof(int64_t) * (n + 1));
+    h->h_rowval = (int32_t*)dup(u.rowval.data(), sizeof(int32_t) * u.nnz);
+    h->h_rowptr = (int32_t*)dup(u.rowptr.data(), sizeof(int32_t) * (n + 1));
+    h->h_colind = (int32_t*)dup(u.colind.data(), sizeof(int32_t) * u.nnz);
+    h->h_csr_of_csc = (int32_t*)dup(u.csr_of_csc.data(), sizeof(int32_t) * u.nnz);
+#define NEPB_UP(buf, src, count, T)                                                                       \
+    do {                                                                                                  \
+        cudaError_t e_ = buf.alloc(count);                                                                \
+        if (e_ == cudaSuccess) e_ = cudaMemcpy(buf.p, src, sizeof(T) * (count), cudaMemcpyHostToDevice);  \
+        if (e_ != cudaSuccess) {                                                                          \
+            set_error("CUDA error while uploading the operator: %s", cudaGetErrorString(e_));             \
+            delete h;                                                                                     \
+            return e_ == cudaErrorMemoryAllocation ? NEPB_E_NOMEM : NEPB_E_CUDA;                          \
+        }                                                                                                 \
+    } while (0)
+    NEPB_UP(h->d_rowptr, u.rowptr.data(), (size_t)n + 1, int32_t);
+    NEPB_UP(h->d_colind, u.colind.data(), (size_t)u.nnz, int32_t);
+    NEPB_UP(h->d_csr_of_csc, u.csr_of_csc.data(), (size_t)u.nnz, int32_t);
+    NEPB_UP(h->d_vals, u.vals.data(), (size_t)u.nnz * u.vw, double);
+#undef NEPB_UP
+    *out = h;
+    return NEPB_OK;
+}
+
+int nepb_spmf_destroy(nepb_spmf* h) {
+    if (h) {
+        if (h->lu_symbolic) lu_symbolic_release(h->lu_symbolic);
+        delete h;
+    }
+    return NEPB_OK;
+}
+
+int nepb_spmf_info(const nepb_spmf* h, int64_t* n, int* p, int64_t* nnz_union, int* val_is_complex) {
+    NEPB_CHECK_ARG(h, "handle is NULL");
+    if (n) *n = h->n;
+    if (p) *p = h->p;
+    if (nnz_union) *nnz_union = h->nnz;
+    if (val_is_complex) *val_is_complex = h->is_complex;
+    return NEPB_OK;
+}
+
+int nepb_spmf_pattern(const nepb_spmf* h, int64_t* colptr, int64_t* rowval) {
+    NEPB_CHECK_ARG(h && colptr && rowval, "NULL argument");
+    for (int64_t j = 0; j <= h->n; ++j) colptr[j] = h->h_colptr[j] + h->index_base;
+    for (int64_t e = 0; e < h->nnz; ++e) rowval[e] = (int64_t)h->h_rowval[e] + h->index_base;
+    return NEPB_OK;
+}
+
+int nepb_spmf_pattern_csr(const nepb_spmf* h, int32_t* rowptr, int32_t* colind, int32_t* csr_of_csc) {
+    NEPB_CHECK_ARG(h, "handle is NULL");
+    if (rowptr) memcpy(rowptr, h->h_rowptr, sizeof(int32_t) * (h->n + 1));
+    if (colind) memcpy(colind, h->h_colind, sizeof(int32_t) * h->nnz);
+    if (csr_of_csc) memcpy(csr_of_csc, h->h_csr_of_csc, sizeof(int32_t) * h->nnz);
+    return NEPB_OK;
+}
+
+int nepb_spmf_mder(const nepb_spmf* h, const double* coef, double* nzval_out) {
+    NEPB_CHECK_ARG(h && coef && nzval_out, "NULL argument");
+    NEPB_CHECK_ARG(h->p <= MAXP, "p=%d exceeds %d", h->p, MAXP);
+    CoefP cp;
+    memset(&cp, 0, sizeof(cp));
+    for (int i = 0; i < h->p; ++i) cp.c[i] = make_double2(coef[2 * i], coef[2 * i + 1]);
+    NEPB_CUDA(h->d_tmp_out.reserve((size_t)2 * h->nnz));
+    NEPB_LAUNCH(mder_kernel, (unsigned)((h->nnz + 255) / 256), 256, 0, h->nnz, h->p, h->is_complex, h->d_csr_of_csc.p,
+                h->d_vals.p, cp, (double2*)h->d_tmp_out.p);
+    NEPB_LAUNCH_CHECK();
+    NEPB_CUDA(cudaMemcpyAsync(nzval_out, h->d_tmp_out.p, sizeof(double) * 2 * h->nnz, cudaMemcpyDeviceToHost, stream()));
+    NEPB_CUDA(cudaStreamSynchronize(stream()));
+    return NEPB_OK;
+}
+
+int nepb_spmf_apply(const nepb_spmf* h, int mode, int k, int q, const double* V, int64_t ldv, const double* C,
+                    double* Z, int64_t ldz) {
+    NEPB_CHECK_ARG(h && V && C && Z, "NULL argument");
+    NEPB_CHECK_ARG(k >= 1 && q >= 1, "k and q must be positive");
+    NEPB_CHECK_ARG(ldv >= h->n && ldz >= h->n, "leading dimension smaller than n");
+    const int64_t n = h->n;
+    NEPB_CUDA(h->d_tmp_in.reserve((size_t)2 * n * k));
+    NEPB_CUDA(h->d_tmp_out.reserve((size_t)2 * n * q));
+    int rc = upload_colmajor(n, k, V, ldv, h->d_stage, h->d_tmp_in.p, k, 0);
+    if (rc) return rc;
+    rc = spmf_apply_device(h, mode, k, q, (const double2*)h->d_tmp_in.p, C, (double2*)h->d_tmp_out.p);
+    if (rc) return rc;
+    return download_colmajor(n, q, h->d_tmp_out.p, q, 0, h->d_stage, Z, ldz);
+}
+
+int nepb_block_create(int64_t n, int k, nepb_block** out) {
+    NEPB_CHECK_ARG(out && n >= 1 && k >= 1, "bad arguments");
+    nepb_block* b = new nepb_block();
+    b->n = n;
+    b->k = k;
+    cudaError_t e = b->d.alloc((size_t)2 * n * k);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d.p, 0, sizeof(double) * 2 * n * k, stream());
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc of a %lld x %d block failed: %s", (long long)n, k, cudaGetErrorString(e));
+        delete b;
+        return e == cudaErrorMemoryAllocation ? NEPB_E_NOMEM : NEPB_E_CUDA;
+    }
+    *out = b;
+    return NEPB_OK;
+}
+
+int nepb_block_destroy(nepb_block* b) {
+    delete b;
+    return NEPB_OK;
+}
+
+static DevBuf<double> g_block_stage;
+
+int nepb_block_upload(nepb_block* b, int k0, int kc, const double* host, int64_t ld) {
+    NEPB_CHECK_ARG(b && host && k0 >= 0 && kc >= 1 && k0 + kc <= b->k && ld >= b->n, "bad arguments");
+    return upload_colmajor(b->n, kc, host, ld, g_block_stage, b->d.p, b->k, k0);
+}
+
+int nepb_block_download(const nepb_block* b, int k0, int kc, double* host, int64_t ld) {
+    NEPB_CHECK_ARG(b && host && k0 >= 0 && kc >= 1 && k0 + kc <= b->k && ld >= b->n, "bad arguments");
+    return download_colmajor(b->n, kc, b->d.p, b->k, k0, g_block_stage, host, ld);
+}
+
+void* nepb_block_dev_ptr(nepb_block* b) { return b ? (void*)b->d.p : nullptr; }
+
+int nepb_spmf_apply_block(const nepb_spmf* h, int mode, const nepb_block* V, int q, const double* C, nepb_block* Z) {
+    NEPB_CHECK_ARG(h && V && Z && C, "NULL argument");
+    NEPB_CHECK_ARG(V->n == h->n && Z->n == h->n, "block row count differs from the operator size");
+    NEPB_CHECK_ARG(Z->k == q, "Z has %d columns, expected q=%d", Z->k, q);
+    NEPB_CHECK_ARG(V->d.p != Z->d.p, "V and Z must not alias");
+    return spmf_apply_device(h, mode, V->k, q, (const double2*)V->d.p, C, (double2*)Z->d.p);
+}
+
+int64_t nepb_spmf_apply_bytes(const nepb_spmf* h, int mode, int k, int q) {
+    if (!h) return 0;
+    const int64_t sA = h->is_complex ? 16 : 8;
+    int64_t b = h->nnz * ((int64_t)h->p * sA + 4) + 4 * (h->n + 1) + h->n * (int64_t)k * 16 + h->n * (int64_t)q * 16;
+    // GENERAL is two-stage: X = V*[C_1..C_p] (n x p*q) is written once and gathered once
+    if (mode == NEPB_COEF_GENERAL) b += 2 * h->n * (int64_t)q * h->p * 16;
+    return b;
+}
+
+}  // extern "C"
