@@ -1,0 +1,14 @@
+"""nepb200: B200-native (sm_100a) hot path for NEP-PACK style nonlinear eigensolvers.
+
+The product is libnepb200.so (csrc/, C ABI in include/nepb200.h) plus the Julia shim in julia/.
+This Python package is the in-container mirror of that shim: the same plugin interface
+(NEP compute contract, LinSolver / LinSolverCreator, contour integrator, orthogonalisation) bound
+with ctypes, so the parity tests read like the reference's own tests.  Importing it requires the
+built library; there is no CPU fallback.
+
+The directory name contains a dot, so it is imported under the alias `nepb200` (see /nepb200.py).
+"""
+from . import _lib  # noqa: F401  (raises ImportError when libnepb200.so is missing)
+from ._lib import NepbError, SingularException, device_count, LIB_PATH  # noqa: F401
+from .functions import ScalarFunction, Monomial, Exp, PowShift, Callable, ONE, IDENTITY  # noqa: F401
+from .neptypes import SPMF_NEP, PEP, DEP, SumNEP, B200SPMF, Block  # noqa: F401

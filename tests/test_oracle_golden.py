@@ -1,0 +1,99 @@
+"""The oracle pinned against the reference's own literal known answers.  CPU only."""
+import numpy as np
+import scipy.sparse as sp
+
+from oracle import gallery as g
+from oracle import nep as o
+
+
+def test_msws_dep0_mder_literal():
+    # src/NEPTypes.jl:74-75: compute_Mder(nep_gallery("dep0"), 3.0)[1,1] == -2.942777908030041
+    nep = o.nep_gallery("dep0")
+    assert o.compute_Mder(nep, 3.0)[0, 0].real == -2.942777908030041
+
+
+def test_dep0_100_mlincomb_norm_literal():
+    # src/Gallery.jl:174-176
+    nep = o.nep_gallery("dep0", 100)
+    z = o.compute_Mlincomb(nep, 1.0 + 1.0j, np.ones(100))
+    assert abs(np.linalg.norm(z) - 57.498446538064954) < 1e-13
+
+
+def test_dep0_eigenvalue_literal():
+    # docs/src/methods.md:18-19
+    nep = o.nep_gallery("dep0")
+    M = o.compute_Mder(nep, -0.15955391823299256)
+    assert np.linalg.svd(M, compute_uv=False)[-1] < 1e-14
+
+
+def test_gun_one_norms_literal():
+    # test/rk_helper/gun_test_utils.jl:50-53
+    K, M, W1, W2 = g.load_gun_matrices()
+    lit = [1.474544889815002e+05, 2.726114618171165e-02, 2.328612251920476e+00, 3.793375498194695e+00]
+    for A, ref in zip((K, M, W1, W2), lit):
+        assert abs(abs(A).sum(axis=0).max() - ref) <= 1e-15 * ref * 4
+    assert K.shape == (9956, 9956)
+    assert (K.nnz, M.nnz, W1.nnz, W2.nnz) == (148308, 148318, 57, 293)
+
+
+def test_gun_reference_eigenvalue_literal():
+    # test/gun_native.jl:9 -- M(lambda_ref) is numerically singular
+    import scipy.sparse.linalg as sla
+    nep = o.nep_gallery("nlevp_native_gun")
+    lam = 22345.116783765 + 0.644998598j
+    M = sp.csc_matrix(o.compute_Mder(nep, lam))
+    lu = sla.splu(M)
+    # inverse iteration: ||M x|| / ||x|| after two steps ~ smallest singular value
+    x = np.ones(nep.n, dtype=complex)
+    for _ in range(3):
+        x = lu.solve(x)
+        x /= np.linalg.norm(x)
+    assert np.linalg.norm(M @ x) / abs(M).sum(axis=0).max() < 1e-13
+
+
+def test_spmf_identities():
+    # test/spmf.jl:37-63: compute_MM vs the closed form, and Mlincomb == from_MM == from_Mder
+    rng = np.random.default_rng(0)
+    n = 6
+    A = [sp.random(n, n, 0.5, random_state=i, format="csc") for i in range(3)]
+    nep = o.SPMF_NEP(A, [o.f_one, o.f_id, o.f_exp(-0.3)])
+    S = rng.standard_normal((3, 3))
+    V = rng.standard_normal((n, 3))
+    import scipy.linalg as L
+    Z = A[0] @ V + A[1] @ V @ S + A[2] @ V @ L.expm(-0.3 * S)
+    assert np.linalg.norm(o.compute_MM(nep, S, V) - Z) < 1e-12
+    a = np.array([1.0, 2.0, 0.5])
+    lam = 0.3 + 0.1j
+    z1 = o.compute_Mlincomb(nep, lam, V, a)
+    z2 = o.compute_Mlincomb_from_MM(nep, lam, V, a)
+    z3 = o.compute_Mlincomb_from_Mder(nep, lam, V, a)
+    assert np.linalg.norm(z1 - z2) < 1e-12 and np.linalg.norm(z1 - z3) < 1e-12
+
+
+def test_pep_dep_equal_spmf():
+    # test/spmf.jl:158-178, :266-283
+    rng = np.random.default_rng(1)
+    n = 5
+    A = [rng.standard_normal((n, n)) for _ in range(3)]
+    pep = o.PEP(A)
+    spmf = o.SPMF_NEP(o.get_Av(pep), o.get_fv(pep))
+    V = rng.standard_normal((n, 4))
+    a = np.array([1.0, 0.0, 3.0, 0.1])
+    lam = -0.4 + 0.2j
+    assert np.linalg.norm(o.compute_Mlincomb(pep, lam, V, a) - o.compute_Mlincomb(spmf, lam, V, a)) < 1e-12
+    dep = o.nep_gallery("dep0")
+    spmf = o.SPMF_NEP(o.get_Av(dep), o.get_fv(dep))
+    V = rng.standard_normal((5, 4))
+    assert np.linalg.norm(o.compute_Mlincomb(dep, lam, V, a) - o.compute_Mlincomb(spmf, lam, V, a)) < 1e-12
+    assert np.linalg.norm(o.compute_Mder(dep, lam, 2) - o.compute_Mder(spmf, lam, 2)) < 1e-12
+
+
+def test_startder_semantics():
+    # test/core.jl:16-32
+    dep = o.nep_gallery("dep0")
+    rng = np.random.default_rng(2)
+    V = rng.standard_normal((5, 3))
+    lam = 0.7
+    z = o.compute_Mlincomb(dep, lam, V, np.ones(3), startder=1)
+    ref = sum(o.compute_Mder(dep, lam, j + 1) @ V[:, j] for j in range(3))
+    assert np.linalg.norm(z - ref) < 1e-12
