@@ -1,20 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- the measurement contract of the nepb200 hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload auto|spmm|contour]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for how every field is produced.
-Workloads (BASELINE.json):
-  contour : config C3 -- gun SPMF, contour_beyn moment integration, N=128 quadrature points, k=20 probe columns,
-            points sharded over the ranks, one NCCL reduce of the moment block (strong scaling).
-  spmm    : config C4 -- synthetic degree-3 PEP, n=10^6, 21-point stencil, fused multi-term SpMM M(lam)V for
-            k in {1,8,20}; this is where `roofline` (HBM) comes from.
-A step is one pass of the hot path over one batch: one full 128-point contour integration (contour) or one
-fused SpMM launch per k (spmm).
+One JSON line on stdout (rank 0).  DESIGN.md "Measurement" explains every field.
+
+Headline (BASELINE.json config C3): contour_beyn on the gun SPMF, N=128 quadrature nodes, k=20 probe columns.
+A step = one full moment integration S_j = sum_i w_ij M(lambda_i)^-1 Vh (128 batched factorisations + 128 x 20 solves
++ accumulate), nodes sharded round-robin over the ranks, one NCCL all-reduce of the moment block.  `value` is
+quadrature-point solves per second of the whole job (strong scaling: the 128 nodes are split over the ranks).
+
+Roofline (BASELINE.json config C4): the fused multi-term SPMF SpMM M(lam)V on the synthetic degree-3 PEP, n=10^6,
+nnz_u=20 956 020, measured live in the same run (k=1 headline, k=8 and k=20 beside it) against the measured HBM peak.
+
+--impl reference times the CPU restatement of the reference's own path (oracle/, SciPy SuperLU standing in for UMFPACK;
+Julia is not installed in this image) on the host cores, one process per core over the quadrature nodes -- the
+reference's documented `@distributed (+)` scheme (docs/src/tutorial_contour.md:205-231).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -26,6 +32,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
+
+GUN_SIGMA = 150.0 ** 2
+GUN_RADIUS = 500.0
+GUN_N = 128
+GUN_K = 20
 
 
 def log(*a):
@@ -56,9 +67,12 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -69,7 +83,9 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -90,12 +106,12 @@ class ClockSampler:
 # distributed plumbing (torch.distributed only for rendezvous / barrier / max-over-ranks)
 # ------------------------------------------------------------------------------------------------
 class Dist:
-    def __init__(self):
+    def __init__(self, use_cuda=True):
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         self.td = None
-        if self.world > 1:
+        if self.world > 1 and use_cuda:
             import torch
             import torch.distributed as td
             torch.cuda.set_device(self.local_rank)
@@ -120,6 +136,15 @@ class Dist:
         self.td.all_reduce(t, op=self.td.ReduceOp.SUM)
         return float(t.item())
 
+    def bcast_bytes(self, b: bytes, n: int) -> bytes:
+        if not self.td:
+            return b
+        t = self.torch.zeros(n, dtype=self.torch.uint8, device="cuda")
+        if self.rank == 0:
+            t.copy_(self.torch.frombuffer(bytearray(b), dtype=self.torch.uint8))
+        self.td.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+
     def close(self):
         if self.td:
             self.td.destroy_process_group()
@@ -134,8 +159,38 @@ def load_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# workload: fused SPMF SpMM on config C4
+# problem set-up
 # ------------------------------------------------------------------------------------------------
+def load_gun_csc():
+    import scipy.sparse as sp
+    z = np.load(os.path.join(ROOT, "tests", "golden", "gun.npz"))
+    n = int(z["n"])
+    return [sp.csc_matrix((z[k + "_data"], z[k + "_indices"], z[k + "_indptr"]), shape=(n, n)) for k in ("K", "M", "W1", "W2")]
+
+
+def gun_operator():
+    import nepb200
+    from nepb200 import ONE, IDENTITY, PowShift
+    K, M, W1, W2 = load_gun_csc()
+    return nepb200.B200SPMF([K, -M, W1, W2], [ONE, IDENTITY, PowShift(0.5, 0.0, 1j), PowShift(0.5, 108.8774 ** 2, 1j)])
+
+
+def gun_probe(n, k):
+    """MSWS 1-2u probe matrix, column-major draw (reproducible in Julia, Python and C)."""
+    from nepb200 import _lib
+    st = _lib.msws_state(0)
+    return np.asfortranarray((1 - 2 * _lib.msws_fill(st, n * k)).reshape(n, k, order="F")).astype(np.complex128)
+
+
+def beyn_nodes(N, sigma, radius):
+    h = 2 * np.pi / N
+    t = h * np.arange(N)
+    g = radius * (np.cos(t) + 1j * np.sin(t))
+    gp = radius * (-np.sin(t) + 1j * np.cos(t))
+    W = np.stack([gp * h / (2j * np.pi), gp * g * h / (2j * np.pi)], axis=1)
+    return g + sigma, W
+
+
 def build_c4(grid):
     import nepb200
     from nepb200 import synthetic, Monomial
@@ -149,16 +204,15 @@ def build_c4(grid):
     return dnep, mats, st
 
 
-def bench_spmm(args, dist, ks=(1, 8, 20)):
-    import nepb200
+# ------------------------------------------------------------------------------------------------
+# workload: fused SPMF SpMM on config C4 (roofline)
+# ------------------------------------------------------------------------------------------------
+def bench_spmm(args, ks=(1, 8, 20)):
     from nepb200 import synthetic, Block, _lib
     lib = _lib.lib
-    import ctypes as C
-    grid = args.grid
-    dnep, mats, st = build_c4(grid)
+    dnep, mats, st = build_c4(args.grid)
     n = dnep.n
-    lam = 0.3 + 0.2j
-    coef = dnep.coefficients(lam)
+    coef = dnep.coefficients(0.3 + 0.2j)
     peak, peak_src = load_peaks()
     out = {}
     for k in ks:
@@ -167,102 +221,309 @@ def bench_spmm(args, dist, ks=(1, 8, 20)):
         for _ in range(max(args.warmup, 3)):
             dnep.apply_block(_lib.COEF_SCALAR, Vb, coef, Zb)
         lib.nepb_synchronize()
-        dist.barrier()
         l0 = lib.nepb_launch_count()
         ms = C.c_float()
+        reps = max(args.steps, 20)
         lib.nepb_timer_start()
-        for _ in range(args.steps):
+        for _ in range(reps):
             dnep.apply_block(_lib.COEF_SCALAR, Vb, coef, Zb)
         lib.nepb_timer_stop(C.byref(ms))
-        dist.barrier()
         launches = lib.nepb_launch_count() - l0
-        t = dist.max(ms.value / args.steps)  # ms per launch, max over ranks
+        t = ms.value / reps
         nbytes = dnep.apply_bytes(_lib.COEF_SCALAR, k, k)
-        # e2e: host buffers through nepb_spmf_apply (H2D of V, D2H of Z inside the timed region)
         Z = dnep.apply(_lib.COEF_SCALAR, V, coef, k)
         t0 = time.perf_counter()
-        reps = max(3, min(args.steps, 10))
-        for _ in range(reps):
+        for _ in range(3):
             Z = dnep.apply(_lib.COEF_SCALAR, V, coef, k)
-        te = dist.max((time.perf_counter() - t0) / reps * 1e3)
+        te = (time.perf_counter() - t0) / 3 * 1e3
         out[k] = {"k": k, "ms": t, "gbs": nbytes / t / 1e6, "bytes": int(nbytes), "frac": nbytes / t / 1e6 / peak,
-                  "launches": int(launches), "e2e_ms": te, "e2e_gbs": nbytes / te / 1e6,
-                  "h2d": int(n * k * 16), "d2h": int(n * k * 16), "checksum": float(np.abs(Z).sum())}
-        log("[bench] spmm k=%d: %.1f us/launch, %.0f GB/s (%.1f%% of %s); e2e %.2f ms" %
+                  "launches": int(launches), "e2e_ms": te, "e2e_gbs": nbytes / te / 1e6, "checksum": float(np.abs(Z).sum())}
+        log("[bench] spmm k=%d: %.1f us/launch, %.0f GB/s (%.1f%% of %s); host-buffer call %.2f ms" %
             (k, t * 1e3, out[k]["gbs"], 100 * out[k]["frac"], peak_src, te))
         Vb.close()
         Zb.close()
-    return dnep, mats, out, peak, peak_src
+    cpu = None
+    if not args.no_cpu_baseline:
+        # CPU port of compute_MM with S = lam*I (NEPTypes.jl:299-311: p separate SpMMs), SciPy CSR, one core
+        lam = 0.3 + 0.2j
+        V = np.ones((n, 1), dtype=complex)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 3.0 or reps < 1:
+            Z = sum(A @ (V * lam ** i) for i, A in enumerate(mats))
+            reps += 1
+        tc = (time.perf_counter() - t0) / reps
+        cpu = {"value": out[1]["bytes"] / tc / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+               "sample": "%d full C4 SpMM passes (k=1), SciPy CSR, p separate products, %.3f s each" % (reps, tc)}
+    dnep.close()
+    return out, peak, peak_src, cpu
 
 
-def cpu_spmm_baseline(mats, k, budget_s=10.0):
-    """CPU port: sum_i c_i A_i V with SciPy CSR (one core), the reference's algorithm for compute_MM with S = lam*I
-    (NEPTypes.jl:299-311: p separate SpMMs).  Bounded sample: as many full passes as fit in the budget (>= 1)."""
-    lam = 0.3 + 0.2j
-    n = mats[0].shape[0]
-    rng = np.random.default_rng(0)
-    V = rng.standard_normal((n, k)) + 1j * rng.standard_normal((n, k))
-    t0 = time.perf_counter()
-    reps = 0
-    while True:
-        Z = np.zeros((n, k), dtype=complex)
-        for i, A in enumerate(mats):
-            Z += A @ (V * lam ** i)
-        reps += 1
-        if time.perf_counter() - t0 > budget_s or reps >= 20:
+# ------------------------------------------------------------------------------------------------
+# CPU arm: oracle contour loop, one process per core over the nodes
+# ------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker_init():
+    from oracle import nep as o
+    _W["nep"] = o.nep_gallery("nlevp_native_gun")
+    n = _W["nep"].n
+    from oracle import gallery as g
+    rng = g.MSWS_RNG(0)
+    u = np.array([g.gen_rng_float(rng) for _ in range(n * GUN_K)])
+    _W["Vh"] = np.asfortranarray((1 - 2 * u).reshape(n, GUN_K, order="F")).astype(np.complex128)
+
+
+def _cpu_worker_nodes(arg):
+    """One worker's share of the trapezoid sum: factor + 20-column solve + accumulate per node (oracle/solvers.py)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as sla
+    from oracle import nep as o
+    lams, W = arg
+    nep, Vh = _W["nep"], _W["Vh"]
+    S = np.zeros(Vh.shape + (2,), dtype=np.complex128)
+    for lam, w in zip(lams, W):
+        M = sp.csc_matrix(o.compute_Mder(nep, lam), dtype=np.complex128)
+        X = sla.splu(M, permc_spec="MMD_AT_PLUS_A").solve(Vh)
+        S[:, :, 0] += X * w[0]
+        S[:, :, 1] += X * w[1]
+    return S
+
+
+def cpu_worker_main():
+    """Child process of CpuContour: `bench.py --cpu-worker`.  Protocol on stdin/stdout: prints "ready", then for every
+    line "<first> <count> <stride>" computes its nodes and answers "done <seconds> <checksum>"."""
+    _cpu_worker_init()
+    lams, W = beyn_nodes(GUN_N, GUN_SIGMA, GUN_RADIUS)
+    print("ready", flush=True)
+    for ln in sys.stdin:
+        f = ln.split()
+        if not f or f[0] == "quit":
             break
-    return (time.perf_counter() - t0) / reps
+        first, count, stride = int(f[0]), int(f[1]), int(f[2])
+        idx = (first + stride * np.arange(count)) % GUN_N
+        t0 = time.perf_counter()
+        S = _cpu_worker_nodes((lams[idx], W[idx]))
+        print("done %.6f %.17g" % (time.perf_counter() - t0, float(np.abs(S).sum())), flush=True)
 
 
+class CpuContour:
+    """One single-threaded worker process per host core over the quadrature nodes -- the reference's `julia -p <cores>`
+    + `@distributed (+)` scheme (docs/src/tutorial_contour.md:205-231).  Start-up (imports, matrix load) is not timed."""
+
+    def __init__(self, cores):
+        self.cores = cores
+        env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            env.pop(k, None)
+        self.procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker"], stdin=subprocess.PIPE,
+                                       stdout=subprocess.PIPE, text=True, env=env, cwd=ROOT) for _ in range(cores)]
+        for p in self.procs:
+            ln = p.stdout.readline()
+            if ln.strip() != "ready":
+                raise RuntimeError("CPU worker failed to start: %r" % ln)
+
+    def run(self, nodes_per_core):
+        t0 = time.perf_counter()
+        for c, p in enumerate(self.procs):
+            p.stdin.write("%d %d %d\n" % (c, nodes_per_core, self.cores))
+            p.stdin.flush()
+        for p in self.procs:
+            ln = p.stdout.readline().split()
+            if not ln or ln[0] != "done":
+                raise RuntimeError("CPU worker died")
+        return self.cores * nodes_per_core, time.perf_counter() - t0
+
+    def close(self):
+        for p in self.procs:
+            try:
+                p.stdin.write("quit\n")
+                p.stdin.flush()
+                p.stdin.close()
+            except Exception:
+                pass
+        for p in self.procs:
+            try:
+                p.wait(timeout=10)
+            except Exception:
+                p.kill()
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = max(1, min(host_cores(), 64))
+    cpu = CpuContour(cores)
+    for _ in range(min(args.warmup, 1)):
+        cpu.run(1)
+    tot_n, tot_t = 0, 0.0
+    steps = max(1, min(args.steps, 5))
+    for _ in range(steps):
+        nn, t = cpu.run(1)
+        tot_n += nn
+        tot_t += t
+    cpu.close()
+    v = tot_n / tot_t
+    sample = "%d steps x %d nodes (one per worker process) of the N=128 gun contour, k=20; SciPy SuperLU (MMD_AT_PLUS_A)" % (steps, cores)
+    line = {"impl": "reference", "metric": "contour_beyn quadrature-point solves/sec (gun, N=128, k=20)", "value": v,
+            "unit": "solves/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": tot_t / steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "gun matrices (reference fixture) + synthetic MSWS probe",
+            "config": {"workload": "C3 gun SPMF n=9956 p=4, contour_beyn sigma=150^2 radius=500 N=128 k=20", "parallelism": "%d host processes over nodes" % cores},
+            "cpu_baseline": {"value": v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU restatement of NEP-PACK's contour loop (Julia/UMFPACK not installable here)"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# main arm
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "spmm", "contour"])
     ap.add_argument("--grid", type=int, default=1000, help="C4 grid side (n = grid^2)")
+    ap.add_argument("--batch", type=int, default=32, help="quadrature nodes factorised concurrently per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-spmm", action="store_true")
+    ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_worker:
+        cpu_worker_main()
+        return
+    if args.impl == "reference":
+        run_reference(args)
+        return
     args.warmup = max(args.warmup, 3)
 
     dist = Dist()
     import nepb200
     from nepb200 import _lib
+    lib = _lib.lib
     if nepb200.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the nepb200 hot path has no CPU fallback")
-    _lib.check(_lib.lib.nepb_set_device(dist.local_rank))
+    _lib.check(lib.nepb_set_device(dist.local_rank))
+    if dist.world > 1:
+        idb = (C.c_char * 128)()
+        if dist.rank == 0:
+            _lib.check(lib.nepb_comm_unique_id(idb))
+        raw = dist.bcast_bytes(bytes(idb.raw), 128)
+        _lib.check(lib.nepb_comm_init(dist.world, dist.rank, raw))
+
+    # ---- contour workload ---------------------------------------------------------------------------------
+    dnep = gun_operator()
+    n = dnep.n
+    Vh = gun_probe(n, GUN_K)
+    lams, W = beyn_nodes(GUN_N, GUN_SIGMA, GUN_RADIUS)
+    mine = np.arange(dist.rank, GUN_N, dist.world)
+    batch = min(args.batch, len(mine))
+    integ = nepb200.ContourIntegrator(dnep, GUN_K, 2, batch)
+    coef = np.ascontiguousarray(np.stack([dnep.coefficients(l) for l in lams[mine]]))
+    Wm = np.ascontiguousarray(W[mine])
+    Vf = _lib.as_c128_f(Vh)
+    S = np.empty((n, GUN_K, 2), dtype=np.complex128, order="F")
+    reduce = 1 if dist.world > 1 else 0
+    _lib.check(lib.nepb_contour_set_probe(integ._h, _lib.ptr(Vf), n))
+
+    def step_dev():
+        _lib.check(lib.nepb_contour_integrate_dev(integ._h, len(mine), _lib.ptr(coef), _lib.ptr(Wm), reduce))
+
+    def step_e2e():
+        _lib.check(lib.nepb_contour_integrate(integ._h, len(mine), _lib.ptr(coef), _lib.ptr(Wm), _lib.ptr(Vf), n, reduce, _lib.ptr(S), None))
 
     sampler = ClockSampler(dist.local_rank)
     if dist.rank == 0:
         sampler.start()
-    dnep, mats, spmm, peak, peak_src = bench_spmm(args, dist)
-    clocks = sampler.stop() if dist.rank == 0 else None
+    for _ in range(args.warmup):
+        step_dev()
+    lib.nepb_synchronize()
+    dist.barrier()
+    l0 = lib.nepb_launch_count()
+    ms = C.c_float()
+    tmark0 = sampler.mark()
+    lib.nepb_timer_start()
+    for _ in range(args.steps):
+        step_dev()
+    lib.nepb_timer_stop(C.byref(ms))
+    lib.nepb_synchronize()
+    tmark1 = sampler.mark()
+    dist.barrier()
+    launches = lib.nepb_launch_count() - l0
+    t_step = dist.max(ms.value / args.steps)  # ms per step, max over ranks
+    launches_total = int(dist.sum(float(launches)))
+    value = GUN_N / (t_step * 1e-3)
+    # end to end through the host-buffer C-ABI call (H2D of the probe, D2H of the moments inside the timed region)
+    step_e2e()
+    dist.barrier()
+    t0 = time.perf_counter()
+    e2e_reps = max(3, min(args.steps, 10))
+    for _ in range(e2e_reps):
+        step_e2e()
+    te = dist.max((time.perf_counter() - t0) / e2e_reps * 1e3)
+    dist.barrier()
+    clocks = sampler.stop(tmark0, tmark1) if dist.rank == 0 else None
+    # sanity of the timed result: the moments must give the gun reference eigenvalue (test/gun_native.jl:9)
+    lam_found = None
+    if dist.rank == 0:
+        lam, V, info = nepb200.beyn_extract(S[:, :, 0], S[:, :, 1], GUN_SIGMA, (GUN_RADIUS, GUN_RADIUS), GUN_K, 5, 1e-6, np.sqrt(np.finfo(float).eps),
+                                            nepb200.DefaultErrmeasure(dnep), True)
+        lam_found = [complex(x) for x in lam]
+        log("[bench] contour: %.2f ms/step -> %.1f solves/s on %d GPU(s); e2e %.2f ms; eigenvalues inside: %s (p=%d)" %
+            (t_step, value, dist.world, te, lam_found, info["p"]))
+    sym = nepb200.symbolic_info(dnep)
+    integ.close()
+    dnep.close()
 
-    head = spmm[1]
+    # ---- SpMM roofline (every rank runs its own replica; rank 0 reports) -------------------------------------
+    spmm, peak, peak_src, cpu_spmm = (None, None, None, None)
+    if not args.no_spmm:
+        spmm, peak, peak_src, cpu_spmm = bench_spmm(args)
+
     line = {
-        "metric": "SPMF fused SpMM GB/s (algorithmic bytes / device time), config C4",
-        "value": head["gbs"] * dist.world, "unit": "GB/s", "n_gpus": dist.world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": head["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 (complex128 V/Z, real f64 A_i)", "data": "synthetic",
-        "config": {"workload": "C4 synthetic PEP deg 3, n=%d, nnz_u=%d, p=4, fused SpMM M(lam)V k=1" % (dnep.n, dnep.nnz_union),
-                   "l2": "inputs (%.0f MB) larger than the 126 MB L2; no flush needed" % (head["bytes"] / 1e6),
-                   "parallelism": "replicas only" if dist.world > 1 else "single GPU"},
-        "roofline": {"bound": "hbm", "achieved": head["gbs"], "peak": peak, "unit": "GB/s", "frac": head["frac"],
-                     "traffic": None, "peak_source": peak_src, "kernel": "spmm_fused_kernel<4,real,SCALAR> k=1",
-                     "algorithmic_bytes_per_launch": head["bytes"]},
-        "spmm": {str(k): {kk: v[kk] for kk in ("ms", "gbs", "frac", "bytes", "e2e_ms")} for k, v in spmm.items()},
-        "e2e": {"value": head["e2e_gbs"] * dist.world, "unit": "GB/s", "h2d_bytes_per_step": head["h2d"],
-                "d2h_bytes_per_step": head["d2h"]},
-        "gpu_launches": int(sum(v["launches"] for v in spmm.values())),
+        "metric": "contour_beyn quadrature-point solves/sec (gun, N=128, k=20)",
+        "value": value, "unit": "solves/s", "n_gpus": dist.world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64 (complex128 factors / solves, real f64 A_i)", "data": "gun matrices (reference fixture) + synthetic MSWS probe",
+        "config": {"workload": "C3 gun SPMF n=9956 p=4 nnz_u=148318, contour_beyn sigma=150^2 radius=500 N=128 k=20",
+                   "parallelism": "quadrature nodes round-robin over %d rank(s), batch %d per GPU, one ncclAllReduce of 6.4 MB" % (dist.world, batch),
+                   "l2": "factor storage per batch %.0f MB > 126 MB L2; SpMM roofline inputs 790 MB > L2; no flush needed" % (batch * sym["front_entries"] * 16e-6),
+                   "lu": sym},
+        "e2e": {"value": GUN_N / (te * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": int(n * GUN_K * 16 + coef.nbytes + Wm.nbytes),
+                "d2h_bytes_per_step": int(n * GUN_K * 2 * 16), "ms_per_step": te},
+        "gpu_launches": launches_total,
         "clocks": clocks,
+        "eigenvalues_from_timed_moments": [[x.real, x.imag] for x in lam_found] if lam_found else None,
     }
+    if spmm:
+        head = spmm[1]
+        line["roofline"] = {"bound": "hbm", "achieved": head["gbs"], "peak": peak, "unit": "GB/s", "frac": head["frac"], "traffic": None,
+                            "peak_source": peak_src, "kernel": "spmm_fused_kernel<VW=4,real,SCALAR> (config C4, k=1)",
+                            "algorithmic_bytes_per_launch": head["bytes"], "us_per_launch": head["ms"] * 1e3}
+        line["spmm"] = {str(k): {kk: v[kk] for kk in ("ms", "gbs", "frac", "bytes", "e2e_ms")} for k, v in spmm.items()}
     if dist.rank == 0 and not args.no_cpu_baseline:
-        t = cpu_spmm_baseline(mats, 1)
-        line["cpu_baseline"] = {"value": head["bytes"] / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
-                                "sample": "full C4 SpMM passes (k=1) with SciPy CSR, p separate products, %.2f s each" % t}
+        cores = max(1, min(host_cores(), 64))
+        cpu = CpuContour(cores)
+        nn, t = cpu.run(1)
+        cpu.close()
+        line["cpu_baseline"] = {"value": nn / t, "unit": "solves/s", "cores": cores, "kind": "port",
+                                "sample": "%d quadrature nodes of the same contour (one per worker process), k=20, SciPy SuperLU MMD_AT_PLUS_A, %.2f s" % (nn, t)}
+        if cpu_spmm:
+            line["cpu_baseline_spmm"] = cpu_spmm
     if dist.rank == 0:
         print(json.dumps(line), flush=True)
+    if dist.world > 1:
+        lib.nepb_comm_destroy()
     dist.close()
 
 

@@ -104,6 +104,61 @@ int nepb_spmf_apply_block(const nepb_spmf* h, int mode, const nepb_block* V, int
 /* algorithmic HBM bytes of one nepb_spmf_apply_block call (SURVEY.md 8(d) formula) */
 int64_t nepb_spmf_apply_bytes(const nepb_spmf* h, int mode, int k, int q);
 
+/* ---- a6,a7: shifted solves -- device multifrontal LU of M(sigma) = sum_i coef_i A_i ------------------------
+ * Replaces FactorizeLinSolver / BackslashLinSolver (src/LinSolvers.jl:109-159) and what their creators build
+ * (src/LinSolverCreators.jl:21-37,62-122).  The symbolic analysis (fill-reducing ordering of A+A^T, elimination
+ * tree, supernodes, index maps) is computed once per operator, lazily, and shared by every factorisation. */
+typedef struct nepb_lu nepb_lu; /* numeric factors of one or several shifts, resident in HBM */
+/* optional, before the first factorisation: ordering 0 = approximate minimum degree, 1 = natural; relax_leaf /
+ * max_np = supernode relaxation and pivot-block width (<=64); user_perm[n] (index base of the operator, new -> old)
+ * overrides the ordering.  Negative / zero / NULL keep the defaults. */
+int nepb_lu_set_options(nepb_spmf* h, int ordering, int relax_leaf, int max_np, const int64_t* user_perm);
+int nepb_lu_symbolic_info(const nepb_spmf* h, int64_t* nnz_factor, int64_t* front_entries, int* nfronts, int* nlevels,
+                          int* max_front, double* flops);
+/* integer results of the analysis (0-based): perm[n] new->old, etree parent[n] (-1 root), sn_ptr[nfronts+1],
+ * sn_parent[nfronts]; any pointer may be NULL */
+int nepb_lu_symbolic_get(const nepb_spmf* h, int32_t* perm, int32_t* parent, int32_t* sn_ptr, int32_t* sn_parent);
+/* the same analysis for an arbitrary pattern on the host only (no device needed); stats[8] = nnz(L+U), front
+ * entries, fronts, levels, max front, max pivot block, factor multiply-adds, solve work rows */
+int nepb_lu_analyse_pattern(int64_t n, const int64_t* colptr, const int64_t* rowval, int index_base, int ordering,
+                            int relax_leaf, int max_np, int32_t* perm, int32_t* parent, int32_t* colcount, double* stats);
+/* factorise nshift matrices at once: coef is nshift x p complex, row s = (f_1(sigma_s) .. f_p(sigma_s)) */
+int nepb_lu_create(const nepb_spmf* h, int nshift, const double* coef, nepb_lu** out);
+int nepb_lu_destroy(nepb_lu* lu);
+/* flags: bit0 = an exactly zero pivot was replaced (matrix singular to working precision), bit1 = non-finite pivot;
+ * nperturbed = pivots below eps*max|M_ij| that were lifted to that threshold; min_pivot_ratio = min|pivot|/max|M_ij| */
+int nepb_lu_status(const nepb_lu* lu, int shift, int* flags, int* nperturbed, double* min_pivot_ratio);
+/* lin_solve (src/LinSolvers.jl:135-137): X = M(sigma_shift)^-1 B, B and X host column-major n x nrhs (may alias).
+ * refine_steps = maximum iterative-refinement steps (the reference's umfpack_refinements); berr_out (optional)
+ * receives the final normwise backward error. */
+int nepb_lu_solve(nepb_lu* lu, int shift, int nrhs, const double* B, int64_t ldb, double* X, int64_t ldx, int refine_steps,
+                  double* berr_out);
+
+/* ---- a9,a10: contour quadrature, sharded over ranks (src/method_contour_common.jl:61-94) ---------------------
+ * S[:,:,j] = sum_i w[i,j] * M(lambda_i)^-1 Vh over the quadrature nodes this rank owns.  coef is nnodes x p complex
+ * (row i = f_1(lambda_i)..f_p(lambda_i)); weights is nnodes x mg complex (row i = h*gp(t_i)*g_j(t_i)[/(2 pi i)], i.e.
+ * `temp*G[i,j]` of :86-90 including the step h).  Nodes are factorised and solved `batch` at a time. */
+typedef struct nepb_contour nepb_contour;
+int nepb_contour_create(const nepb_spmf* h, int k, int mg, int batch, nepb_contour** out);
+int nepb_contour_destroy(nepb_contour* c);
+/* reduce != 0: sum the moments over all ranks of the communicator (one ncclAllReduce, in place in HBM).
+ * node_flags[nnodes] (optional): bit0 zero pivot, bit1 non-finite pivot, bit2 perturbed pivots. */
+int nepb_contour_integrate(nepb_contour* c, int nnodes, const double* coef, const double* weights, const double* Vh,
+                           int64_t ldv, int reduce, double* S /* n x k x mg, column-major */, int* node_flags);
+/* the same in three steps, so that a benchmark can time the device part alone */
+int nepb_contour_set_probe(nepb_contour* c, const double* Vh, int64_t ldv);
+int nepb_contour_integrate_dev(nepb_contour* c, int nnodes, const double* coef, const double* weights, int reduce);
+int nepb_contour_get_moments(nepb_contour* c, double* S);
+
+/* ---- multi-GPU plumbing: one process per GPU, NCCL loaded at run time ------------------------------------------
+ * Rank 0 calls nepb_comm_unique_id and ships the 128 bytes to the other ranks with whatever the host has
+ * (torch.distributed, MPI, Julia Distributed); then every rank calls nepb_comm_init. */
+int nepb_comm_unique_id(char id[128]);
+int nepb_comm_init(int nranks, int rank, const char id[128]);
+int nepb_comm_destroy(void);
+int nepb_comm_info(int* nranks, int* rank, int* nccl_version);
+int nepb_comm_allreduce_sum_dev(void* dev_ptr, int64_t count /* doubles */);
+
 /* ---- deterministic synthetic data (bench / tests): Middle-Square-Weyl stream ------------------- */
 /* state = {x_lo,x_hi,w_lo,w_hi,s_lo,s_hi}; fills out[count] with uniform doubles in [0,1) exactly as
  * gen_rng_float of src/gallery_extra/basic_random_examples.jl:86-95 and advances the state. */

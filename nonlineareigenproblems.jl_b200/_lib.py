@@ -78,6 +78,25 @@ SIGNATURES = {
     "nepb_block_dev_ptr": (vp, [vp]),
     "nepb_spmf_apply_block": (c_int, [vp, c_int, vp, c_int, vp, vp]),
     "nepb_spmf_apply_bytes": (c_i64, [vp, c_int, c_int, c_int]),
+    "nepb_lu_set_options": (c_int, [vp, c_int, c_int, c_int, vp]),
+    "nepb_lu_symbolic_info": (c_int, [vp, P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_int), P(c_dbl)]),
+    "nepb_lu_symbolic_get": (c_int, [vp, vp, vp, vp, vp]),
+    "nepb_lu_analyse_pattern": (c_int, [c_i64, vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp, vp]),
+    "nepb_lu_create": (c_int, [vp, c_int, vp, P(vp)]),
+    "nepb_lu_destroy": (c_int, [vp]),
+    "nepb_lu_status": (c_int, [vp, c_int, P(c_int), P(c_int), P(c_dbl)]),
+    "nepb_lu_solve": (c_int, [vp, c_int, c_int, vp, c_i64, vp, c_i64, c_int, P(c_dbl)]),
+    "nepb_contour_create": (c_int, [vp, c_int, c_int, c_int, P(vp)]),
+    "nepb_contour_destroy": (c_int, [vp]),
+    "nepb_contour_integrate": (c_int, [vp, c_int, vp, vp, vp, c_i64, c_int, vp, vp]),
+    "nepb_contour_set_probe": (c_int, [vp, vp, c_i64]),
+    "nepb_contour_integrate_dev": (c_int, [vp, c_int, vp, vp, c_int]),
+    "nepb_contour_get_moments": (c_int, [vp, vp]),
+    "nepb_comm_unique_id": (c_int, [vp]),
+    "nepb_comm_init": (c_int, [c_int, c_int, vp]),
+    "nepb_comm_destroy": (c_int, []),
+    "nepb_comm_info": (c_int, [P(c_int), P(c_int), P(c_int)]),
+    "nepb_comm_allreduce_sum_dev": (c_int, [vp, c_i64]),
     "nepb_msws_init": (c_int, [C.c_uint64, C.c_uint64, vp]),
     "nepb_msws_fill": (c_int, [vp, c_i64, vp]),
 }

@@ -6,8 +6,10 @@
 #include <stdarg.h>
 #include <string>
 #include <atomic>
+#include <vector>
 
 #include "../../include/nepb200.h"
+#include "lu_symbolic.h"
 
 namespace nepb {
 
@@ -100,5 +102,8 @@ struct nepb_spmf {
     mutable nepb::DevBuf<double> d_tmp_in, d_tmp_out, d_tmp_x, d_coef;
     mutable nepb::DevBuf<double> d_stage;
     void* lu_symbolic = nullptr;  // owned by lu.cu (lazy)
+    nepb::LuOptions lu_opt;
+    bool lu_opt_set = false;
+    std::vector<int32_t> lu_user_perm;
     ~nepb_spmf();
 };

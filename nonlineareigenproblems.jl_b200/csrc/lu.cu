@@ -1,5 +1,915 @@
-// placeholder until the device LU lands (next milestone)
+// Device multifrontal LU of M(sigma) = sum_i c_i A_i on the SPMF union pattern, batched over shifts, and the
+// batched multi-RHS triangular solves against it (sm_100a).
+//
+// Replaces (reference, relative to src/): LinSolvers.jl:109-137 (FactorizeLinSolver: factorize(compute_Mder) +
+// `Afact \ x`), :147-159 (BackslashLinSolver), LinSolverCreators.jl:62-122; the N factor+solve pairs of
+// method_contour_common.jl:81-91.  The arithmetic the reference delegates to UMFPACK is restated here as a
+// multifrontal method because that is what maps onto the GPU: the symbolic analysis (lu_symbolic.cpp) is done once
+// per sparsity pattern, every shift re-uses it, and a *batch* of shifts is factorised concurrently -- the batch
+// and the independent fronts of one elimination-tree level are the two sources of parallelism.
+//
+// Per level of the supernodal tree:
+//   extend-add   parent fronts gather their children's contribution blocks (parent-centric, no atomics,
+//                deterministic summation order)
+//   diag         partial-pivoted LU of the np x np pivot block in shared memory (pivoting restricted to the
+//                fully-summed rows of the front; tiny pivots are perturbed and counted, zero / non-finite
+//                pivots flag the shift as singular)
+//   panel        U12 = L11^-1 P F12 and L21 = F21 U11^-1, tiled over CTAs
+//   schur        F22 -= L21 U12, 64 x 64 output tiles (FP64 FMA pipe; B200 has no faster FP64 path)
+// Fronts are dense column-major nf x nf blocks, all fronts of one shift contiguous (stride front_total).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
 #include "common.h"
+#include "lu_symbolic.h"
+#include "lu_internal.h"
+
 namespace nepb {
-void lu_symbolic_release(void*) {}
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ void cfms(double2& acc, const double2 a, const double2 b) {  // acc -= a*b
+    acc.x = fma(-a.x, b.x, acc.x);
+    acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(-a.x, b.y, acc.y);
+    acc.y = fma(-a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cfma2(double2& acc, const double2 a, const double2 b) {  // acc += a*b
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ double2 crecip(double2 a) {
+    // 1/a with scaling (Smith): no overflow of |a|^2
+    if (fabs(a.x) >= fabs(a.y)) {
+        const double r = a.y / a.x, d = a.x + a.y * r;
+        return make_double2(1.0 / d, -r / d);
+    }
+    const double r = a.x / a.y, d = a.x * r + a.y;
+    return make_double2(r / d, -1.0 / d);
+}
+__device__ __forceinline__ double cabs1(double2 a) { return fabs(a.x) + fabs(a.y); }
+
+// ---------------------------------------------------------------------------------------------
+// assembly: fronts[b][a_pos[e]] = sum_i coef[b][i] * vals[e][i]   (fused compute_Mder + scatter)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lu_assemble_kernel(int64_t nnz, int p, int ca, const int64_t* __restrict__ a_pos,
+                                                          const double* __restrict__ vals, const double2* __restrict__ coef,
+                                                          double2* __restrict__ fronts, int64_t front_total, LuInfo* __restrict__ info) {
+    const int b = blockIdx.y;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double2* c = coef + (size_t)b * p;
+    double a = 0.0;
+    if (e < nnz) {
+        const int vw = ca ? 2 * p : p;
+        const double* v = vals + (size_t)e * vw;
+        double2 m = make_double2(0.0, 0.0);
+        for (int i = 0; i < p; ++i) {
+            const double2 x = ca ? make_double2(v[2 * i], v[2 * i + 1]) : make_double2(v[i], 0.0);
+            cfma2(m, c[i], x);
+        }
+        fronts[(size_t)b * front_total + a_pos[e]] = m;
+        a = cabs1(m);
+    }
+    // max |entry| of M(sigma_b): scale for the tiny-pivot test
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, off));
+    if ((threadIdx.x & 31) == 0 && a > 0.0) atomicMax((unsigned long long*)&info[b].amax_bits, (unsigned long long)__double_as_longlong(a));
+}
+
+// ---------------------------------------------------------------------------------------------
+// extend-add: item = (parent s, parent column slab [j0, j1))
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts) {
+    const int4 it = items[blockIdx.x];
+    const int s = it.x, j0 = it.y, j1 = it.z;
+    const int b = blockIdx.y;
+    double2* base = fronts + (size_t)b * d.front_total;
+    const int nfp = d.nf[s];
+    double2* Fp = base + d.front_off[s];
+    for (int ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ++ci) {
+        const int c = d.child_list[ci];
+        const int nfc = d.nf[c], npc = d.np[c], ncb = nfc - npc;
+        if (ncb == 0) continue;
+        const int* rel = d.rel + d.rel_ptr[c];
+        // rel is strictly increasing: the child columns landing in [j0, j1) form a contiguous range
+        int lo = 0, hi = ncb;
+        while (lo < hi) { int m = (lo + hi) >> 1; if (rel[m] < j0) lo = m + 1; else hi = m; }
+        const int xa = lo;
+        hi = ncb;
+        while (lo < hi) { int m = (lo + hi) >> 1; if (rel[m] < j1) lo = m + 1; else hi = m; }
+        const int xb = lo;
+        const double2* Fc = base + d.front_off[c];
+        const int total = (xb - xa) * ncb;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            const int x = xa + idx / ncb, y = idx % ncb;
+            const double2 v = Fc[(size_t)(npc + y) + (size_t)(npc + x) * nfc];
+            double2* t = Fp + (size_t)rel[y] + (size_t)rel[x] * nfp;
+            double2 o = *t;
+            o.x += v.x;
+            o.y += v.y;
+            *t = o;
+        }
+        __syncthreads();  // children are applied one after the other: fixed summation order
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// diag: LU with partial pivoting of the pivot block, one CTA per (front, shift)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lu_diag_kernel(LuDev d, const int* __restrict__ items, double2* __restrict__ fronts,
+                                                      int* __restrict__ piv, LuInfo* __restrict__ info) {
+    extern __shared__ double2 sA[];  // np x np, column-major, ld = np + 1
+    __shared__ int s_piv;
+    __shared__ double2 s_rp;
+    const int s = items[blockIdx.x];
+    const int b = blockIdx.y;
+    const int nf = d.nf[s], np = d.np[s], ld = np + 1;
+    double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
+    int* pv = piv + (size_t)b * d.n + d.sn_ptr[s];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < np * np; idx += blockDim.x) {
+        const int i = idx % np, j = idx / np;
+        sA[i + j * ld] = F[(size_t)i + (size_t)j * nf];
+    }
+    __syncthreads();
+    const double amax = __longlong_as_double(info[b].amax_bits);
+    const double tiny = 2.220446049250313e-16 * amax;
+    for (int j = 0; j < np; ++j) {
+        if (tid < 32) {
+            // pivot search over rows j..np-1 of column j (np <= 64: two rounds at most)
+            double best = -1.0;
+            int bi = j;
+            for (int i = j + tid; i < np; i += 32) {
+                const double a = cabs1(sA[i + j * ld]);
+                if (a > best || !(a == a)) { best = (a == a) ? a : INFINITY; bi = i; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (tid == 0) {
+                const double dj = cabs1(sA[j + j * ld]);
+                if (dj >= 0.1 * best && dj == dj) bi = j;  // threshold pivoting that prefers the diagonal
+                double2 pvt = sA[bi + j * ld];
+                const double pa = cabs1(pvt);
+                if (!(pa <= 1.79e308) || !(best <= 1.79e308)) {  // NaN / Inf
+                    atomicOr(&info[b].flags, 2);
+                    pvt = make_double2(1.0, 0.0);
+                } else if (pa == 0.0) {
+                    atomicOr(&info[b].flags, 1);  // exactly singular within the front
+                    atomicAdd(&info[b].nperturbed, 1);
+                    pvt = make_double2(tiny > 0.0 ? tiny : 1.0, 0.0);
+                } else if (pa < tiny) {
+                    atomicAdd(&info[b].nperturbed, 1);
+                    const double sc = tiny / pa;
+                    pvt = make_double2(pvt.x * sc, pvt.y * sc);
+                }
+                sA[bi + j * ld] = pvt;
+                s_piv = bi;
+                s_rp = crecip(pvt);
+                pv[j] = bi;
+                // smallest pivot relative to amax, for diagnostics
+                const double ratio = amax > 0.0 ? pa / amax : 0.0;
+                atomicMin((unsigned long long*)&info[b].minpiv_bits, (unsigned long long)__double_as_longlong(ratio));
+            }
+        }
+        __syncthreads();
+        const int pr = s_piv;
+        if (pr != j && tid < np) {
+            const double2 t = sA[j + tid * ld];
+            sA[j + tid * ld] = sA[pr + tid * ld];
+            sA[pr + tid * ld] = t;
+        }
+        __syncthreads();
+        const double2 rp = s_rp;
+        for (int i = j + 1 + tid; i < np; i += blockDim.x) sA[i + j * ld] = cmul(sA[i + j * ld], rp);
+        __syncthreads();
+        const int m = np - j - 1;
+        for (int idx = tid; idx < m * m; idx += blockDim.x) {
+            const int i = j + 1 + idx % m, k = j + 1 + idx / m;
+            cfms(sA[i + k * ld], sA[i + j * ld], sA[j + k * ld]);
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < np * np; idx += blockDim.x) {
+        const int i = idx % np, j = idx / np;
+        F[(size_t)i + (size_t)j * nf] = sA[i + j * ld];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// panel: item = (front s, kind 0 = U tile / 1 = L tile, tile start t0); 64 columns (rows) per tile
+// ---------------------------------------------------------------------------------------------
+constexpr int PANEL_T = 64;
+__global__ void __launch_bounds__(128) lu_panel_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts,
+                                                       const int* __restrict__ piv) {
+    extern __shared__ double2 sm[];
+    const int4 it = items[blockIdx.x];
+    const int s = it.x, kind = it.y, t0 = it.z;
+    const int b = blockIdx.y;
+    const int nf = d.nf[s], np = d.np[s], ncb = nf - np, ld = np + 1;
+    double2* sLU = sm;                   // np x np, ld = np+1
+    double2* sT = sm + (size_t)np * ld;  // tile: U kind [PANEL_T][np+1] (column c at sT + c*ld); L kind [np][PANEL_T]
+    double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
+    const int* pv = piv + (size_t)b * d.n + d.sn_ptr[s];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < np * np; idx += blockDim.x) {
+        const int i = idx % np, j = idx / np;
+        sLU[i + j * ld] = F[(size_t)i + (size_t)j * nf];
+    }
+    const int tw = min(PANEL_T, ncb - t0);
+    if (kind == 0) {
+        // U12 tile: columns np+t0 .. np+t0+tw-1, rows 0..np-1 (contiguous per column)
+        for (int idx = tid; idx < tw * np; idx += blockDim.x) {
+            const int i = idx % np, c = idx / np;
+            sT[i + c * ld] = F[(size_t)i + (size_t)(np + t0 + c) * nf];
+        }
+        __syncthreads();
+        if (tid < tw) {
+            double2* x = sT + tid * ld;
+            for (int j = 0; j < np; ++j) {  // row swaps of the pivot block
+                const int pr = pv[j];
+                if (pr != j) { const double2 t = x[j]; x[j] = x[pr]; x[pr] = t; }
+            }
+            for (int j = 0; j < np; ++j) {  // unit lower solve
+                const double2 xj = x[j];
+                for (int i = j + 1; i < np; ++i) cfms(x[i], sLU[i + j * ld], xj);
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < tw * np; idx += blockDim.x) {
+            const int i = idx % np, c = idx / np;
+            F[(size_t)i + (size_t)(np + t0 + c) * nf] = sT[i + c * ld];
+        }
+    } else {
+        // L21 tile: rows np+t0 .. , columns 0..np-1 ; x U11 = f  ->  x_j = (f_j - sum_{t<j} x_t U[t,j]) / U[j,j]
+        for (int idx = tid; idx < tw * np; idx += blockDim.x) {
+            const int r = idx % tw, j = idx / tw;
+            sT[r + j * PANEL_T] = F[(size_t)(np + t0 + r) + (size_t)j * nf];
+        }
+        __syncthreads();
+        if (tid < tw) {
+            for (int j = 0; j < np; ++j) {
+                double2 x = sT[tid + j * PANEL_T];
+                for (int t = 0; t < j; ++t) cfms(x, sT[tid + t * PANEL_T], sLU[t + j * ld]);
+                sT[tid + j * PANEL_T] = cmul(x, crecip(sLU[j + j * ld]));
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < tw * np; idx += blockDim.x) {
+            const int r = idx % tw, j = idx / tw;
+            F[(size_t)(np + t0 + r) + (size_t)j * nf] = sT[r + j * PANEL_T];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// schur: item = (front s, row tile i0, column tile j0); F22[i0.., j0..] -= L21[i0.., :] * U12[:, j0..]
+// 64 x 64 tile, 256 threads, each 4 x 4 outputs (rows tx + 16 r, columns ty + 16 c)
+// ---------------------------------------------------------------------------------------------
+constexpr int SCHUR_T = 64;
+__global__ void __launch_bounds__(256) lu_schur_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts) {
+    extern __shared__ double2 sm[];
+    const int4 it = items[blockIdx.x];
+    const int s = it.x, i0 = it.y, j0 = it.z;
+    const int b = blockIdx.y;
+    const int nf = d.nf[s], np = d.np[s], ncb = nf - np;
+    double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
+    double2* sL = sm;                           // [np][SCHUR_T]   L21 tile, row index fastest
+    double2* sU = sm + (size_t)np * SCHUR_T;    // [np][SCHUR_T]   U12 tile transposed: sU[t][c]
+    const int tid = threadIdx.x;
+    const int th = min(SCHUR_T, ncb - i0), tw = min(SCHUR_T, ncb - j0);
+    for (int idx = tid; idx < np * SCHUR_T; idx += blockDim.x) {
+        const int r = idx % SCHUR_T, t = idx / SCHUR_T;
+        sL[idx] = (r < th) ? F[(size_t)(np + i0 + r) + (size_t)t * nf] : make_double2(0.0, 0.0);
+    }
+    for (int idx = tid; idx < np * SCHUR_T; idx += blockDim.x) {
+        const int t = idx % np, c = idx / np;  // contiguous reads along t
+        sU[t * SCHUR_T + c] = (c < tw) ? F[(size_t)t + (size_t)(np + j0 + c) * nf] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    const int tx = tid % 16, ty = tid / 16;
+    double2 acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = make_double2(0.0, 0.0);
+    for (int t = 0; t < np; ++t) {
+        double2 l[4], u[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) l[r] = sL[t * SCHUR_T + tx + 16 * r];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) u[c] = sU[t * SCHUR_T + ty + 16 * c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cfma2(acc[r][c], l[r], u[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int cc = ty + 16 * c;
+        if (cc >= tw) continue;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int rr = tx + 16 * r;
+            if (rr >= th) continue;
+            double2* t = F + (size_t)(np + i0 + rr) + (size_t)(np + j0 + cc) * nf;
+            double2 o = *t;
+            o.x -= acc[r][c].x;
+            o.y -= acc[r][c].y;
+            *t = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// solves.  Xp: permuted right-hand sides / solutions, [b][n][k] row-major; W: per-front work rows [b][w_total][k].
+// rhs_stride = 0 when all shifts share one right-hand side block (contour integration).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lu_permute_in_kernel(int n, int k, const int* __restrict__ perm, const double2* __restrict__ Bm,
+                                                            size_t rhs_stride, double2* __restrict__ Xp) {
+    const int b = blockIdx.y;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * k) return;
+    const int i = (int)(idx / k), c = (int)(idx % k);
+    Xp[(size_t)b * n * k + idx] = Bm[b * rhs_stride + (size_t)perm[i] * k + c];
+}
+
+__global__ void __launch_bounds__(256) lu_permute_out_kernel(int n, int k, const int* __restrict__ iperm, const double2* __restrict__ Xp,
+                                                             double2* __restrict__ X, size_t x_stride) {
+    const int b = blockIdx.y;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * k) return;
+    const int i = (int)(idx / k), c = (int)(idx % k);
+    X[b * x_stride + idx] = Xp[(size_t)b * n * k + (size_t)iperm[i] * k + c];
+}
+
+// forward: one CTA per (front, shift)
+__global__ void __launch_bounds__(256) lu_forward_kernel(LuDev d, const int* __restrict__ items, const double2* __restrict__ fronts,
+                                                         const int* __restrict__ piv, double2* __restrict__ Xp, double2* __restrict__ W, int k) {
+    extern __shared__ double2 sy[];  // np x k pivot rows
+    const int s = items[blockIdx.x];
+    const int b = blockIdx.y;
+    const int nf = d.nf[s], np = d.np[s], ncb = nf - np;
+    const double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
+    const int* pv = piv + (size_t)b * d.n + d.sn_ptr[s];
+    double2* Wb = W + (size_t)b * d.w_total * k;
+    double2* Ws = Wb + (size_t)d.w_off[s] * k;
+    double2* Xb = Xp + (size_t)b * d.n * k;
+    const int c0 = d.sn_ptr[s];
+    const int tid = threadIdx.x;
+    // 1. gather: pivot rows from the right-hand side, update rows start at zero; then the children's updates
+    for (int idx = tid; idx < np * k; idx += blockDim.x) sy[idx] = Xb[(size_t)c0 * k + idx];
+    for (int idx = tid; idx < ncb * k; idx += blockDim.x) Ws[(size_t)np * k + idx] = make_double2(0.0, 0.0);
+    __syncthreads();
+    for (int ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ++ci) {
+        const int c = d.child_list[ci];
+        const int npc = d.np[c], ncbc = d.nf[c] - npc;
+        const int* rel = d.rel + d.rel_ptr[c];
+        const double2* Wc = Wb + ((size_t)d.w_off[c] + npc) * k;
+        for (int idx = tid; idx < ncbc * k; idx += blockDim.x) {
+            const int x = idx / k, col = idx % k;
+            const int r = rel[x];
+            const double2 v = Wc[idx];
+            double2* t = (r < np) ? &sy[r * k + col] : &Ws[(size_t)r * k + col];
+            double2 o = *t;
+            o.x += v.x;
+            o.y += v.y;
+            *t = o;
+        }
+        __syncthreads();
+    }
+    // 2. row swaps, 3. unit lower solve on the pivot rows (thread = right-hand side column)
+    if (tid < k) {
+        for (int j = 0; j < np; ++j) {
+            const int pr = pv[j];
+            if (pr != j) { const double2 t = sy[j * k + tid]; sy[j * k + tid] = sy[pr * k + tid]; sy[pr * k + tid] = t; }
+        }
+    }
+    __syncthreads();
+    for (int j = 0; j < np - 1; ++j) {
+        const int m = np - j - 1;
+        for (int idx = tid; idx < m * k; idx += blockDim.x) {
+            const int i = j + 1 + idx / k, col = idx % k;
+            cfms(sy[i * k + col], F[(size_t)i + (size_t)j * nf], sy[j * k + col]);
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < np * k; idx += blockDim.x) Xb[(size_t)c0 * k + idx] = sy[idx];
+    // 4. update rows: W[np + r, :] -= L21[r, :] * y1
+    for (int idx = tid; idx < ncb * k; idx += blockDim.x) {
+        const int r = idx % ncb, col = idx / ncb;  // consecutive threads -> consecutive rows of L21 (coalesced)
+        double2 acc = Ws[(size_t)(np + r) * k + col];
+        const double2* Lr = F + (size_t)(np + r);
+        for (int t = 0; t < np; ++t) cfms(acc, Lr[(size_t)t * nf], sy[t * k + col]);
+        Ws[(size_t)(np + r) * k + col] = acc;
+    }
+}
+
+// backward: x1 = U11^-1 (y1 - U12 x2)
+__global__ void __launch_bounds__(256) lu_backward_kernel(LuDev d, const int* __restrict__ items, const double2* __restrict__ fronts,
+                                                          double2* __restrict__ Xp, int k) {
+    extern __shared__ double2 sy[];  // np x k
+    const int s = items[blockIdx.x];
+    const int b = blockIdx.y;
+    const int nf = d.nf[s], np = d.np[s], ncb = nf - np;
+    const double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
+    double2* Xb = Xp + (size_t)b * d.n * k;
+    const int* rows = d.rows + d.row_ptr[s];
+    const int c0 = d.sn_ptr[s];
+    const int tid = threadIdx.x;
+    // y1 - U12 x2 : thread = (pivot row t, column col)
+    for (int idx = tid; idx < np * k; idx += blockDim.x) {
+        const int t = idx % np, col = idx / np;
+        double2 acc = Xb[(size_t)(c0 + t) * k + col];
+        for (int x = 0; x < ncb; ++x) cfms(acc, F[(size_t)t + (size_t)(np + x) * nf], Xb[(size_t)rows[np + x] * k + col]);
+        sy[t * k + col] = acc;
+    }
+    __syncthreads();
+    for (int j = np - 1; j >= 0; --j) {
+        if (tid < k) sy[j * k + tid] = cmul(sy[j * k + tid], crecip(F[(size_t)j + (size_t)j * nf]));
+        __syncthreads();
+        for (int idx = tid; idx < j * k; idx += blockDim.x) {
+            const int i = idx / k, col = idx % k;
+            cfms(sy[i * k + col], F[(size_t)i + (size_t)j * nf], sy[j * k + col]);
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < np * k; idx += blockDim.x) Xb[(size_t)c0 * k + idx] = sy[idx];
+}
+
+// S[j] += sum_b wgt[b*mg + j] * X[b]   (contour moments, method_contour_common.jl:86-90), elementwise n*k
+__global__ void contour_accumulate_kernel(size_t nk, int nb, int mg, const double2* __restrict__ X, size_t x_stride,
+                                                                 const double2* __restrict__ wgt, double2* __restrict__ S) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nk) return;
+    for (int j = 0; j < mg; ++j) {
+        double2 acc = S[(size_t)j * nk + idx];
+        for (int b = 0; b < nb; ++b) cfma2(acc, wgt[b * mg + j], X[b * x_stride + idx]);
+        S[(size_t)j * nk + idx] = acc;
+    }
+}
+
+// R = B - R  (residual from M*X), elementwise
+__global__ void __launch_bounds__(256) residual_kernel(size_t count, const double2* __restrict__ Bm, double2* __restrict__ R) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const double2 bv = Bm[idx], r = R[idx];
+    R[idx] = make_double2(bv.x - r.x, bv.y - r.y);
+}
+__global__ void __launch_bounds__(256) axpy_kernel(size_t count, const double2* __restrict__ D, double2* __restrict__ X) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    X[idx].x += D[idx].x;
+    X[idx].y += D[idx].y;
+}
+// per-column max |.| of a row-major n x k block -> out[k] (as ordered uint64 bits)
+__global__ void __launch_bounds__(256) colmax_kernel(int n, int k, const double2* __restrict__ A, unsigned long long* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * k) return;
+    const double a = cabs1(A[idx]);
+    atomicMax(out + idx % k, (unsigned long long)__double_as_longlong(a));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <class T>
+static cudaError_t upload(DevBuf<T>& buf, const std::vector<T>& v) {
+    cudaError_t e = buf.alloc(std::max<size_t>(v.size(), 1));
+    if (e != cudaSuccess) return e;
+    if (!v.empty()) e = cudaMemcpy(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+static LuOptions g_default_opt;
+
+int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
+    static std::mutex mtx;
+    std::lock_guard<std::mutex> lock(mtx);
+    nepb_spmf* hm = const_cast<nepb_spmf*>(h);
+    if (hm->lu_symbolic) {
+        *out = (LuSymbolicDev*)hm->lu_symbolic;
+        return NEPB_OK;
+    }
+    NEPB_CHECK_ARG(h->n < (int64_t)1 << 31, "n too large");
+    LuSymbolicDev* sd = new LuSymbolicDev();
+    LuOptions opt = hm->lu_opt_set ? hm->lu_opt : g_default_opt;
+    if (const char* e = getenv("NEPB_LU_MAXNP")) opt.max_np = std::max(1, std::min(64, atoi(e)));
+    if (const char* e = getenv("NEPB_LU_RELAX")) opt.relax_leaf = std::max(1, atoi(e));
+    if (const char* e = getenv("NEPB_LU_ORDERING")) opt.ordering = atoi(e);
+    opt.max_np = std::max(1, std::min(64, opt.max_np));
+    int rc = lu_symbolic_analyse((int)h->n, h->h_rowptr, h->h_colind, hm->lu_user_perm.empty() ? nullptr : hm->lu_user_perm.data(), opt, sd->S);
+    if (rc) {
+        delete sd;
+        return rc;
+    }
+    const LuSymbolic& S = sd->S;
+    const int ns = S.nsuper;
+    std::vector<int32_t> nf(ns), np(ns), child_ptr(ns + 1, 0), child_list;
+    for (int s = 0; s < ns; ++s) {
+        nf[s] = (int)(S.row_ptr[s + 1] - S.row_ptr[s]);
+        np[s] = S.sn_ptr[s + 1] - S.sn_ptr[s];
+        if (S.sn_parent[s] >= 0) child_ptr[S.sn_parent[s] + 1]++;
+    }
+    for (int s = 0; s < ns; ++s) child_ptr[s + 1] += child_ptr[s];
+    child_list.resize(child_ptr[ns]);
+    {
+        std::vector<int32_t> cur(child_ptr.begin(), child_ptr.end() - 1);
+        for (int s = 0; s < ns; ++s)
+            if (S.sn_parent[s] >= 0) child_list[cur[S.sn_parent[s]]++] = s;  // ascending child index: fixed order
+    }
+    // per-level work lists
+    sd->lv.resize(S.nlevels);
+    std::vector<int32_t> fr_items;
+    std::vector<int4> ea_items, pn_items, sc_items;
+    for (int l = 0; l < S.nlevels; ++l) {
+        auto& L = sd->lv[l];
+        L.front_begin = (int)fr_items.size();
+        L.ea_begin = (int)ea_items.size();
+        L.pn_begin = (int)pn_items.size();
+        L.sc_begin = (int)sc_items.size();
+        std::vector<int32_t> fl(S.level_list.begin() + S.level_ptr[l], S.level_list.begin() + S.level_ptr[l + 1]);
+        std::stable_sort(fl.begin(), fl.end(), [&](int a, int b) { return nf[a] > nf[b]; });  // big fronts first
+        for (int s : fl) {
+            fr_items.push_back(s);
+            const int ncb = nf[s] - np[s];
+            if (child_ptr[s + 1] > child_ptr[s]) {
+                // slab width: keep roughly <= 16k entries of child data per CTA
+                int slab = nf[s];
+                if (nf[s] > 96) slab = std::max(16, (int)(16384 / nf[s]));
+                for (int j0 = 0; j0 < nf[s]; j0 += slab) ea_items.push_back(make_int4(s, j0, std::min(nf[s], j0 + slab), 0));
+            }
+            for (int t0 = 0; t0 < ncb; t0 += PANEL_T) {
+                pn_items.push_back(make_int4(s, 0, t0, 0));
+                pn_items.push_back(make_int4(s, 1, t0, 0));
+            }
+            for (int j0 = 0; j0 < ncb; j0 += SCHUR_T)
+                for (int i0 = 0; i0 < ncb; i0 += SCHUR_T) sc_items.push_back(make_int4(s, i0, j0, 0));
+        }
+        L.front_count = (int)fr_items.size() - L.front_begin;
+        L.ea_count = (int)ea_items.size() - L.ea_begin;
+        L.pn_count = (int)pn_items.size() - L.pn_begin;
+        L.sc_count = (int)sc_items.size() - L.sc_begin;
+    }
+    cudaError_t e = cudaSuccess;
+#define UP(buf, vec) if (e == cudaSuccess) e = upload(buf, vec)
+    UP(sd->front_off, S.front_off);
+    UP(sd->nf, nf);
+    UP(sd->np, np);
+    UP(sd->row_ptr, S.row_ptr);
+    UP(sd->rows, S.rows);
+    UP(sd->rel_ptr, S.rel_ptr);
+    UP(sd->rel, S.rel);
+    UP(sd->sn_ptr, S.sn_ptr);
+    UP(sd->w_off, S.w_off);
+    UP(sd->child_ptr, child_ptr);
+    UP(sd->child_list, child_list);
+    UP(sd->a_pos, S.a_pos);
+    UP(sd->perm, S.perm);
+    UP(sd->iperm, S.iperm);
+    UP(sd->fr_items, fr_items);
+    UP(sd->ea_items, ea_items);
+    UP(sd->pn_items, pn_items);
+    UP(sd->sc_items, sc_items);
+#undef UP
+    if (e != cudaSuccess) {
+        set_error("CUDA error while uploading the LU symbolic data: %s", cudaGetErrorString(e));
+        delete sd;
+        return e == cudaErrorMemoryAllocation ? NEPB_E_NOMEM : NEPB_E_CUDA;
+    }
+    LuDev& d = sd->dev;
+    d.front_off = sd->front_off.p;
+    d.nf = sd->nf.p;
+    d.np = sd->np.p;
+    d.row_ptr = sd->row_ptr.p;
+    d.rows = sd->rows.p;
+    d.rel_ptr = sd->rel_ptr.p;
+    d.rel = sd->rel.p;
+    d.sn_ptr = sd->sn_ptr.p;
+    d.w_off = sd->w_off.p;
+    d.child_ptr = sd->child_ptr.p;
+    d.child_list = sd->child_list.p;
+    d.front_total = S.front_total;
+    d.w_total = S.w_total;
+    d.n = S.n;
+    // opt-in shared memory sizes
+    const int mnp = S.max_np;
+    sd->smem_diag = (size_t)mnp * (mnp + 1) * 16;
+    sd->smem_panel = ((size_t)mnp * (mnp + 1) + (size_t)PANEL_T * (mnp + 1)) * 16;
+    sd->smem_schur = (size_t)2 * mnp * SCHUR_T * 16;
+    cudaFuncSetAttribute(lu_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_diag);
+    cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_panel);
+    cudaFuncSetAttribute(lu_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_schur);
+    cudaFuncSetAttribute(lu_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lu_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    hm->lu_symbolic = sd;
+    *out = sd;
+    return NEPB_OK;
+}
+
+void lu_symbolic_release(void* p) { delete (LuSymbolicDev*)p; }
+
+// numeric factorisation of lu->nb shifts into lu->fronts (coefficients already on the device)
+static int lu_factor_device(nepb_lu* lu) {
+    const nepb_spmf* h = lu->op;
+    LuSymbolicDev* sd = lu->sym;
+    const LuSymbolic& S = sd->S;
+    const int nb = lu->nb;
+    NEPB_CUDA(cudaMemsetAsync(lu->fronts.p, 0, sizeof(double) * 2 * (size_t)nb * S.front_total, stream()));
+    lu->h_info.resize(nb);
+    for (auto& x : lu->h_info) {
+        x.amax_bits = 0;
+        x.minpiv_bits = 0x7ff0000000000000ULL;  // +inf
+        x.flags = 0;
+        x.nperturbed = 0;
+    }
+    NEPB_CUDA(cudaMemcpyAsync(lu->info.p, lu->h_info.data(), sizeof(LuInfo) * nb, cudaMemcpyHostToDevice, stream()));
+    {
+        dim3 grid((unsigned)((h->nnz + 255) / 256), nb);
+        NEPB_LAUNCH(lu_assemble_kernel, grid, 256, 0, h->nnz, h->p, h->is_complex, sd->a_pos.p, h->d_vals.p, (const double2*)lu->coef.p,
+                    (double2*)lu->fronts.p, S.front_total, lu->info.p);
+    }
+    double2* F = (double2*)lu->fronts.p;
+    for (int l = 0; l < S.nlevels; ++l) {
+        const auto& L = sd->lv[l];
+        if (L.ea_count) NEPB_LAUNCH(lu_extend_add_kernel, dim3(L.ea_count, nb), 256, 0, sd->dev, sd->ea_items.p + L.ea_begin, F);
+        NEPB_LAUNCH(lu_diag_kernel, dim3(L.front_count, nb), 256, sd->smem_diag, sd->dev, sd->fr_items.p + L.front_begin, F, lu->piv.p, lu->info.p);
+        if (L.pn_count) NEPB_LAUNCH(lu_panel_kernel, dim3(L.pn_count, nb), 128, sd->smem_panel, sd->dev, sd->pn_items.p + L.pn_begin, F, lu->piv.p);
+        if (L.sc_count) NEPB_LAUNCH(lu_schur_kernel, dim3(L.sc_count, nb), 256, sd->smem_schur, sd->dev, sd->sc_items.p + L.sc_begin, F);
+    }
+    NEPB_LAUNCH_CHECK();
+    return NEPB_OK;
+}
+
+// Solve for the shifts [shift0, shift0+nb): Bdev holds right-hand sides [b][n][k] row-major (rhs_stride = n*k) or one
+// shared block (rhs_stride = 0); Xdev [b][n][k].  Asynchronous on the library stream.
+int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev, size_t rhs_stride, double2* Xdev) {
+    LuSymbolicDev* sd = lu->sym;
+    const LuSymbolic& S = sd->S;
+    const int n = S.n;
+    NEPB_CHECK_ARG(shift0 >= 0 && nb >= 1 && shift0 + nb <= lu->nb, "shift window out of range");
+    NEPB_CHECK_ARG(k >= 1 && k <= 256, "number of right-hand sides per solve must be in 1..256 (k=%d)", k);
+    const size_t smem = (size_t)S.max_np * k * 16;
+    NEPB_CHECK_ARG(smem <= 200 * 1024, "k=%d right-hand sides with %d pivot columns per front exceed shared memory", k, S.max_np);
+    NEPB_CUDA(lu->xp.reserve((size_t)2 * nb * n * k));
+    NEPB_CUDA(lu->w.reserve((size_t)2 * nb * S.w_total * k));
+    double2* Xp = (double2*)lu->xp.p;
+    double2* W = (double2*)lu->w.p;
+    const double2* F = (const double2*)lu->fronts.p + (size_t)shift0 * S.front_total;
+    const int* piv = lu->piv.p + (size_t)shift0 * n;
+    dim3 pg((unsigned)(((size_t)n * k + 255) / 256), nb);
+    NEPB_LAUNCH(lu_permute_in_kernel, pg, 256, 0, n, k, sd->perm.p, Bdev, rhs_stride, Xp);
+    for (int l = 0; l < S.nlevels; ++l) {
+        const auto& L = sd->lv[l];
+        NEPB_LAUNCH(lu_forward_kernel, dim3(L.front_count, nb), 256, smem, sd->dev, sd->fr_items.p + L.front_begin, F, piv, Xp, W, k);
+    }
+    for (int l = S.nlevels - 1; l >= 0; --l) {
+        const auto& L = sd->lv[l];
+        NEPB_LAUNCH(lu_backward_kernel, dim3(L.front_count, nb), 256, smem, sd->dev, sd->fr_items.p + L.front_begin, F, Xp, k);
+    }
+    NEPB_LAUNCH(lu_permute_out_kernel, pg, 256, 0, n, k, sd->iperm.p, Xp, Xdev, (size_t)n * k);
+    NEPB_LAUNCH_CHECK();
+    return NEPB_OK;
+}
+
+int spmf_apply_device(const nepb_spmf* h, int mode, int k, int q, const double2* dV, const double* C, double2* dZ);
+int upload_colmajor(int64_t n, int kc, const double* host, int64_t ld, DevBuf<double>& stage, double* dst, int ldd, int k0);
+int download_colmajor(int64_t n, int kc, const double* src, int lds, int k0, DevBuf<double>& stage, double* host, int64_t ld);
+
+int lu_fetch_info(nepb_lu* lu) {
+    lu->h_info.resize(lu->nb);
+    NEPB_CUDA(cudaMemcpyAsync(lu->h_info.data(), lu->info.p, sizeof(LuInfo) * lu->nb, cudaMemcpyDeviceToHost, stream()));
+    NEPB_CUDA(cudaStreamSynchronize(stream()));
+    return NEPB_OK;
+}
+
+int lu_refactor(nepb_lu* lu, int nshift, const double* coef) {
+    NEPB_CHECK_ARG(nshift >= 1 && nshift <= lu->cap, "refactor: %d shifts exceed the capacity %d of this handle", nshift, lu->cap);
+    lu->nb = nshift;
+    lu->h_coef.assign(coef, coef + (size_t)2 * nshift * lu->op->p);
+    NEPB_CUDA(cudaStreamSynchronize(stream()));  // h_coef / h_info may still be read by an earlier async copy
+    NEPB_CUDA(cudaMemcpyAsync(lu->coef.p, lu->h_coef.data(), sizeof(double) * lu->h_coef.size(), cudaMemcpyHostToDevice, stream()));
+    return lu_factor_device(lu);
+}
+
+int lu_create(const nepb_spmf* h, int nshift, const double* coef, nepb_lu** out) {
+    *out = nullptr;
+    LuSymbolicDev* sd = nullptr;
+    int rc = lu_symbolic_get(h, &sd);
+    if (rc) return rc;
+    nepb_lu* lu = new nepb_lu();
+    lu->op = h;
+    lu->sym = sd;
+    lu->nb = lu->cap = nshift;
+    const LuSymbolic& S = sd->S;
+    cudaError_t e = lu->fronts.alloc((size_t)2 * nshift * S.front_total);
+    if (e == cudaSuccess) e = lu->piv.alloc((size_t)nshift * S.n);
+    if (e == cudaSuccess) e = lu->info.alloc(nshift);
+    if (e == cudaSuccess) e = lu->coef.alloc((size_t)2 * nshift * h->p);
+    if (e != cudaSuccess) {
+        set_error("allocating %d factorisations (%.1f MB each) failed: %s", nshift, S.front_total * 16e-6, cudaGetErrorString(e));
+        delete lu;
+        return e == cudaErrorMemoryAllocation ? NEPB_E_NOMEM : NEPB_E_CUDA;
+    }
+    rc = lu_refactor(lu, nshift, coef);
+    if (!rc) rc = lu_fetch_info(lu);
+    if (rc) {
+        delete lu;
+        return rc;
+    }
+    *out = lu;
+    return NEPB_OK;
+}
+
 }  // namespace nepb
+
+using namespace nepb;
+
+extern "C" {
+
+int nepb_lu_set_options(nepb_spmf* h, int ordering, int relax_leaf, int max_np, const int64_t* user_perm) {
+    NEPB_CHECK_ARG(h, "handle is NULL");
+    NEPB_CHECK_ARG(!h->lu_symbolic, "the symbolic analysis of this operator already exists; set options before the first factorisation");
+    h->lu_opt = LuOptions();
+    if (ordering >= 0) h->lu_opt.ordering = ordering;
+    if (relax_leaf > 0) h->lu_opt.relax_leaf = relax_leaf;
+    if (max_np > 0) h->lu_opt.max_np = max_np;
+    h->lu_opt_set = true;
+    h->lu_user_perm.clear();
+    if (user_perm) {
+        h->lu_user_perm.resize(h->n);
+        for (int64_t i = 0; i < h->n; ++i) h->lu_user_perm[i] = (int32_t)(user_perm[i] - h->index_base);
+    }
+    return NEPB_OK;
+}
+
+int nepb_lu_symbolic_info(const nepb_spmf* h, int64_t* nnz_factor, int64_t* front_entries, int* nfronts, int* nlevels, int* max_front,
+                          double* flops) {
+    NEPB_CHECK_ARG(h, "handle is NULL");
+    LuSymbolicDev* sd = nullptr;
+    int rc = lu_symbolic_get(h, &sd);
+    if (rc) return rc;
+    if (nnz_factor) *nnz_factor = sd->S.nnz_factor;
+    if (front_entries) *front_entries = sd->S.front_total;
+    if (nfronts) *nfronts = sd->S.nsuper;
+    if (nlevels) *nlevels = sd->S.nlevels;
+    if (max_front) *max_front = sd->S.max_nf;
+    if (flops) *flops = sd->S.flops;
+    return NEPB_OK;
+}
+
+int nepb_lu_symbolic_get(const nepb_spmf* h, int32_t* perm, int32_t* parent, int32_t* sn_ptr, int32_t* sn_parent) {
+    NEPB_CHECK_ARG(h, "handle is NULL");
+    LuSymbolicDev* sd = nullptr;
+    int rc = lu_symbolic_get(h, &sd);
+    if (rc) return rc;
+    const LuSymbolic& S = sd->S;
+    if (perm) memcpy(perm, S.perm.data(), sizeof(int32_t) * S.n);
+    if (parent) memcpy(parent, S.parent.data(), sizeof(int32_t) * S.n);
+    if (sn_ptr) memcpy(sn_ptr, S.sn_ptr.data(), sizeof(int32_t) * (S.nsuper + 1));
+    if (sn_parent) memcpy(sn_parent, S.sn_parent.data(), sizeof(int32_t) * S.nsuper);
+    return NEPB_OK;
+}
+
+int nepb_lu_analyse_pattern(int64_t n, const int64_t* colptr, const int64_t* rowval, int index_base, int ordering, int relax_leaf,
+                            int max_np, int32_t* perm, int32_t* parent, int32_t* colcount, double* stats) {
+    NEPB_CHECK_ARG(n >= 1 && n < ((int64_t)1 << 31) && colptr && rowval, "bad arguments");
+    const int64_t nnz = colptr[n] - index_base;
+    NEPB_CHECK_ARG(nnz >= 0 && nnz < ((int64_t)1 << 31), "pattern too large");
+    std::vector<int32_t> rp(n + 1), ci(nnz);
+    for (int64_t j = 0; j <= n; ++j) rp[j] = (int32_t)(colptr[j] - index_base);
+    for (int64_t e = 0; e < nnz; ++e) {
+        ci[e] = (int32_t)(rowval[e] - index_base);
+        NEPB_CHECK_ARG(ci[e] >= 0 && ci[e] < n, "index out of range");
+    }
+    LuOptions opt;
+    if (ordering >= 0) opt.ordering = ordering;
+    if (relax_leaf > 0) opt.relax_leaf = relax_leaf;
+    if (max_np > 0) opt.max_np = std::min(64, max_np);
+    LuSymbolic S;
+    // the analysis symmetrises the pattern, so CSC and CSR input are equivalent
+    int rc = lu_symbolic_analyse((int)n, rp.data(), ci.data(), nullptr, opt, S);
+    if (rc) return rc;
+    if (perm) memcpy(perm, S.perm.data(), sizeof(int32_t) * n);
+    if (parent) memcpy(parent, S.parent.data(), sizeof(int32_t) * n);
+    if (colcount) memcpy(colcount, S.colcount.data(), sizeof(int32_t) * n);
+    if (stats) {
+        stats[0] = (double)S.nnz_factor;
+        stats[1] = (double)S.front_total;
+        stats[2] = S.nsuper;
+        stats[3] = S.nlevels;
+        stats[4] = S.max_nf;
+        stats[5] = S.max_np;
+        stats[6] = S.flops;
+        stats[7] = (double)S.w_total;
+    }
+    return NEPB_OK;
+}
+
+int nepb_lu_create(const nepb_spmf* h, int nshift, const double* coef, nepb_lu** out) {
+    NEPB_CHECK_ARG(h && coef && out, "NULL argument");
+    NEPB_CHECK_ARG(nshift >= 1 && nshift <= 65535, "nshift must be in 1..65535");
+    return lu_create(h, nshift, coef, out);
+}
+
+int nepb_lu_destroy(nepb_lu* lu) {
+    delete lu;
+    return NEPB_OK;
+}
+
+int nepb_lu_status(const nepb_lu* lu, int shift, int* flags, int* nperturbed, double* min_pivot_ratio) {
+    NEPB_CHECK_ARG(lu && shift >= 0 && shift < lu->nb, "bad arguments");
+    const LuInfo& I = lu->h_info[shift];
+    if (flags) *flags = I.flags;
+    if (nperturbed) *nperturbed = I.nperturbed;
+    if (min_pivot_ratio) {
+        double r;
+        memcpy(&r, &I.minpiv_bits, 8);
+        *min_pivot_ratio = r;
+    }
+    return NEPB_OK;
+}
+
+// Solve M(sigma_shift) X = B on the host interface (lin_solve, LinSolvers.jl:135-137,157-159): B, X are n x nrhs column-major.
+// refine_steps > 0: iterative refinement with the fused SpMM residual (UMFPACK's control[8] in the reference); it stops
+// early once the normwise backward error max_c |r_c|_inf / (|M|_max |x_c|_inf + |b_c|_inf) is at rounding level or no
+// longer halves.  berr_out (optional) receives the final backward error (computed only when asked for or refining).
+int nepb_lu_solve(nepb_lu* lu, int shift, int nrhs, const double* B, int64_t ldb, double* X, int64_t ldx, int refine_steps,
+                  double* berr_out) {
+    NEPB_CHECK_ARG(lu && B && X, "NULL argument");
+    NEPB_CHECK_ARG(shift >= 0 && shift < lu->nb, "shift index %d out of range (0..%d)", shift, lu->nb - 1);
+    const nepb_spmf* h = lu->op;
+    const int64_t n = h->n;
+    NEPB_CHECK_ARG(nrhs >= 1 && ldb >= n && ldx >= n, "bad right-hand side shape");
+    if (lu->h_info[shift].flags & 2) {
+        set_error("non-finite pivot in the factorisation of shift %d", shift);
+        return NEPB_E_SINGULAR;
+    }
+    const int KC = 64;  // right-hand sides per pass
+    double worst = 0.0;
+    for (int c0 = 0; c0 < nrhs; c0 += KC) {
+        const int k = std::min(KC, nrhs - c0);
+        NEPB_CUDA(lu->rhs.reserve((size_t)2 * n * k));
+        NEPB_CUDA(lu->sol.reserve((size_t)2 * n * k));
+        int rc = upload_colmajor(n, k, B + 2 * (size_t)c0 * ldb, ldb, lu->stage, lu->rhs.p, k, 0);
+        if (rc) return rc;
+        rc = lu_solve_device(lu, shift, 1, k, (const double2*)lu->rhs.p, 0, (double2*)lu->sol.p);
+        if (rc) return rc;
+        if (refine_steps > 0 || berr_out) {
+            NEPB_CUDA(lu->res.reserve((size_t)2 * n * k));
+            NEPB_CUDA(lu->cor.reserve((size_t)2 * n * k));
+            NEPB_CUDA(lu->colmax.reserve(3 * 256));
+            const double* coef = lu->h_coef.data() + (size_t)2 * shift * h->p;
+            const size_t cnt = (size_t)n * k;
+            const unsigned gb = (unsigned)((cnt + 255) / 256);
+            double amax;
+            memcpy(&amax, &lu->h_info[shift].amax_bits, 8);
+            double prev = INFINITY, berr = 0.0;
+            for (int it = 0;; ++it) {
+                rc = spmf_apply_device(h, NEPB_COEF_SCALAR, k, k, (const double2*)lu->sol.p, coef, (double2*)lu->res.p);
+                if (rc) return rc;
+                NEPB_LAUNCH(residual_kernel, gb, 256, 0, cnt, (const double2*)lu->rhs.p, (double2*)lu->res.p);
+                NEPB_CUDA(cudaMemsetAsync(lu->colmax.p, 0, sizeof(unsigned long long) * 3 * 256, stream()));
+                NEPB_LAUNCH(colmax_kernel, gb, 256, 0, (int)n, k, (const double2*)lu->res.p, lu->colmax.p);
+                NEPB_LAUNCH(colmax_kernel, gb, 256, 0, (int)n, k, (const double2*)lu->sol.p, lu->colmax.p + 256);
+                NEPB_LAUNCH(colmax_kernel, gb, 256, 0, (int)n, k, (const double2*)lu->rhs.p, lu->colmax.p + 512);
+                NEPB_LAUNCH_CHECK();
+                unsigned long long hm[3 * 256];
+                NEPB_CUDA(cudaMemcpyAsync(hm, lu->colmax.p, sizeof(hm), cudaMemcpyDeviceToHost, stream()));
+                NEPB_CUDA(cudaStreamSynchronize(stream()));
+                berr = 0.0;
+                for (int c = 0; c < k; ++c) {
+                    double r, x, bb;
+                    memcpy(&r, &hm[c], 8);
+                    memcpy(&x, &hm[256 + c], 8);
+                    memcpy(&bb, &hm[512 + c], 8);
+                    const double den = amax * x + bb;
+                    berr = std::max(berr, den > 0 ? r / den : (r > 0 ? INFINITY : 0.0));
+                }
+                if (it >= refine_steps || berr <= 1.2e-16 || berr >= 0.5 * prev) break;
+                prev = berr;
+                rc = lu_solve_device(lu, shift, 1, k, (const double2*)lu->res.p, 0, (double2*)lu->cor.p);
+                if (rc) return rc;
+                NEPB_LAUNCH(axpy_kernel, gb, 256, 0, cnt, (const double2*)lu->cor.p, (double2*)lu->sol.p);
+            }
+            if (!(berr == berr)) {
+                set_error("solution of shift %d is not finite (singular matrix?)", shift);
+                return NEPB_E_SINGULAR;
+            }
+            worst = std::max(worst, berr);
+        }
+        rc = download_colmajor(n, k, lu->sol.p, k, 0, lu->stage, X + 2 * (size_t)c0 * ldx, ldx);
+        if (rc) return rc;
+    }
+    if (berr_out) *berr_out = worst;
+    return NEPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// Internal layouts shared by lu.cu and contour.cu.
+#pragma once
+#include <vector>
+
+#include "common.h"
+#include "lu_symbolic.h"
+
+namespace nepb {
+
+struct LuDev {  // passed by value to kernels
+    const int64_t* front_off;
+    const int32_t* nf;
+    const int32_t* np;
+    const int64_t* row_ptr;
+    const int32_t* rows;
+    const int64_t* rel_ptr;
+    const int32_t* rel;
+    const int32_t* sn_ptr;
+    const int64_t* w_off;
+    const int32_t* child_ptr;
+    const int32_t* child_list;
+    int64_t front_total, w_total;
+    int n;
+};
+
+struct LuInfo {
+    unsigned long long amax_bits;    // max |M_ij| (bits of a non-negative double)
+    unsigned long long minpiv_bits;  // min |pivot| / amax
+    int flags;                       // 1: exactly zero pivot met (perturbed), 2: non-finite pivot
+    int nperturbed;
+};
+
+struct LuLevel {
+    int front_begin = 0, front_count = 0;
+    int ea_begin = 0, ea_count = 0;
+    int pn_begin = 0, pn_count = 0;
+    int sc_begin = 0, sc_count = 0;
+};
+
+struct LuSymbolicDev {
+    LuSymbolic S;
+    LuDev dev;
+    std::vector<LuLevel> lv;
+    DevBuf<int64_t> front_off, row_ptr, rel_ptr, w_off, a_pos;
+    DevBuf<int32_t> nf, np, rows, rel, sn_ptr, child_ptr, child_list, perm, iperm, fr_items;
+    DevBuf<int4> ea_items, pn_items, sc_items;
+    size_t smem_diag = 0, smem_panel = 0, smem_schur = 0;
+};
+
+int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out);
+
+}  // namespace nepb
+
+struct nepb_lu {
+    const nepb_spmf* op = nullptr;
+    nepb::LuSymbolicDev* sym = nullptr;
+    int nb = 0;   // shifts currently factorised
+    int cap = 0;  // shifts the buffers can hold
+    nepb::DevBuf<double> fronts;  // [nb][front_total] complex
+    nepb::DevBuf<int> piv;        // [nb][n] local pivot rows
+    nepb::DevBuf<nepb::LuInfo> info;
+    nepb::DevBuf<double> coef;    // [nb][p] complex
+    std::vector<double> h_coef;
+    std::vector<nepb::LuInfo> h_info;
+    // scratch
+    nepb::DevBuf<double> xp, w, rhs, sol, res, cor, stage;
+    nepb::DevBuf<unsigned long long> colmax;
+};
+
+namespace nepb {
+int lu_create(const nepb_spmf* h, int nshift, const double* coef, nepb_lu** out);
+// factorise shifts already described by lu->coef (device); used by the contour loop to recycle the storage
+int lu_refactor(nepb_lu* lu, int nshift, const double* coef);
+// solve for shifts [shift0, shift0+nb): Bdev [b][n][k] (rhs_stride = n*k) or shared (0); Xdev [b][n][k]
+int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev, size_t rhs_stride, double2* Xdev);
+}  // namespace nepb

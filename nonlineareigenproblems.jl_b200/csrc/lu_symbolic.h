@@ -1,0 +1,48 @@
+// Host-side symbolic analysis for the device multifrontal LU (one per SPMF union pattern).
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+namespace nepb {
+
+struct LuSymbolic {
+    int n = 0;
+    int64_t nnz = 0;
+    // ordering: perm[new] = old, iperm[old] = new (fill-reducing ordering composed with the etree postorder)
+    std::vector<int32_t> perm, iperm;
+    std::vector<int32_t> parent;  // column elimination tree of the permuted pattern of A + A^T (-1 = root)
+    std::vector<int32_t> colcount;  // |struct(L_j)| including the diagonal
+    // supernodes = fronts
+    int nsuper = 0;
+    std::vector<int32_t> sn_ptr;     // [nsuper+1] first pivot column of each supernode
+    std::vector<int32_t> sn_parent;  // supernodal tree (-1 = root)
+    std::vector<int32_t> col_sn;     // [n] supernode of a permuted column
+    std::vector<int64_t> row_ptr;    // [nsuper+1] offsets into rows
+    std::vector<int32_t> rows;       // front row structure: np pivots first, then the update rows (ascending)
+    std::vector<int64_t> front_off;  // [nsuper+1] offsets (in complex elements) of the nf x nf fronts
+    std::vector<int64_t> rel_ptr;    // [nsuper+1] offsets into rel
+    std::vector<int32_t> rel;        // for the update rows of s: their position in the parent's row structure
+    std::vector<int32_t> level;      // [nsuper] height above the leaves
+    int nlevels = 0;
+    std::vector<int32_t> level_ptr, level_list;  // supernodes grouped by level
+    std::vector<int64_t> a_pos;      // [nnz] CSR nonzero -> offset in the front storage
+    std::vector<int64_t> w_off;      // [nsuper+1] offsets into the solve work vector (nf rows each)
+    int64_t front_total = 0, nnz_factor = 0, w_total = 0;
+    double flops = 0;  // complex multiply-adds of the numeric factorisation
+    int max_nf = 0, max_np = 0;
+};
+
+struct LuOptions {
+    int relax_leaf = 16;   // subtrees with at most this many columns become one supernode
+    int max_np = 32;       // cap on pivot columns per front (wider supernodes are split into chains)
+    int ordering = 0;      // 0 = approximate minimum degree on A + A^T, 1 = natural
+};
+
+// csr rowptr/colind of the n x n union pattern (0-based, int32); user_perm optional (perm[new] = old)
+int lu_symbolic_analyse(int n, const int32_t* rowptr, const int32_t* colind, const int32_t* user_perm,
+                        const LuOptions& opt, LuSymbolic& S);
+
+// approximate-minimum-degree ordering of the symmetric graph (adjacency without diagonal); out[new] = old
+void amd_order(int n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj, std::vector<int32_t>& out);
+
+}  // namespace nepb

@@ -1,0 +1,349 @@
+"""Solver loops that call the hot path through the plugin interface (host-side mirror of the callers).
+
+These follow the reference's drivers line by line on the host and route every heavy operation to the device:
+  contour_beyn   src/method_beyncontour.jl:49-185 + src/method_contour_common.jl:61-94 -- the N quadrature nodes go to
+                 nepb_contour_integrate in one call (batched factor + solve + accumulate, sharded over ranks)
+  iar            src/method_iar.jl:47-184     tiar   src/method_tiar.jl:53-257
+  resinv         src/method_newton.jl:142-226 (+ compute_rf, src/compute_rf_wrapper.jl:25-54)
+Small dense post-processing (eig of H, SVD of the k x k moments, sorting permutations) stays on the host as in the
+reference.  Exceptions mirror NEPCore.jl:324-350.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, ptr
+from .neptypes import B200SPMF
+from .linsolve import B200LinSolverCreator, B200BackslashLinSolverCreator
+
+
+class NoConvergenceException(Exception):
+    def __init__(self, lam, v, errmeasure, msg):
+        super().__init__(msg)
+        self.lam, self.v, self.errmeasure = lam, v, errmeasure
+
+
+class LostOrthogonalityException(Exception):
+    pass
+
+
+# ---------------------------------------------------------------------------------------------
+# error measures (errmeasure.jl:91-101,128-130,174-191)
+# ---------------------------------------------------------------------------------------------
+class ResidualErrmeasure:
+    def __init__(self, nep):
+        self.nep = nep
+
+    def estimate_error(self, lam, v):
+        return float(np.linalg.norm(self.nep.compute_Mlincomb(lam, v)) / np.linalg.norm(v))
+
+    def estimate_errors(self, lams, V):
+        return self.nep.residual_norms(lams, V)
+
+
+class StandardSPMFErrmeasure:
+    def __init__(self, nep):
+        import scipy.sparse as sp
+        self.nep = nep
+        self.coeffs = np.array([np.linalg.norm(A.data) if sp.issparse(A) else np.linalg.norm(A) for A in nep.get_Av()])
+
+    def _denom(self, lam):
+        return float(sum(c * abs(f(complex(lam))) for c, f in zip(self.coeffs, self.nep.get_fv())))
+
+    def estimate_error(self, lam, v):
+        return float(np.linalg.norm(self.nep.compute_Mlincomb(lam, v)) / (np.linalg.norm(v) * self._denom(lam)))
+
+    def estimate_errors(self, lams, V):
+        """All Ritz pairs in one multi-lambda SpMM instead of k SpMVs (method_iar.jl:134-135)."""
+        r = self.nep.residual_norms(lams, V)
+        return r / np.array([self._denom(l) for l in lams])
+
+
+def DefaultErrmeasure(nep):
+    return StandardSPMFErrmeasure(nep)
+
+
+def _errs(errmeasure, lams, Q):
+    if hasattr(errmeasure, "estimate_errors"):
+        return np.asarray(errmeasure.estimate_errors(lams, Q), dtype=float)
+    f = errmeasure.estimate_error if hasattr(errmeasure, "estimate_error") else errmeasure
+    return np.array([f(lams[s], Q[:, s]) for s in range(len(lams))], dtype=float)
+
+
+# ---------------------------------------------------------------------------------------------
+# contour integration
+# ---------------------------------------------------------------------------------------------
+class ContourIntegrator:
+    """The MatrixIntegrator seam (method_contour_common.jl:18-45) for B200 operators: all nodes in one device call."""
+
+    def __init__(self, nep: B200SPMF, k, mg=2, batch=32):
+        h = C.c_void_p()
+        check(lib.nepb_contour_create(nep._h, k, mg, batch, C.byref(h)))
+        self._h = h
+        self.nep, self.k, self.mg, self.batch = nep, k, mg, batch
+
+    def integrate(self, lams, weights, Vh, reduce=False):
+        """S[:,:,j] = sum_i weights[i,j] M(lams[i])^-1 Vh; returns (S (n,k,mg), node_flags)."""
+        lams = np.asarray(lams, dtype=np.complex128)
+        nn = len(lams)
+        coef = np.ascontiguousarray(np.stack([self.nep.coefficients(l) for l in lams])) if nn else np.zeros((0, self.nep.p), complex)
+        W = np.ascontiguousarray(np.asarray(weights, dtype=np.complex128).reshape(nn, self.mg))
+        Vh = _lib.as_c128_f(Vh)
+        S = np.empty((self.nep.n, self.k, self.mg), dtype=np.complex128, order="F")
+        flags = np.zeros(max(nn, 1), dtype=np.int32)
+        check(lib.nepb_contour_integrate(self._h, nn, ptr(coef), ptr(W), ptr(Vh), Vh.shape[0], 1 if reduce else 0, ptr(S), ptr(flags)))
+        return S, flags[:nn]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.nepb_contour_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def beyn_extract(A0, A1, sigma, radius, k, neigs, tol, rank_drop_tol, errmeasure, sanity_check):
+    """method_beyncontour.jl:113-184 (host, k x k sized work + the sorting / filtering permutations)."""
+    V, S, Wh = np.linalg.svd(A0, full_matrices=False)
+    p = int(np.count_nonzero(S / S[0] > rank_drop_tol))
+    V0, W0 = V[:, :p], Wh.conj().T[:, :p]
+    B = (V0.conj().T @ A1 @ W0) @ np.diag(1.0 / S[:p])
+    lam, VB = np.linalg.eig(B)
+    lam = lam + sigma
+    Vv = V0 @ VB
+    r1, r2 = radius
+    info = {"p": p, "S": S}
+
+    def inside_of(ls):
+        return ((ls - sigma).real / r1) ** 2 + ((ls - sigma).imag / r2) ** 2 <= 1
+
+    if not sanity_check:
+        si = np.argsort(np.abs(sigma - lam), kind="stable")
+        idx = si[np.argsort(~inside_of(lam[si]), kind="stable")]
+        return lam[idx], Vv[:, idx], info
+    errs = _errs(errmeasure, lam, Vv)
+    info["errs"] = errs
+    good = np.nonzero(errs < tol)[0]
+    sg = good[np.argsort(np.abs(sigma - lam[good]), kind="stable")]
+    idx = sg[np.argsort(~inside_of(lam[sg]), kind="stable")]
+    if len(idx) > neigs:
+        idx = idx[:neigs]
+    return lam[idx], Vv[:, idx], info
+
+
+def contour_beyn(nep: B200SPMF, Vh=None, sigma=0.0, radius=1.0, N=1000, neigs=2, k=None, tol=np.sqrt(np.finfo(float).eps),
+                 errmeasure=None, sanity_check=True, rank_drop_tol=None, batch=32, rank=0, world=1, integrator=None,
+                 return_moments=False, seed=10):
+    """contour_beyn for B200 operators.  rank/world shard the quadrature nodes (i = rank mod world); with world > 1 the
+    library communicator (nepb_comm_init) must exist and the moments are summed with one NCCL all-reduce."""
+    n = nep.n
+    k = neigs + 1 if k is None else k
+    if k > n:
+        raise ValueError("Cannot compute more eigenvalues than the size of the NEP with contour_beyn() k=%d n=%d" % (k, n))
+    if k <= 0:
+        raise ValueError("k must be positive, k=%d." % k)
+    radius = (radius, radius) if np.isscalar(radius) else tuple(radius)
+    rank_drop_tol = tol if rank_drop_tol is None else rank_drop_tol
+    if Vh is None:  # the reference draws randn(n,k) after Random.seed!(10); any fixed Gaussian probe is equivalent
+        Vh = np.random.default_rng(seed).standard_normal((n, k))
+    errmeasure = errmeasure or DefaultErrmeasure(nep)
+    h = 2 * np.pi / N
+    t = h * np.arange(N)
+    g = radius[0] * np.cos(t) + 1j * radius[1] * np.sin(t)
+    gp = -radius[0] * np.sin(t) + 1j * radius[1] * np.cos(t)
+    # weights: temp*G[i,j] with temp = X_i*gp_i, summed, times h, divided by 2 pi i (method_contour_common.jl:86-93, beyn :110-111)
+    W = np.stack([gp * h / (2j * np.pi), gp * g * h / (2j * np.pi)], axis=1)
+    mine = np.arange(rank, N, world)
+    own = integrator is None
+    integ = integrator or ContourIntegrator(nep, k, 2, min(batch, max(1, len(mine))))
+    try:
+        S, flags = integ.integrate(g[mine] + sigma, W[mine], Vh, reduce=world > 1)
+    finally:
+        if own:
+            integ.close()
+    if np.any(flags & 2):
+        raise _lib.SingularException(_lib.NEPB_E_SINGULAR, "non-finite pivot at a quadrature node: an eigenvalue lies on the contour")
+    A0, A1 = S[:, :, 0], S[:, :, 1]
+    lam, V, info = beyn_extract(A0, A1, sigma, radius, k, neigs, tol, rank_drop_tol, errmeasure, sanity_check)
+    info["node_flags"] = flags
+    if return_moments:
+        return lam, V, A0, A1, info
+    return lam, V
+
+
+# ---------------------------------------------------------------------------------------------
+# orthogonalisation (host reference implementation of the DGKS hook; the device version is in orth.py)
+# ---------------------------------------------------------------------------------------------
+def dgks_host(V, w, h):
+    h[:] = V.conj().T @ w
+    w -= V @ h
+    nrm = np.linalg.norm(w)
+    ps = np.linalg.norm(h)
+    while nrm < ps / np.sqrt(2.0):
+        c = V.conj().T @ w
+        ps = np.linalg.norm(c)
+        w -= V @ c
+        h += c
+        nrm = np.linalg.norm(w)
+    w *= 1.0 / nrm
+    return nrm
+
+
+# ---------------------------------------------------------------------------------------------
+# resinv
+# ---------------------------------------------------------------------------------------------
+def compute_rf(nep, x, y=None, lam=0.0, tol=np.finfo(float).eps * 100, maxit=80):
+    y = x if y is None else y
+    li = complex(lam)
+    dl, count = np.inf, 0
+    while abs(dl) > tol and count < maxit:
+        count += 1
+        z1 = nep.compute_Mlincomb(li, x.reshape(-1, 1))
+        z2 = nep.compute_Mlincomb(li, x.reshape(-1, 1), np.array([1.0]), 1)
+        dl = -np.vdot(y, z1) / np.vdot(y, z2)
+        li += dl
+    return li
+
+
+def resinv(nep, lam=0.0, v=None, c=None, tol=np.finfo(float).eps * 100, maxit=100, linsolvercreator=None, errmeasure=None):
+    n = nep.n
+    lam = complex(lam)
+    v = np.array(v, dtype=np.complex128)
+    c = v.copy() if c is None else np.array(c, dtype=np.complex128)
+    errmeasure = errmeasure or DefaultErrmeasure(nep)
+    linsolver = (linsolvercreator or B200LinSolverCreator()).create_linsolver(nep, lam)
+    use_v = np.linalg.norm(c) == 0
+    err = np.inf
+    for _ in range(maxit):
+        v = v / np.linalg.norm(v)
+        err = errmeasure.estimate_error(lam, v)
+        if use_v:
+            c = v.copy()
+        if err < tol:
+            return lam, v
+        lam1 = compute_rf(nep, v, y=c, lam=lam)
+        dv = -linsolver.lin_solve(nep.compute_Mlincomb(lam1, v.reshape(n, 1)))
+        lam, v = lam1, v + dv
+    raise NoConvergenceException(lam, v, err, "Number of iterations exceeded. maxit=%d." % maxit)
+
+
+# ---------------------------------------------------------------------------------------------
+# iar / tiar
+# ---------------------------------------------------------------------------------------------
+def iar(nep, maxit=30, linsolvercreator=None, tol=np.finfo(float).eps * 10000, neigs=6, errmeasure=None, sigma=0.0, gamma=1.0,
+        v=None, check_error_every=1, orthmethod=dgks_host):
+    n, m = nep.n, maxit
+    sigma = complex(sigma)
+    errmeasure = errmeasure or DefaultErrmeasure(nep)
+    V = np.zeros((n * (m + 1), m + 1), dtype=np.complex128, order="F")
+    H = np.zeros((m + 1, m), dtype=np.complex128)
+    y = np.zeros((n, m + 1), dtype=np.complex128, order="F")
+    alpha = np.asarray(gamma, dtype=np.complex128) ** np.arange(m + 1)
+    alpha[0] = 0
+    M0inv = (linsolvercreator or B200LinSolverCreator()).create_linsolver(nep, sigma)
+    err = np.full((m, m), np.nan)
+    lam = np.zeros(m + 1, dtype=np.complex128)
+    Q = np.zeros((n, m + 1), dtype=np.complex128)
+    v = np.random.default_rng(0).standard_normal(n) if v is None else np.asarray(v, dtype=np.complex128)
+    V[:n, 0] = v / np.linalg.norm(v)
+    k, conv_eig = 1, 0
+    while k <= m and conv_eig < neigs:
+        VV = V[:n * (k + 1), :k]
+        vv = V[:n * (k + 1), k]
+        y[:, 1:k + 1] = VV[:n * k, k - 1].reshape(n, k, order="F")
+        y[:, 1:k + 1] /= np.arange(1, k + 1)[None, :]
+        y[:, 0] = nep.compute_Mlincomb(sigma, y[:, :k + 1], alpha[:k + 1])
+        y[:, 0] = -M0inv.lin_solve(y[:, 0].copy())
+        vv[:] = y[:, :k + 1].reshape((k + 1) * n, order="F")
+        H[k, k - 1] = orthmethod(VV, vv, H[:k, k - 1])
+        if k % check_error_every == 0 or k == m:
+            D, Zm = np.linalg.eig(H[:k, :k])
+            Q = V[:n, :k] @ Zm
+            lam = sigma + gamma / D
+            e = _errs(errmeasure, lam, Q)
+            err[k - 1, :len(lam)] = e
+            conv_eig = int(np.count_nonzero(e < tol))
+            idx = np.argsort(err[k - 1, :k], kind="stable")
+            err[k - 1, :k] = err[k - 1, idx]
+            if k == m or conv_eig >= neigs:
+                nrof = int(min(len(lam), neigs))
+                Q = Q[:, idx[:len(lam)]]
+                lam = lam[idx[:nrof]]
+        k += 1
+    k -= 1
+    if conv_eig < neigs and neigs != np.inf:
+        raise NoConvergenceException(lam, Q, err[k - 1, :k], "Number of iterations exceeded. maxit=%d." % maxit)
+    lam = lam[:min(len(lam), conv_eig)]
+    Q = Q[:, :min(Q.shape[1], conv_eig)]
+    return lam, Q, V[:, :k]
+
+
+def tiar(nep, maxit=30, linsolvercreator=None, tol=np.finfo(float).eps * 10000, neigs=6, errmeasure=None, sigma=0.0, gamma=1.0,
+         v=None, check_error_every=1, orthmethod=dgks_host):
+    n, m = nep.n, maxit
+    if n < m:
+        raise LostOrthogonalityException("Loss of orthogonality in the matrix Z. The problem size is too small, use iar instead.")
+    sigma = complex(sigma)
+    errmeasure = errmeasure or DefaultErrmeasure(nep)
+    a = np.zeros((m + 1, m + 1, m + 1), dtype=np.complex128)
+    Z = np.zeros((n, m + 1), dtype=np.complex128, order="F")
+    t = np.zeros(m + 1, dtype=np.complex128)
+    H = np.zeros((m + 1, m), dtype=np.complex128)
+    y = np.zeros((n, m + 1), dtype=np.complex128, order="F")
+    alpha = np.asarray(gamma, dtype=np.complex128) ** np.arange(m + 1)
+    alpha[0] = 0
+    M0inv = (linsolvercreator or B200LinSolverCreator()).create_linsolver(nep, sigma)
+    err = np.full((m + 1, m + 1), np.nan)
+    lam = np.zeros(m + 1, dtype=np.complex128)
+    Q = np.zeros((n, m + 1), dtype=np.complex128)
+    v = np.random.default_rng(0).standard_normal(n) if v is None else np.asarray(v, dtype=np.complex128)
+    Z[:, 0] = v / np.linalg.norm(v)
+    a[0, 0, 0] = 1
+    hist = np.zeros(m + 1, dtype=int)
+    k, conv_eig = 1, 0
+    while k <= m and conv_eig < neigs:
+        y[:, 1:k + 1] = Z[:, :k] @ a[:k, k - 1, :k].T
+        y[:, 1:k + 1] /= np.arange(1, k + 1)[None, :]
+        y[:, 0] = nep.compute_Mlincomb(sigma, y[:, :k + 1], alpha[:k + 1])
+        y[:, 0] = -M0inv.lin_solve(y[:, 0].copy())
+        Z[:, k] = y[:, 0]
+        t[k] = orthmethod(Z[:, :k], Z[:, k], t[:k])
+        g = np.zeros((k + 1, k + 1), dtype=np.complex128)
+        g[1:, :] = a[:k, k - 1, :k + 1] / np.arange(1, k + 1)[:, None]
+        g[0, :] = t[:k + 1]
+        h = np.einsum("ijl,il->j", a[:k, :k, :k].conj(), g[:k, :k])
+        f = g
+        f[:, :k] -= np.einsum("ijl,j->il", a[:k + 1, :k, :k], h)
+        hh = np.einsum("ijl,il->j", a[:k, :k, :k].conj(), f[:k, :k])
+        f[:, :k] -= np.einsum("ijl,j->il", a[:k + 1, :k, :k], hh)
+        h = h + hh
+        beta = np.linalg.norm(f)
+        H[:k, k - 1] = h
+        H[k, k - 1] = beta
+        a[:k + 1, k, :k + 1] = f / beta
+        if k % check_error_every == 0 or k == m:
+            D, W = np.linalg.eig(H[:k, :k])
+            VV = Z[:, :k] @ a[0, :k, :k].T
+            Q = VV @ W
+            lam = sigma + gamma / D
+            e = _errs(errmeasure, lam, Q)
+            err[k - 1, :len(lam)] = e
+            conv_eig = int(np.count_nonzero(e < tol))
+            idx = np.argsort(err[k - 1, :k], kind="stable")
+            err[k - 1, :k] = err[k - 1, idx]
+            if k == m or conv_eig >= neigs:
+                nrof = int(min(len(lam), neigs))
+                lam = lam[idx[:nrof]]
+                Q = Q[:, idx[:nrof]]
+            hist[k - 1] = conv_eig
+        k += 1
+    k -= 1
+    if conv_eig < neigs and neigs != np.inf:
+        raise NoConvergenceException(lam, Q, err[k - 1], "Number of iterations exceeded. maxit=%d." % maxit)
+    lam = lam[:min(len(lam), conv_eig)]
+    Q = Q[:, :min(Q.shape[1], conv_eig)]
+    return lam, Q, Z[:, :k], hist

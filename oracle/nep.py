@@ -43,10 +43,43 @@ def f_pow(j):
     return f
 
 
+def _jordan_like(S):
+    """True when S = lam*I + (strictly lower bidiagonal): the only matrices compute_Mlincomb / DerSPMF feed to f_i
+    (NEPTypes.jl:993, :1117-1121).  For those f(S) = sum_d t_d N^d exactly (N nilpotent), t_d the Taylor coefficients."""
+    k = S.shape[0]
+    if k < 2:
+        return False
+    d = np.diag(S)
+    if np.any(d != d[0]):
+        return False
+    R = S - np.diag(d) - np.diag(np.diag(S, -1), -1)
+    return not np.any(R)
+
+
+def _fun_of_jordan_like(S, t0, ratio):
+    """f(S) for S = lam*I + subdiag(s): entry (i, i-d) = t_d * prod_{l=i-d+1..i} s_l, built from the Taylor ratios
+    rho_d = t_d / t_{d-1} so that no intermediate under/overflows (same quantity the reference obtains from its
+    generic matrix function; checked against sqrtm/expm at small sizes in tests/test_oracle_golden.py)."""
+    k = S.shape[0]
+    s = np.diag(S, -1).astype(np.complex128)
+    F = np.zeros((k, k), dtype=np.complex128)
+    for i in range(k):
+        e = t0
+        F[i, i] = e
+        for d in range(1, i + 1):
+            e = e * ratio(d) * s[i - d]
+            F[i, i - d] = e
+    return F
+
+
 def f_exp(c):
     """S -> exp(c*S)."""
     def f(S):
-        return sla.expm(c * S) if _is_mat(S) else np.exp(c * S)
+        if _is_mat(S):
+            if _jordan_like(S) and S.shape[0] > 6:
+                return _fun_of_jordan_like(S, np.exp(c * S[0, 0]), lambda d: c / d)
+            return sla.expm(c * S)
+        return np.exp(c * S)
     return f
 
 
@@ -54,6 +87,9 @@ def f_isqrt_shift(c):
     """S -> 1im*sqrt(S - c*I): the gun nonlinearities (NLEVP_native.jl:13-14), principal branch."""
     def f(S):
         if _is_mat(S):
+            if _jordan_like(S) and S.shape[0] > 6:
+                z = complex(S[0, 0]) - c
+                return _fun_of_jordan_like(S, 1j * np.sqrt(z), lambda d: (0.5 - d + 1) / (d * z))
             return 1j * sla.sqrtm(S.astype(np.complex128) - c * np.eye(S.shape[0]))
         return 1j * np.sqrt(complex(S) - c)
     return f

@@ -1,0 +1,351 @@
+"""Oracle: linear solves, contour integration and the solver loops that call the hot path
+(test infrastructure, see oracle/__init__.py).
+
+NumPy/SciPy restatement of
+  * src/LinSolvers.jl:109-159 (FactorizeLinSolver / BackslashLinSolver) with SciPy's SuperLU standing in for
+    UMFPACK (third-party in the reference: SuiteSparse_jll 5.10.1; parity pinned at the solution level only,
+    test/linsolver.jl:21-68),
+  * src/method_contour_common.jl:61-94 (integrate_interval, MatrixTrapezoidal),
+  * src/method_beyncontour.jl:49-185 (contour_beyn),
+  * src/method_iar.jl:47-184 (iar), src/method_tiar.jl:53-257 (tiar),
+  * src/method_newton.jl:142-226 (resinv) with src/compute_rf_wrapper.jl:25-54 (scalar Newton Rayleigh functional),
+  * IterativeSolvers 0.9.2 `orthogonalize_and_normalize!(V, w, h, DGKS)` (third-party, restated from its published
+    algorithm: classical Gram-Schmidt, re-orthogonalise while ||w|| < ||h||/sqrt(2)).
+The Beyn probe matrix is an argument: the reference draws it with Julia's randn after Random.seed!(10)
+(method_beyncontour.jl:85-86), which cannot be reproduced outside Julia ("parity unpinned" for that draw).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as sla
+
+from . import nep as o
+
+
+class NoConvergenceException(Exception):
+    def __init__(self, lam, v, errmeasure, msg):
+        super().__init__(msg)
+        self.lam, self.v, self.errmeasure = lam, v, errmeasure
+
+
+class LostOrthogonalityException(Exception):
+    pass
+
+
+# --------------------------------------------------------------------------------------------
+# linear solvers
+# --------------------------------------------------------------------------------------------
+class FactorizeLinSolver:
+    def __init__(self, nep, lam):
+        M = o.compute_Mder(nep, lam)
+        if sp.issparse(M):
+            self.lu = sla.splu(sp.csc_matrix(M, dtype=np.complex128))
+            self.solve = self.lu.solve
+        else:
+            import scipy.linalg as L
+            lu = L.lu_factor(np.asarray(M, dtype=np.complex128))
+            self.solve = lambda b: L.lu_solve(lu, b)
+
+    def lin_solve(self, b, tol=0):
+        return self.solve(np.asarray(b, dtype=np.complex128))
+
+
+class BackslashLinSolver:
+    def __init__(self, nep, lam):
+        self.nep, self.lam = nep, lam
+
+    def lin_solve(self, b, tol=0):
+        return FactorizeLinSolver(self.nep, self.lam).lin_solve(b)
+
+
+class FactorizeLinSolverCreator:
+    def create_linsolver(self, nep, lam):
+        return FactorizeLinSolver(nep, lam)
+
+
+class BackslashLinSolverCreator:
+    def create_linsolver(self, nep, lam):
+        return BackslashLinSolver(nep, lam)
+
+
+# --------------------------------------------------------------------------------------------
+# orthogonalisation (IterativeSolvers DGKS)
+# --------------------------------------------------------------------------------------------
+def orthogonalize_and_normalize_dgks(V, w, h):
+    """In place on w and h; returns the norm.  V: (rows x k), w: rows, h: k."""
+    h[:] = V.conj().T @ w
+    w -= V @ h
+    nrm = np.linalg.norm(w)
+    eta = 1.0 / np.sqrt(2.0)
+    projection_size = np.linalg.norm(h)
+    while nrm < eta * projection_size:
+        correction = V.conj().T @ w
+        projection_size = np.linalg.norm(correction)
+        w -= V @ correction
+        h += correction
+        nrm = np.linalg.norm(w)
+    w *= 1.0 / nrm
+    return nrm
+
+
+# --------------------------------------------------------------------------------------------
+# error measures
+# --------------------------------------------------------------------------------------------
+def default_errmeasure(nep):
+    """errmeasure.jl:91-101: StandardSPMFErrmeasure for AbstractSPMF, otherwise the residual."""
+    if isinstance(nep, (o.SPMF_NEP, o.PEP, o.DEP, o.SumNEP, o.DerSPMF)):
+        return o.standard_spmf_errmeasure(nep)
+    return o.residual_errmeasure(nep)
+
+
+# --------------------------------------------------------------------------------------------
+# contour integration
+# --------------------------------------------------------------------------------------------
+def integrate_interval_trapezoidal(f, gv, a, b, N):
+    """method_contour_common.jl:61-94."""
+    h = (b - a) / N
+    t = a + h * np.arange(N)
+    f1 = f(t[0])
+    m = len(gv)
+    S = np.zeros(f1.shape + (m,), dtype=np.complex128)
+    G = np.zeros((N, m), dtype=np.complex128)
+    for j in range(m):
+        G[:, j] = [gv[j](tt) for tt in t]
+    for i in range(N):
+        temp = f1 if i == 0 else f(t[i])
+        for j in range(m):
+            S[:, :, j] += temp * G[i, j]
+    return S * h
+
+
+def beyn_extract(A0, A1, sigma, radius, k, neigs, tol, rank_drop_tol, errmeasure, sanity_check):
+    """method_beyncontour.jl:113-184: SVD rank decision, B matrix, eigenpairs, filtering / sorting."""
+    V, S, Wh = np.linalg.svd(A0, full_matrices=False)
+    W = Wh.conj().T
+    p = int(np.count_nonzero(S / S[0] > rank_drop_tol))
+    V0, W0 = V[:, :p], W[:, :p]
+    B = (V0.conj().T @ A1 @ W0) @ np.diag(1.0 / S[:p])
+    lam, VB = np.linalg.eig(B)
+    lam = lam + sigma
+    Vv = V0 @ VB  # note: the reference's normalize! acts on a copy (:129-131), the columns stay as they are
+    r1, r2 = radius
+    if not sanity_check:
+        sorted_index = np.argsort(np.abs(sigma - lam), kind="stable")
+        ls = lam[sorted_index]
+        inside = ((ls - sigma).real / r1) ** 2 + ((ls - sigma).imag / r2) ** 2 <= 1
+        inside_perm = np.argsort(~inside, kind="stable")
+        idx = sorted_index[inside_perm]
+        return lam[idx], Vv[:, idx], {"p": p, "S": S}
+    errs = np.array([errmeasure(lam[i], Vv[:, i]) for i in range(p)])
+    good = np.nonzero(errs < tol)[0]
+    sorted_good = good[np.argsort(np.abs(sigma - lam[good]), kind="stable")]
+    ls = lam[sorted_good]
+    inside = ((ls - sigma).real / r1) ** 2 + ((ls - sigma).imag / r2) ** 2 <= 1
+    perm = np.argsort(~inside, kind="stable")
+    idx = sorted_good[perm]
+    if len(idx) > neigs:
+        idx = idx[:neigs]
+    return lam[idx], Vv[:, idx], {"p": p, "S": S, "errs": errs}
+
+
+def contour_beyn(nep, Vh, sigma=0.0, radius=1.0, N=1000, neigs=2, k=None, tol=np.sqrt(np.finfo(float).eps),
+                 linsolvercreator=None, errmeasure=None, sanity_check=True, rank_drop_tol=None, return_moments=False):
+    """method_beyncontour.jl:49-185 with the probe matrix Vh (n x k) supplied by the caller."""
+    n = nep.n
+    k = neigs + 1 if k is None else k
+    if k > n:
+        raise ValueError("Cannot compute more eigenvalues than the size of the NEP with contour_beyn() k=%d n=%d" % (k, n))
+    if k <= 0:
+        raise ValueError("k must be positive, k=%d." % k)
+    radius = (radius, radius) if np.isscalar(radius) else tuple(radius)
+    rank_drop_tol = tol if rank_drop_tol is None else rank_drop_tol
+    creator = linsolvercreator or BackslashLinSolverCreator()
+    errmeasure = errmeasure or default_errmeasure(nep)
+    Vh = np.asarray(Vh, dtype=np.complex128)
+    g = lambda t: complex(radius[0] * np.cos(t), radius[1] * np.sin(t))
+    gp = lambda t: complex(-radius[0] * np.sin(t), radius[1] * np.cos(t))
+
+    def f(t):
+        M0inv = creator.create_linsolver(nep, g(t) + sigma)
+        return M0inv.lin_solve(Vh) * gp(t)
+
+    AA = integrate_interval_trapezoidal(f, [lambda s: 1.0 + 0j, g], 0.0, 2 * np.pi, N)
+    A0 = AA[:, :, 0] / (2j * np.pi)
+    A1 = AA[:, :, 1] / (2j * np.pi)
+    lam, V, info = beyn_extract(A0, A1, sigma, radius, k, neigs, tol, rank_drop_tol, errmeasure, sanity_check)
+    if return_moments:
+        return lam, V, A0, A1, info
+    return lam, V
+
+
+# --------------------------------------------------------------------------------------------
+# resinv
+# --------------------------------------------------------------------------------------------
+def compute_rf_scalar_newton(nep, x, y=None, lam=0.0, tol=np.finfo(float).eps * 100, maxit=80):
+    """compute_rf_wrapper.jl:25-54."""
+    y = x if y is None else y
+    lam_iter = complex(lam)
+    dl = np.inf
+    count = 0
+    while abs(dl) > tol and count < maxit:
+        count += 1
+        z1 = o.compute_Mlincomb(nep, lam_iter, x.reshape(-1, 1))
+        z2 = o.compute_Mlincomb(nep, lam_iter, x.reshape(-1, 1), np.array([1.0]), startder=1)
+        dl = -np.vdot(y, z1) / np.vdot(y, z2)
+        lam_iter += dl
+    return lam_iter
+
+
+def resinv(nep, lam=0.0, v=None, c=None, tol=np.finfo(float).eps * 100, maxit=100, linsolvercreator=None, errmeasure=None):
+    """method_newton.jl:142-226 (armijo_factor = 1: no line search)."""
+    n = nep.n
+    lam = complex(lam)
+    v = np.array(v, dtype=np.complex128)
+    c = v.copy() if c is None else np.array(c, dtype=np.complex128)
+    errmeasure = errmeasure or default_errmeasure(nep)
+    linsolver = (linsolvercreator or FactorizeLinSolverCreator()).create_linsolver(nep, lam)
+    use_v = np.linalg.norm(c) == 0
+    err = np.inf
+    for k in range(maxit):
+        v = v / np.linalg.norm(v)
+        err = errmeasure(lam, v)
+        if use_v:
+            c = v.copy()
+        if err < tol:
+            return lam, v
+        lam1 = compute_rf_scalar_newton(nep, v, y=c, lam=lam)
+        dlam = lam1 - lam
+        dv = -linsolver.lin_solve(o.compute_Mlincomb(nep, lam1, v.reshape(n, 1)))
+        lam = lam + dlam
+        v = v + dv
+    raise NoConvergenceException(lam, v, err, "Number of iterations exceeded. maxit=%d." % maxit)
+
+
+# --------------------------------------------------------------------------------------------
+# iar
+# --------------------------------------------------------------------------------------------
+def iar(nep, maxit=30, linsolvercreator=None, tol=np.finfo(float).eps * 10000, neigs=6, errmeasure=None, sigma=0.0, gamma=1.0,
+        v=None, check_error_every=1, orth=orthogonalize_and_normalize_dgks):
+    """method_iar.jl:47-184 without proj_solve."""
+    n, m = nep.n, maxit
+    sigma = complex(sigma)
+    errmeasure = errmeasure or default_errmeasure(nep)
+    V = np.zeros((n * (m + 1), m + 1), dtype=np.complex128, order="F")
+    H = np.zeros((m + 1, m), dtype=np.complex128)
+    y = np.zeros((n, m + 1), dtype=np.complex128, order="F")
+    alpha = np.asarray(gamma, dtype=np.complex128) ** np.arange(m + 1)
+    alpha[0] = 0
+    M0inv = (linsolvercreator or FactorizeLinSolverCreator()).create_linsolver(nep, sigma)
+    err = np.full((m, m), np.nan)
+    lam = np.zeros(m + 1, dtype=np.complex128)
+    Q = np.zeros((n, m + 1), dtype=np.complex128)
+    v = np.asarray(v, dtype=np.complex128)
+    V[:n, 0] = v / np.linalg.norm(v)
+    k, conv_eig = 1, 0
+    while k <= m and conv_eig < neigs:
+        VV = V[:n * (k + 1), :k]
+        vv = V[:n * (k + 1), k]
+        y[:, 1:k + 1] = VV[:n * k, k - 1].reshape(n, k, order="F")
+        y[:, 1:k + 1] /= np.arange(1, k + 1)[None, :]
+        y[:, 0] = o.compute_Mlincomb(nep, sigma, y[:, :k + 1], alpha[:k + 1])
+        y[:, 0] = -M0inv.lin_solve(y[:, 0].copy())
+        vv[:] = y[:, :k + 1].reshape((k + 1) * n, order="F")
+        H[k, k - 1] = orth(VV, vv, H[:k, k - 1])
+        if k % check_error_every == 0 or k == m:
+            D, Z = np.linalg.eig(H[:k, :k])
+            Q = V[:n, :k] @ Z
+            lam = sigma + gamma / D
+            conv_eig = 0
+            err[k - 1, :len(lam)] = [errmeasure(lam[s], Q[:, s]) for s in range(len(lam))]
+            conv_eig = int(np.count_nonzero(err[k - 1, :len(lam)] < tol))
+            idx = np.argsort(err[k - 1, :k], kind="stable")
+            err[k - 1, :k] = err[k - 1, idx]
+            if k == m or conv_eig >= neigs:
+                nrof = int(min(len(lam), neigs))
+                Q = Q[:, idx[:len(lam)]]
+                lam = lam[idx[:nrof]]
+        k += 1
+    k -= 1
+    if conv_eig < neigs and neigs != np.inf:
+        raise NoConvergenceException(lam, Q, err[k - 1, :k], "Number of iterations exceeded. maxit=%d." % maxit)
+    lam = lam[:min(len(lam), conv_eig)]
+    Q = Q[:, :min(Q.shape[1], conv_eig)]
+    return lam, Q, V[:, :k]
+
+
+# --------------------------------------------------------------------------------------------
+# tiar
+# --------------------------------------------------------------------------------------------
+def tiar(nep, maxit=30, linsolvercreator=None, tol=np.finfo(float).eps * 10000, neigs=6, errmeasure=None, sigma=0.0, gamma=1.0,
+         v=None, check_error_every=1, orth=orthogonalize_and_normalize_dgks):
+    """method_tiar.jl:53-257 without proj_solve.  Index translation: Julia a[i,j,l] == a[i-1,j-1,l-1] here."""
+    n, m = nep.n, maxit
+    if n < m:
+        raise LostOrthogonalityException("Loss of orthogonality in the matrix Z. The problem size is too small, use iar instead.")
+    sigma = complex(sigma)
+    errmeasure = errmeasure or default_errmeasure(nep)
+    a = np.zeros((m + 1, m + 1, m + 1), dtype=np.complex128)
+    Z = np.zeros((n, m + 1), dtype=np.complex128, order="F")
+    t = np.zeros(m + 1, dtype=np.complex128)
+    H = np.zeros((m + 1, m), dtype=np.complex128)
+    y = np.zeros((n, m + 1), dtype=np.complex128, order="F")
+    alpha = np.asarray(gamma, dtype=np.complex128) ** np.arange(m + 1)
+    alpha[0] = 0
+    M0inv = (linsolvercreator or FactorizeLinSolverCreator()).create_linsolver(nep, sigma)
+    err = np.full((m + 1, m + 1), np.nan)
+    lam = np.zeros(m + 1, dtype=np.complex128)
+    Q = np.zeros((n, m + 1), dtype=np.complex128)
+    v = np.asarray(v, dtype=np.complex128)
+    Z[:, 0] = v / np.linalg.norm(v)
+    a[0, 0, 0] = 1
+    conv_hist = np.zeros(m + 1, dtype=int)
+    k, conv_eig = 1, 0
+    while k <= m and conv_eig < neigs:
+        y[:, 1:k + 1] = Z[:, :k] @ a[:k, k - 1, :k].T
+        y[:, 1:k + 1] /= np.arange(1, k + 1)[None, :]
+        y[:, 0] = o.compute_Mlincomb(nep, sigma, y[:, :k + 1], alpha[:k + 1])
+        y[:, 0] = -M0inv.lin_solve(y[:, 0].copy())
+        Z[:, k] = y[:, 0]
+        t[k] = orth(Z[:, :k], Z[:, k], t[:k])
+        g = np.zeros((k + 1, k + 1), dtype=np.complex128)
+        for l in range(k + 1):
+            g[1:k + 1, l] = a[:k, k - 1, l] / np.arange(1, k + 1)
+            g[0, l] = t[l]
+        h = np.zeros(k, dtype=np.complex128)
+        for l in range(k):
+            h += a[:k, :k, l].conj().T @ g[:k, l]
+        f = g
+        for l in range(k):
+            f[:k + 1, l] -= a[:k + 1, :k, l] @ h
+        hh = np.zeros(k, dtype=np.complex128)
+        for l in range(k):
+            hh += a[:k, :k, l].conj().T @ f[:k, l]
+        for l in range(k):
+            f[:k + 1, l] -= a[:k + 1, :k, l] @ hh
+        h = h + hh
+        beta = np.linalg.norm(f[:k + 1, :k + 1])
+        H[:k, k - 1] = h
+        H[k, k - 1] = beta
+        a[:k + 1, k, :k + 1] = f[:k + 1, :k + 1] / beta
+        if k % check_error_every == 0 or k == m:
+            D, W = np.linalg.eig(H[:k, :k])
+            VV = Z[:, :k] @ a[0, :k, :k].T
+            Q = VV @ W
+            lam = sigma + gamma / D
+            err[k - 1, :len(lam)] = [errmeasure(lam[s], Q[:, s]) for s in range(len(lam))]
+            conv_eig = int(np.count_nonzero(err[k - 1, :len(lam)] < tol))
+            idx = np.argsort(err[k - 1, :k], kind="stable")
+            err[k - 1, :k] = err[k - 1, idx]
+            if k == m or conv_eig >= neigs:
+                nrof = int(min(len(lam), neigs))
+                lam = lam[idx[:nrof]]
+                Q = Q[:, idx[:nrof]]
+            conv_hist[k - 1] = conv_eig
+        k += 1
+    k -= 1
+    if conv_eig < neigs and neigs != np.inf:
+        raise NoConvergenceException(lam, Q, err[k - 1], "Number of iterations exceeded. maxit=%d." % maxit)
+    lam = lam[:min(len(lam), conv_eig)]
+    Q = Q[:, :min(Q.shape[1], conv_eig)]
+    return lam, Q, Z[:, :k], conv_hist

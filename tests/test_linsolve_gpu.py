@@ -1,0 +1,156 @@
+"""Device LU + triangular solves behind the LinSolver plugin interface, against the CPU oracle (SuperLU).
+Mirrors test/linsolver.jl:11-94 and test/rk_helper/cached_lin_solver.jl:8-37 of the reference."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as sla
+
+import nepb200
+from nepb200 import B200SPMF, ONE, IDENTITY, PowShift, Monomial, Exp
+from oracle import gallery as g
+from oracle import nep as o
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+def gun_pair():
+    K, M, W1, W2 = g.load_gun_matrices()
+    onep = o.nep_gallery("nlevp_native_gun")
+    dnep = B200SPMF([K, -M, W1, W2], [ONE, IDENTITY, PowShift(0.5, 0.0, 1j), PowShift(0.5, 108.8774 ** 2, 1j)])
+    return onep, dnep
+
+
+def test_gun_factorize_and_backslash_agree_with_oracle():
+    # test/linsolver.jl:11-68: lambda = 250^2 + 1im, x = ones(n)
+    onep, dnep = gun_pair()
+    lam = 250.0 ** 2 + 1j
+    Mo = sp.csc_matrix(o.compute_Mder(onep, lam))
+    n = dnep.n
+    b = np.ones(n, dtype=complex)
+    xo = sla.splu(Mo).solve(b)
+    norm1 = abs(Mo).sum(axis=0).max()
+    fs = nepb200.B200LinSolverCreator().create_linsolver(dnep, lam)
+    bs = nepb200.B200BackslashLinSolverCreator().create_linsolver(dnep, lam)
+    x1 = fs.lin_solve(b)
+    x2 = bs.lin_solve(b)
+    for x in (x1, x2):
+        assert np.linalg.norm(Mo @ x - b) / norm1 < EPS  # the reference's own criterion
+        assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-10
+    assert fs.status["flags"] == 0 and fs.status["nperturbed"] == 0
+    # matrix right-hand side (method_beyncontour.jl:90-93)
+    rng = np.random.default_rng(0)
+    B = rng.standard_normal((n, 20)) + 1j * rng.standard_normal((n, 20))
+    X = fs.lin_solve(B)
+    assert X.shape == (n, 20)
+    assert np.linalg.norm(Mo @ X - B) / (norm1 * np.linalg.norm(X)) < 10 * EPS
+    assert np.linalg.norm(X - sla.splu(Mo).solve(B)) / np.linalg.norm(X) < 1e-10
+
+
+def test_refinement_steps():
+    # test/linsolver.jl:77-94: refinements 0 vs default
+    onep, dnep = gun_pair()
+    lam = 150.0 ** 2 + 2j
+    Mo = sp.csc_matrix(o.compute_Mder(onep, lam))
+    b = np.arange(1.0, dnep.n + 1) + 0j
+    s0 = nepb200.B200FactorizeLinSolver(dnep, lam, umfpack_refinements=0)
+    s10 = nepb200.B200FactorizeLinSolver(dnep, lam, umfpack_refinements=10)
+    x0, x10 = s0.lin_solve(b), s10.lin_solve(b)
+    r0 = np.linalg.norm(Mo @ x0 - b) / np.linalg.norm(b)
+    r10 = np.linalg.norm(Mo @ x10 - b) / np.linalg.norm(b)
+    assert r0 < 1e-10 and r10 <= r0 * 1.5
+    assert s10.lu.last_berr < 1e-15
+
+
+def test_batched_shifts_match_single():
+    onep, dnep = gun_pair()
+    lams = 150.0 ** 2 + 500.0 * np.exp(2j * np.pi * np.arange(5) / 5)
+    lu = nepb200.B200LU(dnep, lams)
+    rng = np.random.default_rng(1)
+    B = rng.standard_normal((dnep.n, 3)) + 0j
+    for s, lam in enumerate(lams):
+        Mo = sp.csc_matrix(o.compute_Mder(onep, lam))
+        X = lu.solve(B, shift=s)
+        assert np.linalg.norm(Mo @ X - B) / (abs(Mo).sum(axis=0).max() * np.linalg.norm(X)) < 10 * EPS
+        single = nepb200.B200LU(dnep, [lam])
+        assert np.array_equal(single.solve(B), X)  # batch membership must not change a single bit
+
+
+def test_dense_dep0_and_pivoting():
+    # config C1: dense 5x5 (one front, full partial pivoting) and a matrix that needs row exchanges
+    A0, A1, tauv = g.dep0_matrices(5)
+    dnep = B200SPMF.from_nep(nepb200.DEP([A0, A1], tauv))
+    onep = o.nep_gallery("dep0")
+    lam = -0.2 + 0.1j
+    Mo = o.compute_Mder(onep, lam)
+    b = np.ones(5)
+    x = nepb200.B200LinSolverCreator().create_linsolver(dnep, lam).lin_solve(b)
+    assert np.linalg.norm(Mo @ x - b) < 1e-14
+    P = sp.csc_matrix(np.array([[0.0, 2.0, 0.0], [1.0, 0.0, 3.0], [0.0, 4.0, 1e-3]]))
+    d = B200SPMF([P], [ONE])
+    x = nepb200.B200FactorizeLinSolver(d, 0.0).lin_solve(np.array([1.0, 2.0, 3.0]))
+    assert np.linalg.norm(P @ x - [1.0, 2.0, 3.0]) < 1e-13
+
+
+def test_qdep0_unsymmetric_sparse():
+    A0, A1 = g.load_qdep0_matrices()
+    n = A0.shape[0]
+    onep = o.nep_gallery("qdep0")
+    dnep = B200SPMF([-sp.identity(n, format="csc"), A0, A1], [Monomial(2), ONE, Exp(-1.0)])
+    lam = -1.0 + 0.2j
+    Mo = sp.csc_matrix(o.compute_Mder(onep, lam))
+    rng = np.random.default_rng(2)
+    B = rng.standard_normal((n, 4)) + 1j * rng.standard_normal((n, 4))
+    X = nepb200.B200FactorizeLinSolver(dnep, lam).lin_solve(B)
+    assert np.linalg.norm(Mo @ X - B) / (abs(Mo).sum(axis=0).max() * np.linalg.norm(X)) < 10 * EPS
+    assert np.linalg.norm(X - sla.splu(Mo).solve(B)) / np.linalg.norm(X) < 1e-9
+
+
+def test_stencil_pep_solve():
+    from nepb200 import synthetic
+    mats, _ = synthetic.stencil_pep(48)
+    dnep = B200SPMF([m.tocsc() for m in mats], [Monomial(i) for i in range(4)])
+    lam = 0.3 + 0.2j
+    Mo = sum(m * lam ** i for i, m in enumerate(mats)).tocsc()
+    b = np.ones(dnep.n) + 0j
+    x = nepb200.B200FactorizeLinSolver(dnep, lam).lin_solve(b)
+    assert np.linalg.norm(Mo @ x - b) / (abs(Mo).sum(axis=0).max() * np.linalg.norm(x)) < 10 * EPS
+
+
+def test_singular_matrix_is_reported():
+    Z = sp.csc_matrix(np.array([[1.0, 2.0], [2.0, 4.0]]))
+    d = B200SPMF([Z], [ONE])
+    s = nepb200.B200FactorizeLinSolver(d, 0.0, umfpack_refinements=0)
+    assert s.status["flags"] & 1  # exactly singular: flagged, like UMFPACK's singular-matrix warning status
+
+
+def test_creator_cache_semantics():
+    # LinSolverCreators.jl:62-122 and test/rk_helper/cached_lin_solver.jl
+    onep, dnep = gun_pair()
+    c = nepb200.B200LinSolverCreator(max_factorizations=2)
+    a = c.create_linsolver(dnep, 1e4 + 1j)
+    assert c.create_linsolver(dnep, 1e4 + 1j) is a
+    c.create_linsolver(dnep, 2e4)
+    c.create_linsolver(dnep, 3e4)
+    assert len(c.recycled_factorizations) == 2
+    cache = nepb200.LinSolverCache(dnep)
+    y = np.ones(dnep.n, dtype=complex)
+    x = cache.solve(2e4 + 5j, y)
+    assert len(cache.solvers) == 1
+    cache.solve(3e4, y, add_to_cache=False)
+    assert len(cache.solvers) == 1
+    Mo = sp.csc_matrix(o.compute_Mder(onep, 2e4 + 5j))
+    assert np.linalg.norm(Mo @ x - y) / np.linalg.norm(y) < 1e-10
+    with pytest.raises(ValueError):
+        nepb200.B200LinSolverCreator(precomp_values=[1.0])
+
+
+def test_symbolic_from_handle_matches_host_analysis():
+    onep, dnep = gun_pair()
+    perm, parent, sn_ptr, sn_parent = nepb200.symbolic_get(dnep)
+    K, M, W1, W2 = g.load_gun_matrices()
+    A = (abs(K) + abs(M) + abs(W1) + abs(W2)).tocsc()
+    perm2, parent2, _, st = nepb200.analyse_pattern(A)
+    assert np.array_equal(perm, perm2) and np.array_equal(parent, parent2)
+    assert sn_ptr[0] == 0 and sn_ptr[-1] == dnep.n and np.all(np.diff(sn_ptr) > 0)
+    assert np.all((sn_parent == -1) | (sn_parent > np.arange(len(sn_parent))))

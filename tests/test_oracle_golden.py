@@ -97,3 +97,50 @@ def test_startder_semantics():
     z = o.compute_Mlincomb(dep, lam, V, np.ones(3), startder=1)
     ref = sum(o.compute_Mder(dep, lam, j + 1) @ V[:, j] for j in range(3))
     assert np.linalg.norm(z - ref) < 1e-12
+
+
+def test_structured_matrix_functions_match_generic_ones():
+    # the oracle's closed form for f(lam*I + subdiag) against sqrtm / expm at a size where both are accurate
+    import scipy.linalg as L
+    k = 9
+    lam = 3.0 + 0.5j
+    S = np.diag(np.full(k, lam)) + np.diag(0.3 * np.arange(1, k), -1)
+    F = o.f_isqrt_shift(0.7)(S)
+    assert np.linalg.norm(F - 1j * L.sqrtm(S - 0.7 * np.eye(k))) < 1e-12 * np.linalg.norm(F)
+    E = o.f_exp(-0.4)(S)
+    assert np.linalg.norm(E - L.expm(-0.4 * S)) < 1e-12 * np.linalg.norm(E)
+
+
+def test_oracle_resinv_dep0_literal():
+    # docs/src/methods.md:18-19: resinv on dep0 converges to -0.15955391823299256
+    from oracle import solvers as s
+    nep = o.nep_gallery("dep0")
+    lam, v = s.resinv(nep, lam=-0.2, v=np.ones(5), tol=1e-14)
+    assert abs(lam - (-0.15955391823299256)) < 1e-13
+
+
+def test_oracle_beyn_dep0_three_eigenvalues():
+    # test/beyn.jl:34-37: exactly 3 eigenvalues in the disk of radius 1 centred at 0.2
+    from oracle import solvers as s
+    nep = o.nep_gallery("dep0")
+    rng = np.random.default_rng(10)
+    lam, V = s.contour_beyn(nep, rng.standard_normal((5, 5)), sigma=0.2, radius=1.0, N=1000, neigs=4, sanity_check=False)
+    assert len(lam) == 3
+    for l, v in zip(lam, V.T):
+        assert np.linalg.svd(o.compute_Mder(nep, l), compute_uv=False)[-1] < 10000 * np.finfo(float).eps
+        assert np.linalg.norm(o.compute_Mlincomb(nep, l, v)) / np.linalg.norm(v) < 10000 * np.finfo(float).eps
+
+
+def test_oracle_iar_tiar_dep0():
+    # test/iar.jl:23-37 (n=5, sigma... residual checks) and test/tiar.jl:59-70 (tiar == iar)
+    from oracle import solvers as s
+    nep = o.nep_gallery("dep0", 100)
+    v0 = np.ones(100)
+    lam, Q, V = s.iar(nep, sigma=0.0, gamma=1.0, neigs=3, maxit=60, v=v0, tol=1e-10)
+    for l, q in zip(lam, Q.T):
+        assert np.linalg.norm(o.compute_Mlincomb(nep, l, q)) / np.linalg.norm(q) < 1e-8
+    G = V.conj().T @ V
+    assert np.linalg.norm(G - np.eye(G.shape[0])) < 1e-6  # test/iar.jl:44-62
+    lam2, Q2, Z, hist = s.tiar(nep, sigma=0.0, gamma=1.0, neigs=3, maxit=60, v=v0, tol=1e-10)
+    assert np.allclose(np.sort_complex(lam), np.sort_complex(lam2), atol=1e-6)
+    assert np.linalg.norm(Z.conj().T @ Z - np.eye(Z.shape[1])) < 1e-6

@@ -1,0 +1,143 @@
+"""The callers of the hot path (contour_beyn, iar, tiar, resinv) running on the B200 operators, against the CPU oracle.
+Mirrors test/beyn.jl, test/iar.jl, test/tiar.jl, test/gun_native.jl and the C1 plumbing config of BASELINE.json.
+Tolerance: eigenvalues / residuals within 1e-10 relative of the oracle (north star); sort permutations identical."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import nepb200
+from nepb200 import B200SPMF, ONE, IDENTITY, PowShift
+from oracle import gallery as g
+from oracle import nep as o
+from oracle import solvers as osol
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+def dep0_pair(n=5):
+    A0, A1, tauv = g.dep0_matrices(n)
+    return o.nep_gallery("dep0", n), B200SPMF.from_nep(nepb200.DEP([A0, A1], tauv))
+
+
+def gun_pair():
+    K, M, W1, W2 = g.load_gun_matrices()
+    dnep = B200SPMF([K, -M, W1, W2], [ONE, IDENTITY, PowShift(0.5, 0.0, 1j), PowShift(0.5, 108.8774 ** 2, 1j)])
+    return o.nep_gallery("nlevp_native_gun"), dnep
+
+
+def msws_probe(n, k, seed=0):
+    rng = g.MSWS_RNG(seed)
+    return g.gen_rng_mat(rng, n, k)
+
+
+def test_resinv_dep0_plumbing():
+    # BASELINE config C1: dep0 n=5, lambda0=-0.2, v=ones, tol=1e-14 -> -0.15955391823299256 (docs/src/methods.md:18-19)
+    onep, dnep = dep0_pair()
+    lam, v = nepb200.resinv(dnep, lam=-0.2, v=np.ones(5), tol=1e-14)
+    assert abs(lam - (-0.15955391823299256)) < 1e-13
+    lo, vo = osol.resinv(onep, lam=-0.2, v=np.ones(5), tol=1e-14)
+    assert abs(lam - lo) < 1e-13
+    assert np.linalg.norm(o.compute_Mlincomb(onep, lam, v)) / np.linalg.norm(v) < 1e-13
+
+
+def test_beyn_dep0_shifted_disk():
+    # test/beyn.jl:32-46
+    onep, dnep = dep0_pair()
+    Vh = msws_probe(5, 5)
+    lam, V = nepb200.contour_beyn(dnep, Vh, sigma=0.2, radius=1.0, N=1000, neigs=4, sanity_check=False, batch=250)
+    assert len(lam) == 3
+    lo, Vo = osol.contour_beyn(onep, Vh, sigma=0.2, radius=1.0, N=1000, neigs=4, sanity_check=False)
+    assert np.allclose(lam, lo, rtol=0, atol=1e-12)  # same values in the same (sorted) order
+    for l, v in zip(lam, V.T):
+        assert np.linalg.svd(o.compute_Mder(onep, l), compute_uv=False)[-1] < EPS * 10000
+        assert np.linalg.norm(o.compute_Mlincomb(onep, l, v)) / np.linalg.norm(v) < EPS * 10000
+
+
+def test_beyn_dep0_disk_at_origin_with_sanity_check():
+    # test/beyn.jl:13-30, docstring example method_beyncontour.jl:36-42
+    onep, dnep = dep0_pair()
+    Vh = msws_probe(5, 3, seed=3)
+    lam, V = nepb200.contour_beyn(dnep, Vh, radius=1.1, N=500, neigs=3, k=3 + 1 if False else 3)
+    lo, Vo = osol.contour_beyn(onep, Vh, radius=1.1, N=500, neigs=3, k=3)
+    assert len(lam) == len(lo)
+    assert np.allclose(lam, lo, atol=1e-11)
+
+
+def test_beyn_gun_reference_eigenvalue_and_moment_parity():
+    # config C3 geometry at reduced N / k: sigma=150^2, radius=500 encloses exactly the eigenvalue of test/gun_native.jl:9
+    onep, dnep = gun_pair()
+    n = dnep.n
+    Vh = msws_probe(n, 4)
+    N = 16
+    lam, V, A0, A1, info = nepb200.contour_beyn(dnep, Vh, sigma=150.0 ** 2, radius=500.0, N=N, neigs=3, k=4,
+                                               batch=8, return_moments=True)
+    lo, Vo, A0o, A1o, infoo = osol.contour_beyn(onep, Vh, sigma=150.0 ** 2, radius=500.0, N=N, neigs=3, k=4, return_moments=True)
+    assert np.linalg.norm(A0 - A0o) / np.linalg.norm(A0o) < 1e-10
+    assert np.linalg.norm(A1 - A1o) / np.linalg.norm(A1o) < 1e-10
+    assert info["p"] == infoo["p"] == 1
+    assert len(lam) == 1 and abs(lam[0] - (22345.116783765 + 0.644998598j)) < 10 ** -3.5  # test/gun_native.jl:18-19
+    assert abs(lam[0] - lo[0]) / abs(lo[0]) < 1e-10
+    r = np.linalg.norm(o.compute_Mlincomb(onep, lam[0], V[:, 0])) / np.linalg.norm(V[:, 0])
+    ro = np.linalg.norm(o.compute_Mlincomb(onep, lo[0], Vo[:, 0])) / np.linalg.norm(Vo[:, 0])
+    assert r < max(10 * ro, 1e-9 * abs(sp.csc_matrix(o.compute_Mder(onep, lam[0]))).sum(axis=0).max())
+
+
+def test_beyn_sharded_nodes_sum_to_the_full_integral():
+    # the multi-GPU seam without a communicator: two half-jobs (rank 0 / 1 of world 2) add up to the full moments
+    onep, dnep = gun_pair()
+    Vh = msws_probe(dnep.n, 3)
+    kw = dict(sigma=150.0 ** 2, radius=500.0, N=8, neigs=2, k=3, return_moments=True, sanity_check=False)
+    _, _, A0, A1, _ = nepb200.contour_beyn(dnep, Vh, **kw)
+    integ = nepb200.ContourIntegrator(dnep, 3, 2, 4)
+    h = 2 * np.pi / 8
+    t = h * np.arange(8)
+    gpt = 500.0 * (-np.sin(t) + 1j * np.cos(t))
+    gt = 500.0 * (np.cos(t) + 1j * np.sin(t))
+    W = np.stack([gpt * h / (2j * np.pi), gpt * gt * h / (2j * np.pi)], axis=1)
+    parts = [integ.integrate(gt[r::2] + 150.0 ** 2, W[r::2], Vh)[0] for r in (0, 1)]
+    S = parts[0] + parts[1]
+    assert np.linalg.norm(S[:, :, 0] - A0) / np.linalg.norm(A0) < 1e-13
+    assert np.linalg.norm(S[:, :, 1] - A1) / np.linalg.norm(A1) < 1e-13
+
+
+def test_iar_dep0_matches_oracle():
+    # test/iar.jl:23-37 at n=100 (shared start vector instead of randn)
+    onep, dnep = dep0_pair(100)
+    v0 = np.ones(100)
+    lam, Q, V = nepb200.iar(dnep, sigma=0.0, neigs=3, maxit=60, v=v0, tol=1e-10)
+    lo, Qo, Vo = osol.iar(onep, sigma=0.0, neigs=3, maxit=60, v=v0, tol=1e-10, errmeasure=None)
+    assert len(lam) == len(lo) == 3
+    assert np.allclose(np.sort_complex(lam), np.sort_complex(lo), atol=1e-9)
+    for l, q in zip(lam, Q.T):
+        assert np.linalg.norm(o.compute_Mlincomb(onep, l, q)) / np.linalg.norm(q) < 1e-8
+    assert np.linalg.norm(V.conj().T @ V - np.eye(V.shape[1])) < 1e-6
+
+
+def test_tiar_equals_iar_dep0():
+    # test/tiar.jl:59-70
+    onep, dnep = dep0_pair(100)
+    v0 = np.ones(100)
+    lam, Q, Z, hist = nepb200.tiar(dnep, sigma=0.0, neigs=3, maxit=60, v=v0, tol=1e-10)
+    lam2, Q2, V = nepb200.iar(dnep, sigma=0.0, neigs=3, maxit=60, v=v0, tol=1e-10)
+    assert np.allclose(np.sort_complex(lam), np.sort_complex(lam2), atol=1e-6)
+    assert np.linalg.norm(Z.conj().T @ Z - np.eye(Z.shape[1])) < 1e-6
+    with pytest.raises(nepb200.LostOrthogonalityException):
+        nepb200.tiar(dep0_pair(5)[1], maxit=30, v=np.ones(5))  # method_tiar.jl:82-85
+    with pytest.raises(nepb200.NoConvergenceException):
+        nepb200.iar(dnep, sigma=0.0, neigs=30, maxit=5, v=v0)  # test/iar.jl:65-70
+
+
+def test_iar_gun_short_run_matches_oracle():
+    # config C2 at reduced depth: sigma=250^2, gamma=300^2-200^2, v=ones
+    onep, dnep = gun_pair()
+    n = dnep.n
+    sigma, gamma = 250.0 ** 2, 300.0 ** 2 - 200.0 ** 2
+    kw = dict(sigma=sigma, gamma=gamma, neigs=np.inf, maxit=25, v=np.ones(n), tol=1e-10, check_error_every=25)
+    lam, Q, V = nepb200.iar(dnep, **kw)
+    lo, Qo, Vo = osol.iar(onep, **kw)
+    assert len(lam) == len(lo) and len(lam) >= 1
+    a, b = np.sort_complex(lam), np.sort_complex(lo)
+    assert np.max(np.abs(a - b) / np.abs(b)) < 1e-8
+    for l, q in zip(lam, Q.T):
+        assert np.linalg.norm(o.compute_Mlincomb(onep, l, q)) / np.linalg.norm(q) < 1e-6 * abs(l)
