@@ -88,12 +88,12 @@ __global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev d, const int4*
     const int s = it.x, j0 = it.y, j1 = it.z;
     const int b = blockIdx.y;
     double2* base = fronts + (size_t)b * d.front_total;
-    const int nfp = d.nf[s];
+    const int ldp = d.ld[s];
     double2* Fp = base + d.front_off[s];
     for (int ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ++ci) {
         const int c = d.child_list[ci];
-        const int nfc = d.nf[c], npc = d.np[c], ncb = nfc - npc;
-        if (ncb == 0) continue;
+        const int nfc = d.nf[c], npc = d.np[c], ncb = nfc - npc, ldc = d.ld[c];
+        if (ncb == 0 || d.in_place[c]) continue;  // in-place child: its Schur update already landed in this front
         const int* rel = d.rel + d.rel_ptr[c];
         // rel is strictly increasing: the child columns landing in [j0, j1) form a contiguous range
         int lo = 0, hi = ncb;
@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev d, const int4*
         const int total = (xb - xa) * ncb;
         for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
             const int x = xa + idx / ncb, y = idx % ncb;
-            const double2 v = Fc[(size_t)(npc + y) + (size_t)(npc + x) * nfc];
-            double2* t = Fp + (size_t)rel[y] + (size_t)rel[x] * nfp;
+            const double2 v = Fc[(size_t)(npc + y) + (size_t)(npc + x) * ldc];
+            double2* t = Fp + (size_t)rel[y] + (size_t)rel[x] * ldp;
             double2 o = *t;
             o.x += v.x;
             o.y += v.y;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) lu_diag_kernel(LuDev d, const int* __rest
     __shared__ double2 s_rp;
     const int s = items[blockIdx.x];
     const int b = blockIdx.y;
-    const int nf = d.nf[s], np = d.np[s], ld = np + 1;
+    const int nf = d.ld[s], np = d.np[s], ld = np + 1;  // nf: leading dimension of the front storage
     double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
     int* pv = piv + (size_t)b * d.n + d.sn_ptr[s];
     const int tid = threadIdx.x;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128) lu_panel_kernel(LuDev d, const int4* __re
     const int4 it = items[blockIdx.x];
     const int s = it.x, kind = it.y, t0 = it.z;
     const int b = blockIdx.y;
-    const int nf = d.nf[s], np = d.np[s], ncb = nf - np, ld = np + 1;
+    const int nf = d.ld[s], np = d.np[s], ncb = d.nf[s] - np, ld = np + 1;  // nf: leading dimension of the front storage
     double2* sLU = sm;                   // np x np, ld = np+1
     double2* sT = sm + (size_t)np * ld;  // tile: U kind [PANEL_T][np+1] (column c at sT + c*ld); L kind [np][PANEL_T]
     double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
@@ -279,10 +279,10 @@ __global__ void __launch_bounds__(256) lu_schur_kernel(LuDev d, const int4* __re
     const int4 it = items[blockIdx.x];
     const int s = it.x, i0 = it.y, j0 = it.z;
     const int b = blockIdx.y;
-    const int nf = d.nf[s], np = d.np[s], ncb = nf - np;
+    const int nf = d.ld[s], np = d.np[s], ncb = d.nf[s] - np;  // nf: leading dimension of the front storage
     double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
     double2* sL = sm;                           // [np][SCHUR_T]   L21 tile, row index fastest
-    double2* sU = sm + (size_t)np * SCHUR_T;    // [np][SCHUR_T]   U12 tile transposed: sU[t][c]
+    double2* sU = sm + (size_t)np * SCHUR_T;    // [np][SCHUR_T+1] U12 tile transposed: sU[t][c] (padded: conflict-free transposing store)
     const int tid = threadIdx.x;
     const int th = min(SCHUR_T, ncb - i0), tw = min(SCHUR_T, ncb - j0);
     for (int idx = tid; idx < np * SCHUR_T; idx += blockDim.x) {
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) lu_schur_kernel(LuDev d, const int4* __re
     }
     for (int idx = tid; idx < np * SCHUR_T; idx += blockDim.x) {
         const int t = idx % np, c = idx / np;  // contiguous reads along t
-        sU[t * SCHUR_T + c] = (c < tw) ? F[(size_t)t + (size_t)(np + j0 + c) * nf] : make_double2(0.0, 0.0);
+        sU[t * (SCHUR_T + 1) + c] = (c < tw) ? F[(size_t)t + (size_t)(np + j0 + c) * nf] : make_double2(0.0, 0.0);
     }
     __syncthreads();
     const int tx = tid % 16, ty = tid / 16;
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(256) lu_schur_kernel(LuDev d, const int4* __re
 #pragma unroll
         for (int r = 0; r < 4; ++r) l[r] = sL[t * SCHUR_T + tx + 16 * r];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) u[c] = sU[t * SCHUR_T + ty + 16 * c];
+        for (int c = 0; c < 4; ++c) u[c] = sU[t * (SCHUR_T + 1) + ty + 16 * c];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -350,13 +350,121 @@ __global__ void __launch_bounds__(256) lu_permute_out_kernel(int n, int k, const
     X[b * x_stride + idx] = Xp[(size_t)b * n * k + (size_t)iperm[i] * k + c];
 }
 
-// forward: one CTA per (front, shift)
+constexpr int SOLVE_BIG = 192;    // fronts with more update rows than this get several CTAs in the solves
+constexpr int SOLVE_CHUNK = 128;  // update rows per CTA for those
+constexpr int SOLVE_TILE = 64;    // update rows staged in shared memory at a time
+
+// shared memory of the solve kernels: sy [np*k] | sT [np*SOLVE_TILE] | sX [SOLVE_TILE*k]
+__host__ __device__ inline size_t solve_smem_bytes(int max_np, int k) {
+    return ((size_t)max_np * k + (size_t)max_np * SOLVE_TILE + (size_t)SOLVE_TILE * k) * 16;
+}
+
+// W[np + r, :] -= L21[r, :] * y1 for the update rows [ra, rb): 64-row tiles of L21 are staged in shared memory with
+// coalesced, independent loads (the factors stream from HBM exactly once), then every thread owns one row and CK columns.
+template <int CK>
+__device__ __forceinline__ void fwd_update_rows(const double2* __restrict__ F, int ld, int np, int ra, int rb, const double2* sy, int k,
+                                                double2* __restrict__ Ws, double2* sT) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int nck = (k + CK - 1) / CK;
+    for (int r0 = ra; r0 < rb; r0 += SOLVE_TILE) {
+        const int th = min(SOLVE_TILE, rb - r0);
+        __syncthreads();
+        for (int idx = tid; idx < np * SOLVE_TILE; idx += nth) {
+            const int r = idx % SOLVE_TILE, t = idx / SOLVE_TILE;
+            sT[idx] = (r < th) ? F[(size_t)(np + r0 + r) + (size_t)t * ld] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        for (int item = tid; item < SOLVE_TILE * nck; item += nth) {
+            const int r = item % SOLVE_TILE, cb = (item / SOLVE_TILE) * CK;
+            if (r >= th) continue;
+            double2 acc[CK];
+#pragma unroll
+            for (int c = 0; c < CK; ++c) acc[c] = make_double2(0.0, 0.0);
+            for (int t = 0; t < np; ++t) {
+                const double2 l = sT[t * SOLVE_TILE + r];
+                const double2* yy = sy + t * k + cb;
+#pragma unroll
+                for (int c = 0; c < CK; ++c)
+                    if (cb + c < k) cfma2(acc[c], l, yy[c]);
+            }
+            double2* w = Ws + (size_t)(np + r0 + r) * k + cb;
+#pragma unroll
+            for (int c = 0; c < CK; ++c)
+                if (cb + c < k) {
+                    double2 o = w[c];
+                    o.x -= acc[c].x;
+                    o.y -= acc[c].y;
+                    w[c] = o;
+                }
+        }
+    }
+}
+
+// sp[np x k] -= (sign) U12[:, x0:x1] * x2[x0:x1]; tiles of 64 update rows staged in shared memory; the x-range of a
+// tile is split over 4 thread groups whose partial sums are added in a fixed order.
+template <int CK>
+__device__ __forceinline__ void bwd_product(const double2* __restrict__ F, int ld, int np, int x0, int x1, const int* __restrict__ rows,
+                                            const double2* __restrict__ Xb, int k, double2* sp, double2* sT, double2* sX, bool subtract) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int nck = (k + CK - 1) / CK;
+    constexpr int Q = 4;
+    for (int xa = x0; xa < x1; xa += SOLVE_TILE) {
+        const int tw = min(SOLVE_TILE, x1 - xa);
+        __syncthreads();
+        for (int idx = tid; idx < np * tw; idx += nth) {
+            const int t = idx % np, x = idx / np;
+            sT[idx] = F[(size_t)t + (size_t)(np + xa + x) * ld];  // sT[x*np + t]
+        }
+        for (int idx = tid; idx < tw * k; idx += nth) {
+            const int x = idx / k, c = idx % k;
+            sX[idx] = Xb[(size_t)rows[xa + x] * k + c];
+        }
+        __syncthreads();
+        const int xq = (tw + Q - 1) / Q;
+        const int nitems = np * nck * Q;
+        for (int base = 0; base < nitems; base += nth) {  // uniform trip count: barriers inside
+            const int item = base + tid;
+            const bool ok = item < nitems;
+            const int t = item % np, cb = ((item / np) % nck) * CK, q = item / (np * nck);
+            double2 acc[CK];
+#pragma unroll
+            for (int c = 0; c < CK; ++c) acc[c] = make_double2(0.0, 0.0);
+            if (ok) {
+                const int xe = min(tw, (q + 1) * xq);
+                for (int x = q * xq; x < xe; ++x) {
+                    const double2 u = sT[x * np + t];
+                    const double2* xx = sX + x * k + cb;
+#pragma unroll
+                    for (int c = 0; c < CK; ++c)
+                        if (cb + c < k) cfma2(acc[c], u, xx[c]);
+                }
+            }
+            for (int qq = 0; qq < Q; ++qq) {
+                if (ok && q == qq) {
+                    double2* y = sp + t * k + cb;
+#pragma unroll
+                    for (int c = 0; c < CK; ++c)
+                        if (cb + c < k) {
+                            if (subtract) { y[c].x -= acc[c].x; y[c].y -= acc[c].y; }
+                            else { y[c].x += acc[c].x; y[c].y += acc[c].y; }
+                        }
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// forward: one CTA per (front, shift).  CK = right-hand-side columns held in registers per pass.
+template <int CK>
 __global__ void __launch_bounds__(256) lu_forward_kernel(LuDev d, const int* __restrict__ items, const double2* __restrict__ fronts,
-                                                         const int* __restrict__ piv, double2* __restrict__ Xp, double2* __restrict__ W, int k) {
-    extern __shared__ double2 sy[];  // np x k pivot rows
+                                                         const int* __restrict__ piv, double2* __restrict__ Xp, double2* __restrict__ W, int k,
+                                                         int max_np) {
+    extern __shared__ double2 sy[];  // np x k pivot rows | L21 tile
+    double2* sT = sy + (size_t)max_np * k;
     const int s = items[blockIdx.x];
     const int b = blockIdx.y;
-    const int nf = d.nf[s], np = d.np[s], ncb = nf - np;
+    const int nf = d.nf[s], np = d.np[s], ncb = nf - np, ld = d.ld[s];
     const double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
     const int* pv = piv + (size_t)b * d.n + d.sn_ptr[s];
     double2* Wb = W + (size_t)b * d.w_total * k;
@@ -364,12 +472,21 @@ __global__ void __launch_bounds__(256) lu_forward_kernel(LuDev d, const int* __r
     double2* Xb = Xp + (size_t)b * d.n * k;
     const int c0 = d.sn_ptr[s];
     const int tid = threadIdx.x;
-    // 1. gather: pivot rows from the right-hand side, update rows start at zero; then the children's updates
-    for (int idx = tid; idx < np * k; idx += blockDim.x) sy[idx] = Xb[(size_t)c0 * k + idx];
-    for (int idx = tid; idx < ncb * k; idx += blockDim.x) Ws[(size_t)np * k + idx] = make_double2(0.0, 0.0);
+    // 1. gather: pivot rows from the right-hand side, update rows start at zero; then the children's updates.
+    //    An in-place child has already left its update rows in this front's work rows (they are the same memory).
+    if (d.has_ip[s]) {
+        for (int idx = tid; idx < np * k; idx += blockDim.x) {
+            const double2 a = Xb[(size_t)c0 * k + idx], w = Ws[idx];
+            sy[idx] = make_double2(a.x + w.x, a.y + w.y);
+        }
+    } else {
+        for (int idx = tid; idx < np * k; idx += blockDim.x) sy[idx] = Xb[(size_t)c0 * k + idx];
+        for (int idx = tid; idx < ncb * k; idx += blockDim.x) Ws[(size_t)np * k + idx] = make_double2(0.0, 0.0);
+    }
     __syncthreads();
     for (int ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ++ci) {
         const int c = d.child_list[ci];
+        if (d.in_place[c]) continue;
         const int npc = d.np[c], ncbc = d.nf[c] - npc;
         const int* rel = d.rel + d.rel_ptr[c];
         const double2* Wc = Wb + ((size_t)d.w_off[c] + npc) * k;
@@ -385,59 +502,110 @@ __global__ void __launch_bounds__(256) lu_forward_kernel(LuDev d, const int* __r
         }
         __syncthreads();
     }
-    // 2. row swaps, 3. unit lower solve on the pivot rows (thread = right-hand side column)
+    // 2. row swaps, 3. unit lower solve on the pivot rows (L11 staged in shared memory)
     if (tid < k) {
         for (int j = 0; j < np; ++j) {
             const int pr = pv[j];
             if (pr != j) { const double2 t = sy[j * k + tid]; sy[j * k + tid] = sy[pr * k + tid]; sy[pr * k + tid] = t; }
         }
     }
+    for (int idx = tid; idx < np * np; idx += blockDim.x) sT[idx] = F[(size_t)(idx % np) + (size_t)(idx / np) * ld];
     __syncthreads();
     for (int j = 0; j < np - 1; ++j) {
         const int m = np - j - 1;
         for (int idx = tid; idx < m * k; idx += blockDim.x) {
             const int i = j + 1 + idx / k, col = idx % k;
-            cfms(sy[i * k + col], F[(size_t)i + (size_t)j * nf], sy[j * k + col]);
+            cfms(sy[i * k + col], sT[i + j * np], sy[j * k + col]);
         }
         __syncthreads();
     }
     for (int idx = tid; idx < np * k; idx += blockDim.x) Xb[(size_t)c0 * k + idx] = sy[idx];
-    // 4. update rows: W[np + r, :] -= L21[r, :] * y1
-    for (int idx = tid; idx < ncb * k; idx += blockDim.x) {
-        const int r = idx % ncb, col = idx / ncb;  // consecutive threads -> consecutive rows of L21 (coalesced)
-        double2 acc = Ws[(size_t)(np + r) * k + col];
-        const double2* Lr = F + (size_t)(np + r);
-        for (int t = 0; t < np; ++t) cfms(acc, Lr[(size_t)t * nf], sy[t * k + col]);
-        Ws[(size_t)(np + r) * k + col] = acc;
-    }
+    // 4. update rows; big fronts leave this to lu_forward_update_kernel (several CTAs per front)
+    if (ncb > SOLVE_BIG) return;
+    fwd_update_rows<CK>(F, ld, np, 0, ncb, sy, k, Ws, sT);
 }
 
-// backward: x1 = U11^-1 (y1 - U12 x2)
+// forward, big fronts: item = (front s, first update row r0, end r1); W[np + r, :] -= L21[r, :] * y1 with y1 from Xp
+template <int CK>
+__global__ void __launch_bounds__(128) lu_forward_update_kernel(LuDev d, const int4* __restrict__ items, const double2* __restrict__ fronts,
+                                                                const double2* __restrict__ Xp, double2* __restrict__ W, int k, int max_np) {
+    extern __shared__ double2 sy[];
+    double2* sT = sy + (size_t)max_np * k;
+    const int4 it = items[blockIdx.x];
+    const int s = it.x;
+    const int b = blockIdx.y;
+    const int np = d.np[s], ld = d.ld[s];
+    const double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
+    double2* Ws = W + (size_t)b * d.w_total * k + (size_t)d.w_off[s] * k;
+    const double2* Xb = Xp + (size_t)b * d.n * k;
+    const int c0 = d.sn_ptr[s];
+    for (int idx = threadIdx.x; idx < np * k; idx += blockDim.x) sy[idx] = Xb[(size_t)c0 * k + idx];
+    fwd_update_rows<CK>(F, ld, np, it.y, it.z, sy, k, Ws, sT);
+}
+
+// backward, big fronts: item = (front s, update rows [x0, x1), slot); part[b][slot][np x k] = U12[:, x0:x1] * x2[x0:x1]
+template <int CK>
+__global__ void __launch_bounds__(128) lu_backward_partial_kernel(LuDev d, const int4* __restrict__ items, const double2* __restrict__ fronts,
+                                                                  const double2* __restrict__ Xp, double2* __restrict__ part, int part_slots,
+                                                                  int max_np, int k) {
+    extern __shared__ double2 sp[];
+    double2* sT = sp + (size_t)max_np * k;
+    double2* sX = sT + (size_t)max_np * SOLVE_TILE;
+    const int4 it = items[blockIdx.x];
+    const int s = it.x;
+    const int b = blockIdx.y;
+    const int np = d.np[s], ld = d.ld[s];
+    const double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
+    const double2* Xb = Xp + (size_t)b * d.n * k;
+    const int* rows = d.rows + d.row_ptr[s] + np;
+    for (int idx = threadIdx.x; idx < np * k; idx += blockDim.x) sp[idx] = make_double2(0.0, 0.0);
+    bwd_product<CK>(F, ld, np, it.y, it.z, rows, Xb, k, sp, sT, sX, false);
+    double2* out = part + ((size_t)b * part_slots + it.w) * (size_t)max_np * k;
+    for (int idx = threadIdx.x; idx < np * k; idx += blockDim.x) out[idx] = sp[idx];
+}
+
+// backward: x1 = U11^-1 (y1 - U12 x2), one CTA per (front, shift)
+template <int CK>
 __global__ void __launch_bounds__(256) lu_backward_kernel(LuDev d, const int* __restrict__ items, const double2* __restrict__ fronts,
-                                                          double2* __restrict__ Xp, int k) {
-    extern __shared__ double2 sy[];  // np x k
+                                                          double2* __restrict__ Xp, const double2* __restrict__ part, int part_slots,
+                                                          int max_np, int k) {
+    extern __shared__ double2 sy[];
+    double2* sT = sy + (size_t)max_np * k;
+    double2* sX = sT + (size_t)max_np * SOLVE_TILE;
     const int s = items[blockIdx.x];
     const int b = blockIdx.y;
-    const int nf = d.nf[s], np = d.np[s], ncb = nf - np;
+    const int nf = d.nf[s], np = d.np[s], ncb = nf - np, ld = d.ld[s];
     const double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
     double2* Xb = Xp + (size_t)b * d.n * k;
-    const int* rows = d.rows + d.row_ptr[s];
+    const int* rows = d.rows + d.row_ptr[s] + np;
     const int c0 = d.sn_ptr[s];
     const int tid = threadIdx.x;
-    // y1 - U12 x2 : thread = (pivot row t, column col)
-    for (int idx = tid; idx < np * k; idx += blockDim.x) {
-        const int t = idx % np, col = idx / np;
-        double2 acc = Xb[(size_t)(c0 + t) * k + col];
-        for (int x = 0; x < ncb; ++x) cfms(acc, F[(size_t)t + (size_t)(np + x) * nf], Xb[(size_t)rows[np + x] * k + col]);
-        sy[t * k + col] = acc;
+    if (ncb > SOLVE_BIG) {
+        // the products were formed by lu_backward_partial_kernel: subtract the partial sums slot after slot
+        const int nslots = (ncb + SOLVE_CHUNK - 1) / SOLVE_CHUNK;
+        const double2* pp = part + ((size_t)b * part_slots + d.bw_slot[s]) * (size_t)max_np * k;
+        for (int idx = tid; idx < np * k; idx += blockDim.x) {
+            double2 a = Xb[(size_t)c0 * k + idx];
+            for (int q = 0; q < nslots; ++q) {
+                const double2 v = pp[(size_t)q * max_np * k + idx];
+                a.x -= v.x;
+                a.y -= v.y;
+            }
+            sy[idx] = a;
+        }
+    } else {
+        for (int idx = tid; idx < np * k; idx += blockDim.x) sy[idx] = Xb[(size_t)c0 * k + idx];
+        bwd_product<CK>(F, ld, np, 0, ncb, rows, Xb, k, sy, sT, sX, true);
     }
     __syncthreads();
+    for (int idx = tid; idx < np * np; idx += blockDim.x) sT[idx] = F[(size_t)(idx % np) + (size_t)(idx / np) * ld];
+    __syncthreads();
     for (int j = np - 1; j >= 0; --j) {
-        if (tid < k) sy[j * k + tid] = cmul(sy[j * k + tid], crecip(F[(size_t)j + (size_t)j * nf]));
+        if (tid < k) sy[j * k + tid] = cmul(sy[j * k + tid], crecip(sT[j + j * np]));
         __syncthreads();
         for (int idx = tid; idx < j * k; idx += blockDim.x) {
             const int i = idx / k, col = idx % k;
-            cfms(sy[i * k + col], F[(size_t)i + (size_t)j * nf], sy[j * k + col]);
+            cfms(sy[i * k + col], sT[i + j * np], sy[j * k + col]);
         }
         __syncthreads();
     }
@@ -528,19 +696,27 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     // per-level work lists
     sd->lv.resize(S.nlevels);
     std::vector<int32_t> fr_items;
-    std::vector<int4> ea_items, pn_items, sc_items;
+    std::vector<int4> ea_items, pn_items, sc_items, fu_items, bp_items;
+    std::vector<int32_t> bw_slot(ns, 0);
+    sd->part_slots = 0;
     for (int l = 0; l < S.nlevels; ++l) {
         auto& L = sd->lv[l];
         L.front_begin = (int)fr_items.size();
         L.ea_begin = (int)ea_items.size();
         L.pn_begin = (int)pn_items.size();
         L.sc_begin = (int)sc_items.size();
+        L.fu_begin = (int)fu_items.size();
+        L.bp_begin = (int)bp_items.size();
+        int slots = 0;
         std::vector<int32_t> fl(S.level_list.begin() + S.level_ptr[l], S.level_list.begin() + S.level_ptr[l + 1]);
         std::stable_sort(fl.begin(), fl.end(), [&](int a, int b) { return nf[a] > nf[b]; });  // big fronts first
         for (int s : fl) {
             fr_items.push_back(s);
             const int ncb = nf[s] - np[s];
-            if (child_ptr[s + 1] > child_ptr[s]) {
+            bool needs_ea = false;
+            for (int ci = child_ptr[s]; ci < child_ptr[s + 1]; ++ci)
+                if (!S.in_place_child[child_list[ci]] && nf[child_list[ci]] > np[child_list[ci]]) needs_ea = true;
+            if (needs_ea) {
                 // slab width: keep roughly <= 16k entries of child data per CTA
                 int slab = nf[s];
                 if (nf[s] > 96) slab = std::max(16, (int)(16384 / nf[s]));
@@ -552,7 +728,17 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
             }
             for (int j0 = 0; j0 < ncb; j0 += SCHUR_T)
                 for (int i0 = 0; i0 < ncb; i0 += SCHUR_T) sc_items.push_back(make_int4(s, i0, j0, 0));
+            if (ncb > SOLVE_BIG) {
+                bw_slot[s] = slots;
+                for (int r0 = 0; r0 < ncb; r0 += SOLVE_CHUNK) {
+                    fu_items.push_back(make_int4(s, r0, std::min(ncb, r0 + SOLVE_CHUNK), 0));
+                    bp_items.push_back(make_int4(s, r0, std::min(ncb, r0 + SOLVE_CHUNK), slots++));
+                }
+            }
         }
+        sd->part_slots = std::max(sd->part_slots, slots);
+        L.fu_count = (int)fu_items.size() - L.fu_begin;
+        L.bp_count = (int)bp_items.size() - L.bp_begin;
         L.front_count = (int)fr_items.size() - L.front_begin;
         L.ea_count = (int)ea_items.size() - L.ea_begin;
         L.pn_count = (int)pn_items.size() - L.pn_begin;
@@ -563,6 +749,8 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     UP(sd->front_off, S.front_off);
     UP(sd->nf, nf);
     UP(sd->np, np);
+    UP(sd->ld, S.front_ld);
+    UP(sd->in_place, S.in_place_child);
     UP(sd->row_ptr, S.row_ptr);
     UP(sd->rows, S.rows);
     UP(sd->rel_ptr, S.rel_ptr);
@@ -578,6 +766,10 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     UP(sd->ea_items, ea_items);
     UP(sd->pn_items, pn_items);
     UP(sd->sc_items, sc_items);
+    UP(sd->fu_items, fu_items);
+    UP(sd->bp_items, bp_items);
+    UP(sd->bw_slot, bw_slot);
+    UP(sd->has_ip, S.has_in_place_child);
 #undef UP
     if (e != cudaSuccess) {
         set_error("CUDA error while uploading the LU symbolic data: %s", cudaGetErrorString(e));
@@ -588,6 +780,10 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     d.front_off = sd->front_off.p;
     d.nf = sd->nf.p;
     d.np = sd->np.p;
+    d.ld = sd->ld.p;
+    d.in_place = sd->in_place.p;
+    d.has_ip = sd->has_ip.p;
+    d.bw_slot = sd->bw_slot.p;
     d.row_ptr = sd->row_ptr.p;
     d.rows = sd->rows.p;
     d.rel_ptr = sd->rel_ptr.p;
@@ -603,12 +799,17 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     const int mnp = S.max_np;
     sd->smem_diag = (size_t)mnp * (mnp + 1) * 16;
     sd->smem_panel = ((size_t)mnp * (mnp + 1) + (size_t)PANEL_T * (mnp + 1)) * 16;
-    sd->smem_schur = (size_t)2 * mnp * SCHUR_T * 16;
+    sd->smem_schur = (size_t)mnp * (2 * SCHUR_T + 1) * 16;
     cudaFuncSetAttribute(lu_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_diag);
     cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_panel);
     cudaFuncSetAttribute(lu_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_schur);
-    cudaFuncSetAttribute(lu_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(lu_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+#define NEPB_SOLVE_ATTR(CK_)                                                                                    \
+    cudaFuncSetAttribute(lu_forward_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);       \
+    cudaFuncSetAttribute(lu_backward_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);       \
+    cudaFuncSetAttribute(lu_forward_update_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+    cudaFuncSetAttribute(lu_backward_partial_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    NEPB_SOLVE_ATTR(1) NEPB_SOLVE_ATTR(4) NEPB_SOLVE_ATTR(8) NEPB_SOLVE_ATTR(10) NEPB_SOLVE_ATTR(16)
+#undef NEPB_SOLVE_ATTR
     hm->lu_symbolic = sd;
     *out = sd;
     return NEPB_OK;
@@ -656,7 +857,7 @@ int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev,
     const int n = S.n;
     NEPB_CHECK_ARG(shift0 >= 0 && nb >= 1 && shift0 + nb <= lu->nb, "shift window out of range");
     NEPB_CHECK_ARG(k >= 1 && k <= 256, "number of right-hand sides per solve must be in 1..256 (k=%d)", k);
-    const size_t smem = (size_t)S.max_np * k * 16;
+    const size_t smem = solve_smem_bytes(S.max_np, k);
     NEPB_CHECK_ARG(smem <= 200 * 1024, "k=%d right-hand sides with %d pivot columns per front exceed shared memory", k, S.max_np);
     NEPB_CUDA(lu->xp.reserve((size_t)2 * nb * n * k));
     NEPB_CUDA(lu->w.reserve((size_t)2 * nb * S.w_total * k));
@@ -666,14 +867,33 @@ int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev,
     const int* piv = lu->piv.p + (size_t)shift0 * n;
     dim3 pg((unsigned)(((size_t)n * k + 255) / 256), nb);
     NEPB_LAUNCH(lu_permute_in_kernel, pg, 256, 0, n, k, sd->perm.p, Bdev, rhs_stride, Xp);
-    for (int l = 0; l < S.nlevels; ++l) {
-        const auto& L = sd->lv[l];
-        NEPB_LAUNCH(lu_forward_kernel, dim3(L.front_count, nb), 256, smem, sd->dev, sd->fr_items.p + L.front_begin, F, piv, Xp, W, k);
-    }
-    for (int l = S.nlevels - 1; l >= 0; --l) {
-        const auto& L = sd->lv[l];
-        NEPB_LAUNCH(lu_backward_kernel, dim3(L.front_count, nb), 256, smem, sd->dev, sd->fr_items.p + L.front_begin, F, Xp, k);
-    }
+#define NEPB_SOLVE_LEVELS(CK_)                                                                                                           \
+    do {                                                                                                                                  \
+        for (int l = 0; l < S.nlevels; ++l) {                                                                                             \
+            const auto& L = sd->lv[l];                                                                                                    \
+            NEPB_LAUNCH((lu_forward_kernel<CK_>), dim3(L.front_count, nb), 256, smem, sd->dev, sd->fr_items.p + L.front_begin, F, piv, Xp, \
+                        W, k, S.max_np);                                                                                                          \
+            if (L.fu_count)                                                                                                               \
+                NEPB_LAUNCH((lu_forward_update_kernel<CK_>), dim3(L.fu_count, nb), 128, smem, sd->dev, sd->fu_items.p + L.fu_begin, F,     \
+                            (const double2*)Xp, W, k, S.max_np);                                                                                 \
+        }                                                                                                                                 \
+        for (int l = S.nlevels - 1; l >= 0; --l) {                                                                                        \
+            const auto& L = sd->lv[l];                                                                                                    \
+            if (L.bp_count)                                                                                                               \
+                NEPB_LAUNCH((lu_backward_partial_kernel<CK_>), dim3(L.bp_count, nb), 128, smem, sd->dev, sd->bp_items.p + L.bp_begin, F,   \
+                            (const double2*)Xp, part, sd->part_slots, S.max_np, k);                                                       \
+            NEPB_LAUNCH((lu_backward_kernel<CK_>), dim3(L.front_count, nb), 256, smem, sd->dev, sd->fr_items.p + L.front_begin, F, Xp,     \
+                        (const double2*)part, sd->part_slots, S.max_np, k);                                                               \
+        }                                                                                                                                 \
+    } while (0)
+    NEPB_CUDA(lu->part.reserve((size_t)2 * nb * std::max(sd->part_slots, 1) * S.max_np * k));
+    double2* part = (double2*)lu->part.p;
+    if (k == 1) NEPB_SOLVE_LEVELS(1);
+    else if (k <= 4) NEPB_SOLVE_LEVELS(4);
+    else if (k <= 8) NEPB_SOLVE_LEVELS(8);
+    else if (k <= 10 || (k > 16 && k <= 20)) NEPB_SOLVE_LEVELS(10);
+    else NEPB_SOLVE_LEVELS(16);
+#undef NEPB_SOLVE_LEVELS
     NEPB_LAUNCH(lu_permute_out_kernel, pg, 256, 0, n, k, sd->iperm.p, Xp, Xdev, (size_t)n * k);
     NEPB_LAUNCH_CHECK();
     return NEPB_OK;

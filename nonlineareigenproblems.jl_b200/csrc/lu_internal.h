@@ -11,6 +11,10 @@ struct LuDev {  // passed by value to kernels
     const int64_t* front_off;
     const int32_t* nf;
     const int32_t* np;
+    const int32_t* ld;         // leading dimension of the front storage
+    const uint8_t* in_place;   // the front's contribution block is its parent's front
+    const uint8_t* has_ip;     // the front has such a child
+    const int32_t* bw_slot;    // first partial-sum slot of a big front in the backward solve
     const int64_t* row_ptr;
     const int32_t* rows;
     const int64_t* rel_ptr;
@@ -35,6 +39,8 @@ struct LuLevel {
     int ea_begin = 0, ea_count = 0;
     int pn_begin = 0, pn_count = 0;
     int sc_begin = 0, sc_count = 0;
+    int fu_begin = 0, fu_count = 0;  // forward update items (big fronts)
+    int bp_begin = 0, bp_count = 0;  // backward partial-product items (big fronts)
 };
 
 struct LuSymbolicDev {
@@ -42,8 +48,11 @@ struct LuSymbolicDev {
     LuDev dev;
     std::vector<LuLevel> lv;
     DevBuf<int64_t> front_off, row_ptr, rel_ptr, w_off, a_pos;
-    DevBuf<int32_t> nf, np, rows, rel, sn_ptr, child_ptr, child_list, perm, iperm, fr_items;
-    DevBuf<int4> ea_items, pn_items, sc_items;
+    DevBuf<uint8_t> in_place, has_ip;
+    DevBuf<int32_t> bw_slot;
+    int part_slots = 0;
+    DevBuf<int32_t> nf, np, ld, rows, rel, sn_ptr, child_ptr, child_list, perm, iperm, fr_items;
+    DevBuf<int4> ea_items, pn_items, sc_items, fu_items, bp_items;
     size_t smem_diag = 0, smem_panel = 0, smem_schur = 0;
 };
 
@@ -63,7 +72,7 @@ struct nepb_lu {
     std::vector<double> h_coef;
     std::vector<nepb::LuInfo> h_info;
     // scratch
-    nepb::DevBuf<double> xp, w, rhs, sol, res, cor, stage;
+    nepb::DevBuf<double> xp, w, part, rhs, sol, res, cor, stage;
     nepb::DevBuf<unsigned long long> colmax;
 };
 

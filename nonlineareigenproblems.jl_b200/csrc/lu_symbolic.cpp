@@ -485,14 +485,67 @@ int lu_symbolic_analyse(int n, const int32_t* rowptr, const int32_t* colind, con
         }
     }
     // ---- offsets, statistics, relative indices ---------------------------------------------------------------
+    // A front whose only child hands it a contribution block with exactly its own row structure (the links of a
+    // supernode split by max_np, and any other such pair) lives *inside* the child's front: its storage is the child's
+    // F22 block, so the child's Schur update lands in place and no extend-add / extra memory is needed.
     S.front_off.assign(ns + 1, 0);
+    S.front_ld.assign(ns, 0);
+    S.in_place_child.assign(ns, 0);
     S.w_off.assign(ns + 1, 0);
     S.rel_ptr.assign(ns + 1, 0);
+    {
+        std::vector<int32_t> nchild(ns, 0), only_child(ns, -1);
+        for (int s = 0; s < ns; ++s)
+            if (S.sn_parent[s] >= 0) {
+                nchild[S.sn_parent[s]]++;
+                only_child[S.sn_parent[s]] = s;
+            }
+        int64_t total = 0;
+        for (int s = 0; s < ns; ++s) {
+            const int64_t nf = S.row_ptr[s + 1] - S.row_ptr[s];
+            const int c = only_child[s];
+            bool alias = false;
+            if (opt.alias_chains && nchild[s] == 1) {
+                const int64_t nfc = S.row_ptr[c + 1] - S.row_ptr[c];
+                const int64_t npc = S.sn_ptr[c + 1] - S.sn_ptr[c];
+                alias = (nfc - npc == nf);
+                if (alias) {
+                    S.front_ld[s] = S.front_ld[c];
+                    S.front_off[s] = S.front_off[c] + npc * ((int64_t)S.front_ld[c] + 1);
+                    S.in_place_child[c] = 1;
+                }
+            }
+            if (!alias) {
+                S.front_ld[s] = (int32_t)nf;
+                S.front_off[s] = total;
+                total += nf * nf;
+            }
+        }
+        S.front_off[ns] = total;
+    }
+    // solve work rows: one nf x k block per front; an in-place parent re-uses its child's update rows
+    S.has_in_place_child.assign(ns, 0);
+    {
+        int64_t wtotal = 0;
+        std::vector<int32_t> ipc(ns, -1);
+        for (int s = 0; s < ns; ++s)
+            if (S.in_place_child[s]) ipc[S.sn_parent[s]] = s;
+        for (int s = 0; s < ns; ++s) {
+            const int64_t nf = S.row_ptr[s + 1] - S.row_ptr[s];
+            if (ipc[s] >= 0) {
+                const int c = ipc[s];
+                S.has_in_place_child[s] = 1;
+                S.w_off[s] = S.w_off[c] + (S.sn_ptr[c + 1] - S.sn_ptr[c]);
+            } else {
+                S.w_off[s] = wtotal;
+                wtotal += nf;
+            }
+        }
+        S.w_off[ns] = wtotal;
+    }
     for (int s = 0; s < ns; ++s) {
         const int64_t nf = S.row_ptr[s + 1] - S.row_ptr[s];
         const int64_t np = S.sn_ptr[s + 1] - S.sn_ptr[s];
-        S.front_off[s + 1] = S.front_off[s] + nf * nf;
-        S.w_off[s + 1] = S.w_off[s] + nf;
         S.rel_ptr[s + 1] = S.rel_ptr[s] + (nf - np);
         S.nnz_factor += 2 * np * nf - np * np;
         S.max_nf = std::max<int>(S.max_nf, (int)nf);
@@ -552,7 +605,7 @@ int lu_symbolic_analyse(int n, const int32_t* rowptr, const int32_t* colind, con
             const int32_t* ri = std::lower_bound(r, r + nf, pi);
             const int32_t* rj = std::lower_bound(r, r + nf, pj);
             if (ri == r + nf || *ri != pi || rj == r + nf || *rj != pj) { bad2 = 1; continue; }
-            S.a_pos[e] = S.front_off[s] + (ri - r) + (rj - r) * nf;  // column-major front
+            S.a_pos[e] = S.front_off[s] + (ri - r) + (rj - r) * (int64_t)S.front_ld[s];  // column-major front
         }
     }
     NEPB_CHECK_ARG(!bad2, "internal: a matrix entry does not fall into its front");

@@ -19,14 +19,17 @@ struct LuSymbolic {
     std::vector<int32_t> col_sn;     // [n] supernode of a permuted column
     std::vector<int64_t> row_ptr;    // [nsuper+1] offsets into rows
     std::vector<int32_t> rows;       // front row structure: np pivots first, then the update rows (ascending)
-    std::vector<int64_t> front_off;  // [nsuper+1] offsets (in complex elements) of the nf x nf fronts
+    std::vector<int64_t> front_off;  // [nsuper] offsets (in complex elements) of the fronts; [nsuper] = total storage
+    std::vector<int32_t> front_ld;   // [nsuper] leading dimension (nf, or the owner's when the front lives inside its child)
+    std::vector<uint8_t> in_place_child;  // [nsuper] 1 = this front's contribution block IS its parent's front
+    std::vector<uint8_t> has_in_place_child;  // [nsuper] 1 = one of the children is in place
     std::vector<int64_t> rel_ptr;    // [nsuper+1] offsets into rel
     std::vector<int32_t> rel;        // for the update rows of s: their position in the parent's row structure
     std::vector<int32_t> level;      // [nsuper] height above the leaves
     int nlevels = 0;
     std::vector<int32_t> level_ptr, level_list;  // supernodes grouped by level
     std::vector<int64_t> a_pos;      // [nnz] CSR nonzero -> offset in the front storage
-    std::vector<int64_t> w_off;      // [nsuper+1] offsets into the solve work vector (nf rows each)
+    std::vector<int64_t> w_off;      // [nsuper] offsets into the solve work rows (nf each; in-place parents alias); [nsuper] = total
     int64_t front_total = 0, nnz_factor = 0, w_total = 0;
     double flops = 0;  // complex multiply-adds of the numeric factorisation
     int max_nf = 0, max_np = 0;
@@ -36,6 +39,7 @@ struct LuOptions {
     int relax_leaf = 16;   // subtrees with at most this many columns become one supernode
     int max_np = 32;       // cap on pivot columns per front (wider supernodes are split into chains)
     int ordering = 0;      // 0 = approximate minimum degree on A + A^T, 1 = natural
+    int alias_chains = 1;  // parent fronts with one structurally identical child live inside that child's storage
 };
 
 // csr rowptr/colind of the n x n union pattern (0-based, int32); user_perm optional (perm[new] = old)
