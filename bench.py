@@ -394,7 +394,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=1000, help="C4 grid side (n = grid^2)")
-    ap.add_argument("--batch", type=int, default=32, help="quadrature nodes factorised concurrently per GPU")
+    ap.add_argument("--batch", type=int, default=128, help="quadrature nodes factorised concurrently per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spmm", action="store_true")
     ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)

@@ -116,12 +116,15 @@ int nepb_lu_set_options(nepb_spmf* h, int ordering, int relax_leaf, int max_np, 
 int nepb_lu_symbolic_info(const nepb_spmf* h, int64_t* nnz_factor, int64_t* front_entries, int* nfronts, int* nlevels,
                           int* max_front, double* flops);
 /* integer results of the analysis (0-based): perm[n] new->old, etree parent[n] (-1 root), sn_ptr[nfronts+1],
- * sn_parent[nfronts]; any pointer may be NULL */
-int nepb_lu_symbolic_get(const nepb_spmf* h, int32_t* perm, int32_t* parent, int32_t* sn_ptr, int32_t* sn_parent);
+ * sn_parent[nfronts], sn_rows[nfronts] (front order nf), sn_level[nfronts]; any pointer may be NULL */
+int nepb_lu_symbolic_get(const nepb_spmf* h, int32_t* perm, int32_t* parent, int32_t* sn_ptr, int32_t* sn_parent,
+                         int32_t* sn_rows, int32_t* sn_level);
 /* the same analysis for an arbitrary pattern on the host only (no device needed); stats[8] = nnz(L+U), front
- * entries, fronts, levels, max front, max pivot block, factor multiply-adds, solve work rows */
+ * entries, fronts, levels, max front, max pivot block, factor multiply-adds, solve work rows; sn_ptr[n+1],
+ * sn_rows[n], sn_level[n] (optional, caller-allocated for the worst case of n fronts) describe the fronts */
 int nepb_lu_analyse_pattern(int64_t n, const int64_t* colptr, const int64_t* rowval, int index_base, int ordering,
-                            int relax_leaf, int max_np, int32_t* perm, int32_t* parent, int32_t* colcount, double* stats);
+                            int relax_leaf, int max_np, int32_t* perm, int32_t* parent, int32_t* colcount, double* stats,
+                            int32_t* sn_ptr, int32_t* sn_rows, int32_t* sn_level);
 /* factorise nshift matrices at once: coef is nshift x p complex, row s = (f_1(sigma_s) .. f_p(sigma_s)) */
 int nepb_lu_create(const nepb_spmf* h, int nshift, const double* coef, nepb_lu** out);
 int nepb_lu_destroy(nepb_lu* lu);

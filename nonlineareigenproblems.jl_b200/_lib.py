@@ -80,8 +80,8 @@ SIGNATURES = {
     "nepb_spmf_apply_bytes": (c_i64, [vp, c_int, c_int, c_int]),
     "nepb_lu_set_options": (c_int, [vp, c_int, c_int, c_int, vp]),
     "nepb_lu_symbolic_info": (c_int, [vp, P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_int), P(c_dbl)]),
-    "nepb_lu_symbolic_get": (c_int, [vp, vp, vp, vp, vp]),
-    "nepb_lu_analyse_pattern": (c_int, [c_i64, vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp, vp]),
+    "nepb_lu_symbolic_get": (c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "nepb_lu_analyse_pattern": (c_int, [c_i64, vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp]),
     "nepb_lu_create": (c_int, [vp, c_int, vp, P(vp)]),
     "nepb_lu_destroy": (c_int, [vp]),
     "nepb_lu_status": (c_int, [vp, c_int, P(c_int), P(c_int), P(c_dbl)]),

@@ -204,6 +204,194 @@ __global__ void __launch_bounds__(256) lu_diag_kernel(LuDev d, const int* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// diag, pivot blocks of at most 32 columns: ONE WARP per (front, shift), lane = row, the whole block in registers.
+// No shared memory and no block barriers: pivot search is a warp arg-max, row exchange and the rank-1 update use
+// shuffles.  Same pivoting rule and the same arithmetic order per entry as lu_diag_kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 shfl_c(double2 v, int src) {
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+__global__ void __launch_bounds__(32) lu_diag_warp_kernel(LuDev d, const int* __restrict__ items, double2* __restrict__ fronts,
+                                                          int* __restrict__ piv, LuInfo* __restrict__ info) {
+    constexpr int NP = 32;
+    const int s = items[blockIdx.x];
+    const int b = blockIdx.y;
+    const int np = d.np[s], ld = d.ld[s];
+    double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
+    int* pv = piv + (size_t)b * d.n + d.sn_ptr[s];
+    const int lane = threadIdx.x;
+    double2 a[NP];
+#pragma unroll
+    for (int c = 0; c < NP; ++c) a[c] = (lane < np && c < np) ? F[(size_t)lane + (size_t)c * ld] : make_double2(lane == c ? 1.0 : 0.0, 0.0);
+    const double amax = __longlong_as_double(info[b].amax_bits);
+    const double tiny = 2.220446049250313e-16 * amax;
+    double minratio = INFINITY;
+    int nperturbed = 0, flags = 0;
+    // j is a run-time loop (a fully unrolled elimination is instruction-fetch bound); the register array is only ever
+    // indexed by the unrolled c, column j is picked / written back with predicated moves.
+#pragma unroll 1
+    for (int j = 0; j < np; ++j) {
+        double2 aj = a[0];
+#pragma unroll
+        for (int c = 1; c < NP; ++c)
+            if (c == j) aj = a[c];
+        const double mine = cabs1(aj);
+        double best = (lane >= j && lane < np) ? ((mine == mine) ? mine : INFINITY) : -1.0;
+        int bi = lane;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        const double dj = __shfl_sync(0xffffffffu, mine, j);
+        if (dj >= 0.1 * best && dj == dj) bi = j;  // threshold pivoting that prefers the diagonal
+        if (bi != j) {
+            const int src = (lane == j) ? bi : j;
+#pragma unroll
+            for (int c = 0; c < NP; ++c) {
+                const double2 o = shfl_c(a[c], src);
+                if (lane == j || lane == bi) a[c] = o;
+            }
+            const double2 o = shfl_c(aj, src);
+            if (lane == j || lane == bi) aj = o;
+        }
+        double2 pvt = shfl_c(aj, j);
+        const double pa = cabs1(pvt);
+        if (!(pa <= 1.79e308) || !(best <= 1.79e308)) {
+            flags |= 2;
+            pvt = make_double2(1.0, 0.0);
+        } else if (pa == 0.0) {
+            flags |= 1;
+            ++nperturbed;
+            pvt = make_double2(tiny > 0.0 ? tiny : 1.0, 0.0);
+        } else if (pa < tiny) {
+            ++nperturbed;
+            const double sc = tiny / pa;
+            pvt = make_double2(pvt.x * sc, pvt.y * sc);
+        }
+        if (lane == 0) pv[j] = bi;
+        minratio = fmin(minratio, amax > 0.0 ? pa / amax : 0.0);
+        const double2 rp = crecip(pvt);
+        if (lane == j) aj = pvt;
+        if (lane > j) aj = cmul(aj, rp);  // multiplier l_ij
+#pragma unroll
+        for (int c = 0; c < NP; ++c) {
+            if (c == j) a[c] = aj;
+            if (c > j) {  // warp-uniform
+                const double2 rj = shfl_c(a[c], j);
+                if (lane > j) cfms(a[c], aj, rj);
+            }
+        }
+    }
+    if (lane < np) {
+#pragma unroll
+        for (int c = 0; c < NP; ++c)
+            if (c < np) F[(size_t)lane + (size_t)c * ld] = a[c];
+    }
+    if (lane == 0) {
+        if (flags) atomicOr(&info[b].flags, flags);
+        if (nperturbed) atomicAdd(&info[b].nperturbed, nperturbed);
+        atomicMin((unsigned long long*)&info[b].minpiv_bits, (unsigned long long)__double_as_longlong(minratio));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// panel for pivot blocks of at most 32 columns: the thread's column (row) lives in registers and both triangular
+// solves are fully unrolled, L11 / U11 come from shared memory as warp-wide broadcasts.
+// ---------------------------------------------------------------------------------------------
+constexpr size_t PANEL32_SMEM = (32 * 33 + 64 * 33 + 32) * 16;
+__global__ void __launch_bounds__(64) lu_panel32_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts,
+                                                        const int* __restrict__ piv) {
+    constexpr int NP = 32, LD = NP + 1, TW = 64;
+    extern __shared__ double2 sm[];
+    double2* sLU = sm;            // NP x LD
+    double2* sT = sLU + NP * LD;  // TW x LD
+    double2* srp = sT + TW * LD;  // NP
+    const int4 it = items[blockIdx.x];
+    const int s = it.x, kind = it.y, t0 = it.z;
+    const int b = blockIdx.y;
+    const int nf = d.ld[s], np = d.np[s], ncb = d.nf[s] - np;
+    double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
+    const int* pv = piv + (size_t)b * d.n + d.sn_ptr[s];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < NP * NP; idx += 64) {
+        const int i = idx % NP, j = idx / NP;
+        sLU[i + j * LD] = (i < np && j < np) ? F[(size_t)i + (size_t)j * nf] : make_double2(i == j ? 1.0 : 0.0, 0.0);
+    }
+    const int tw = min(TW, ncb - t0);
+    if (kind == 0) {
+        for (int idx = tid; idx < tw * NP; idx += 64) {
+            const int i = idx % NP, c = idx / NP;
+            sT[i + c * LD] = (i < np) ? F[(size_t)i + (size_t)(np + t0 + c) * nf] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        if (tid < tw) {
+            double2* xs = sT + tid * LD;
+            for (int j = 0; j < np; ++j) {
+                const int pr = pv[j];
+                if (pr != j) { const double2 t = xs[j]; xs[j] = xs[pr]; xs[pr] = t; }
+            }
+            double2 x[NP];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) x[i] = xs[i];
+#pragma unroll 1
+            for (int j = 0; j < np - 1; ++j) {  // run-time j, static register indices (see lu_diag_warp_kernel)
+                double2 xj = x[0];
+#pragma unroll
+                for (int i = 1; i < NP; ++i)
+                    if (i == j) xj = x[i];
+#pragma unroll
+                for (int i = 1; i < NP; ++i)
+                    if (i > j) cfms(x[i], sLU[i + j * LD], xj);
+            }
+#pragma unroll
+            for (int i = 0; i < NP; ++i) xs[i] = x[i];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < tw * np; idx += 64) {
+            const int i = idx % np, c = idx / np;
+            F[(size_t)i + (size_t)(np + t0 + c) * nf] = sT[i + c * LD];
+        }
+    } else {
+        for (int idx = tid; idx < TW * NP; idx += 64) {
+            const int r = idx % TW, j = idx / TW;
+            sT[r + j * TW] = (r < tw && j < np) ? F[(size_t)(np + t0 + r) + (size_t)j * nf] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        if (tid < NP) srp[tid] = crecip(sLU[tid + tid * LD]);
+        __syncthreads();
+        if (tid < tw) {
+            double2 x[NP];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) x[j] = sT[tid + j * TW];
+            // right-looking: once x_t is final, subtract x_t U[t, j] from every later column j
+#pragma unroll 1
+            for (int t = 0; t < np; ++t) {
+                double2 xt = x[0];
+#pragma unroll
+                for (int j = 1; j < NP; ++j)
+                    if (j == t) xt = x[j];
+                xt = cmul(xt, srp[t]);
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    if (j == t) x[j] = xt;
+                    if (j > t) cfms(x[j], xt, sLU[t + j * LD]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NP; ++j) sT[tid + j * TW] = x[j];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < tw * np; idx += 64) {
+            const int r = idx % tw, j = idx / tw;
+            F[(size_t)(np + t0 + r) + (size_t)j * nf] = sT[r + j * TW];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // panel: item = (front s, kind 0 = U tile / 1 = L tile, tile start t0); 64 columns (rows) per tile
 // ---------------------------------------------------------------------------------------------
 constexpr int PANEL_T = 64;
@@ -325,6 +513,99 @@ __global__ void __launch_bounds__(256) lu_schur_kernel(LuDev d, const int4* __re
             o.y -= acc[r][c].y;
             *t = o;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// schur, pipelined: item = (front s, row tile i0, first column tile j0, number of column tiles).  The L21 tile stays in
+// shared memory for all column tiles of the item; U12 tiles are double-buffered with cp.async so that the next tile
+// streams in while the current one is multiplied.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+constexpr int SCHUR_GROUP = 4;  // column tiles per item
+__global__ void __launch_bounds__(256, 2) lu_schur_pipe_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts) {
+    extern __shared__ double2 sm[];
+    const int4 it = items[blockIdx.x];
+    const int s = it.x, i0 = it.y, jfirst = it.z, ntiles = it.w;
+    const int b = blockIdx.y;
+    const int nf = d.ld[s], np = d.np[s], ncb = d.nf[s] - np;
+    double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
+    constexpr int ULD = SCHUR_T + 1;
+    double2* sL = sm;                         // [np][SCHUR_T]
+    double2* sU0 = sm + (size_t)np * SCHUR_T;  // 2 x [np][ULD]
+    const int tid = threadIdx.x;
+    const int th = min(SCHUR_T, ncb - i0);
+    auto stage_u = [&](int j0, double2* sU) {
+        const int tw = min(SCHUR_T, ncb - j0);
+        for (int idx = tid; idx < np * SCHUR_T; idx += 256) {
+            const int t = idx % np, c = idx / np;
+            if (c < tw) cp_async16(&sU[t * ULD + c], &F[(size_t)t + (size_t)(np + j0 + c) * nf]);
+            else sU[t * ULD + c] = make_double2(0.0, 0.0);
+        }
+    };
+    for (int idx = tid; idx < np * SCHUR_T; idx += 256) {
+        const int r = idx % SCHUR_T, t = idx / SCHUR_T;
+        if (r < th) cp_async16(&sL[idx], &F[(size_t)(np + i0 + r) + (size_t)t * nf]);
+        else sL[idx] = make_double2(0.0, 0.0);
+    }
+    stage_u(jfirst, sU0);
+    cp_async_commit();
+    const int tx = tid % 16, ty = tid / 16;
+    for (int q = 0; q < ntiles; ++q) {
+        const int j0 = jfirst + q * SCHUR_T;
+        double2* sU = sU0 + (size_t)(q & 1) * np * ULD;
+        if (q + 1 < ntiles) {
+            stage_u(j0 + SCHUR_T, sU0 + (size_t)((q + 1) & 1) * np * ULD);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int tw = min(SCHUR_T, ncb - j0);
+        double2 acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = make_double2(0.0, 0.0);
+#pragma unroll 2
+        for (int t = 0; t < np; ++t) {
+            double2 l[4], u[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) l[r] = sL[t * SCHUR_T + tx + 16 * r];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) u[c] = sU[t * ULD + ty + 16 * c];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) cfma2(acc[r][c], l[r], u[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int cc = ty + 16 * c;
+            if (cc < tw) {
+                double2* col = F + (size_t)(np + i0) + (size_t)(np + j0 + cc) * nf;
+                double2 o[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (tx + 16 * r < th) o[r] = col[tx + 16 * r];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (tx + 16 * r < th) {
+                        o[r].x -= acc[r][c].x;
+                        o[r].y -= acc[r][c].y;
+                        col[tx + 16 * r] = o[r];
+                    }
+            }
+        }
+        __syncthreads();  // the buffer of tile q is refilled in iteration q + 1
     }
 }
 
@@ -696,7 +977,7 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     // per-level work lists
     sd->lv.resize(S.nlevels);
     std::vector<int32_t> fr_items;
-    std::vector<int4> ea_items, pn_items, sc_items, fu_items, bp_items;
+    std::vector<int4> ea_items, pn_items, sc_items, sp_items, fu_items, bp_items;
     std::vector<int32_t> bw_slot(ns, 0);
     sd->part_slots = 0;
     for (int l = 0; l < S.nlevels; ++l) {
@@ -705,6 +986,7 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
         L.ea_begin = (int)ea_items.size();
         L.pn_begin = (int)pn_items.size();
         L.sc_begin = (int)sc_items.size();
+        L.sp_begin = (int)sp_items.size();
         L.fu_begin = (int)fu_items.size();
         L.bp_begin = (int)bp_items.size();
         int slots = 0;
@@ -728,6 +1010,9 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
             }
             for (int j0 = 0; j0 < ncb; j0 += SCHUR_T)
                 for (int i0 = 0; i0 < ncb; i0 += SCHUR_T) sc_items.push_back(make_int4(s, i0, j0, 0));
+            for (int j0 = 0; j0 < ncb; j0 += SCHUR_T * SCHUR_GROUP)
+                for (int i0 = 0; i0 < ncb; i0 += SCHUR_T)
+                    sp_items.push_back(make_int4(s, i0, j0, std::min(SCHUR_GROUP, (ncb - j0 + SCHUR_T - 1) / SCHUR_T)));
             if (ncb > SOLVE_BIG) {
                 bw_slot[s] = slots;
                 for (int r0 = 0; r0 < ncb; r0 += SOLVE_CHUNK) {
@@ -743,6 +1028,7 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
         L.ea_count = (int)ea_items.size() - L.ea_begin;
         L.pn_count = (int)pn_items.size() - L.pn_begin;
         L.sc_count = (int)sc_items.size() - L.sc_begin;
+        L.sp_count = (int)sp_items.size() - L.sp_begin;
     }
     cudaError_t e = cudaSuccess;
 #define UP(buf, vec) if (e == cudaSuccess) e = upload(buf, vec)
@@ -766,6 +1052,7 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     UP(sd->ea_items, ea_items);
     UP(sd->pn_items, pn_items);
     UP(sd->sc_items, sc_items);
+    UP(sd->sp_items, sp_items);
     UP(sd->fu_items, fu_items);
     UP(sd->bp_items, bp_items);
     UP(sd->bw_slot, bw_slot);
@@ -800,9 +1087,13 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     sd->smem_diag = (size_t)mnp * (mnp + 1) * 16;
     sd->smem_panel = ((size_t)mnp * (mnp + 1) + (size_t)PANEL_T * (mnp + 1)) * 16;
     sd->smem_schur = (size_t)mnp * (2 * SCHUR_T + 1) * 16;
+    sd->smem_schur_pipe = (size_t)mnp * (3 * SCHUR_T + 2) * 16;
+    sd->schur_pipe = sd->smem_schur_pipe <= 110 * 1024 && !getenv("NEPB_LU_SCHUR_SIMPLE");
+    cudaFuncSetAttribute(lu_schur_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_schur_pipe);
     cudaFuncSetAttribute(lu_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_diag);
     cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_panel);
     cudaFuncSetAttribute(lu_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_schur);
+    cudaFuncSetAttribute(lu_panel32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL32_SMEM);
 #define NEPB_SOLVE_ATTR(CK_)                                                                                    \
     cudaFuncSetAttribute(lu_forward_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);       \
     cudaFuncSetAttribute(lu_backward_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);       \
@@ -841,9 +1132,17 @@ static int lu_factor_device(nepb_lu* lu) {
     for (int l = 0; l < S.nlevels; ++l) {
         const auto& L = sd->lv[l];
         if (L.ea_count) NEPB_LAUNCH(lu_extend_add_kernel, dim3(L.ea_count, nb), 256, 0, sd->dev, sd->ea_items.p + L.ea_begin, F);
-        NEPB_LAUNCH(lu_diag_kernel, dim3(L.front_count, nb), 256, sd->smem_diag, sd->dev, sd->fr_items.p + L.front_begin, F, lu->piv.p, lu->info.p);
-        if (L.pn_count) NEPB_LAUNCH(lu_panel_kernel, dim3(L.pn_count, nb), 128, sd->smem_panel, sd->dev, sd->pn_items.p + L.pn_begin, F, lu->piv.p);
-        if (L.sc_count) NEPB_LAUNCH(lu_schur_kernel, dim3(L.sc_count, nb), 256, sd->smem_schur, sd->dev, sd->sc_items.p + L.sc_begin, F);
+        if (S.max_np <= 32) {
+            NEPB_LAUNCH(lu_diag_warp_kernel, dim3(L.front_count, nb), 32, 0, sd->dev, sd->fr_items.p + L.front_begin, F, lu->piv.p, lu->info.p);
+            if (L.pn_count) NEPB_LAUNCH(lu_panel32_kernel, dim3(L.pn_count, nb), 64, PANEL32_SMEM, sd->dev, sd->pn_items.p + L.pn_begin, F, lu->piv.p);
+        } else {
+            NEPB_LAUNCH(lu_diag_kernel, dim3(L.front_count, nb), 256, sd->smem_diag, sd->dev, sd->fr_items.p + L.front_begin, F, lu->piv.p, lu->info.p);
+            if (L.pn_count) NEPB_LAUNCH(lu_panel_kernel, dim3(L.pn_count, nb), 128, sd->smem_panel, sd->dev, sd->pn_items.p + L.pn_begin, F, lu->piv.p);
+        }
+        if (L.sc_count && sd->schur_pipe)
+            NEPB_LAUNCH(lu_schur_pipe_kernel, dim3(L.sp_count, nb), 256, sd->smem_schur_pipe, sd->dev, sd->sp_items.p + L.sp_begin, F);
+        else if (L.sc_count)
+            NEPB_LAUNCH(lu_schur_kernel, dim3(L.sc_count, nb), 256, sd->smem_schur, sd->dev, sd->sc_items.p + L.sc_begin, F);
     }
     NEPB_LAUNCH_CHECK();
     return NEPB_OK;
@@ -985,7 +1284,8 @@ int nepb_lu_symbolic_info(const nepb_spmf* h, int64_t* nnz_factor, int64_t* fron
     return NEPB_OK;
 }
 
-int nepb_lu_symbolic_get(const nepb_spmf* h, int32_t* perm, int32_t* parent, int32_t* sn_ptr, int32_t* sn_parent) {
+int nepb_lu_symbolic_get(const nepb_spmf* h, int32_t* perm, int32_t* parent, int32_t* sn_ptr, int32_t* sn_parent, int32_t* sn_rows,
+                         int32_t* sn_level) {
     NEPB_CHECK_ARG(h, "handle is NULL");
     LuSymbolicDev* sd = nullptr;
     int rc = lu_symbolic_get(h, &sd);
@@ -995,11 +1295,15 @@ int nepb_lu_symbolic_get(const nepb_spmf* h, int32_t* perm, int32_t* parent, int
     if (parent) memcpy(parent, S.parent.data(), sizeof(int32_t) * S.n);
     if (sn_ptr) memcpy(sn_ptr, S.sn_ptr.data(), sizeof(int32_t) * (S.nsuper + 1));
     if (sn_parent) memcpy(sn_parent, S.sn_parent.data(), sizeof(int32_t) * S.nsuper);
+    if (sn_rows)
+        for (int s = 0; s < S.nsuper; ++s) sn_rows[s] = (int32_t)(S.row_ptr[s + 1] - S.row_ptr[s]);
+    if (sn_level) memcpy(sn_level, S.level.data(), sizeof(int32_t) * S.nsuper);
     return NEPB_OK;
 }
 
 int nepb_lu_analyse_pattern(int64_t n, const int64_t* colptr, const int64_t* rowval, int index_base, int ordering, int relax_leaf,
-                            int max_np, int32_t* perm, int32_t* parent, int32_t* colcount, double* stats) {
+                            int max_np, int32_t* perm, int32_t* parent, int32_t* colcount, double* stats, int32_t* sn_ptr,
+                            int32_t* sn_rows, int32_t* sn_level) {
     NEPB_CHECK_ARG(n >= 1 && n < ((int64_t)1 << 31) && colptr && rowval, "bad arguments");
     const int64_t nnz = colptr[n] - index_base;
     NEPB_CHECK_ARG(nnz >= 0 && nnz < ((int64_t)1 << 31), "pattern too large");
@@ -1030,6 +1334,10 @@ int nepb_lu_analyse_pattern(int64_t n, const int64_t* colptr, const int64_t* row
         stats[6] = S.flops;
         stats[7] = (double)S.w_total;
     }
+    if (sn_ptr) memcpy(sn_ptr, S.sn_ptr.data(), sizeof(int32_t) * (S.nsuper + 1));
+    if (sn_rows)
+        for (int s = 0; s < S.nsuper; ++s) sn_rows[s] = (int32_t)(S.row_ptr[s + 1] - S.row_ptr[s]);
+    if (sn_level) memcpy(sn_level, S.level.data(), sizeof(int32_t) * S.nsuper);
     return NEPB_OK;
 }
 

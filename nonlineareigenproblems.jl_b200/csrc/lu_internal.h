@@ -39,6 +39,7 @@ struct LuLevel {
     int ea_begin = 0, ea_count = 0;
     int pn_begin = 0, pn_count = 0;
     int sc_begin = 0, sc_count = 0;
+    int sp_begin = 0, sp_count = 0;  // pipelined schur items
     int fu_begin = 0, fu_count = 0;  // forward update items (big fronts)
     int bp_begin = 0, bp_count = 0;  // backward partial-product items (big fronts)
 };
@@ -52,8 +53,9 @@ struct LuSymbolicDev {
     DevBuf<int32_t> bw_slot;
     int part_slots = 0;
     DevBuf<int32_t> nf, np, ld, rows, rel, sn_ptr, child_ptr, child_list, perm, iperm, fr_items;
-    DevBuf<int4> ea_items, pn_items, sc_items, fu_items, bp_items;
-    size_t smem_diag = 0, smem_panel = 0, smem_schur = 0;
+    DevBuf<int4> ea_items, pn_items, sc_items, sp_items, fu_items, bp_items;
+    size_t smem_diag = 0, smem_panel = 0, smem_schur = 0, smem_schur_pipe = 0;
+    bool schur_pipe = false;
 };
 
 int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out);

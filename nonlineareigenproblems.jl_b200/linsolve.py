@@ -72,19 +72,36 @@ def symbolic_get(nep: B200SPMF):
     parent = np.empty(nep.n, np.int32)
     sn_ptr = np.empty(info["nfronts"] + 1, np.int32)
     sn_parent = np.empty(info["nfronts"], np.int32)
-    check(lib.nepb_lu_symbolic_get(nep._h, ptr(perm), ptr(parent), ptr(sn_ptr), ptr(sn_parent)))
+    check(lib.nepb_lu_symbolic_get(nep._h, ptr(perm), ptr(parent), ptr(sn_ptr), ptr(sn_parent), None, None))
     return perm, parent, sn_ptr, sn_parent
 
 
-def analyse_pattern(A, ordering=0, relax_leaf=0, max_np=0):
+def symbolic_fronts(nep: B200SPMF):
+    """(pivot columns, front order, level) of every front."""
+    info = symbolic_info(nep)
+    ns = info["nfronts"]
+    sn_ptr, rows, level = np.empty(ns + 1, np.int32), np.empty(ns, np.int32), np.empty(ns, np.int32)
+    check(lib.nepb_lu_symbolic_get(nep._h, None, None, ptr(sn_ptr), None, ptr(rows), ptr(level)))
+    return np.diff(sn_ptr), rows, level
+
+
+def analyse_pattern(A, ordering=0, relax_leaf=0, max_np=0, fronts=False):
     """Host-only symbolic analysis of the pattern of a scipy sparse matrix (no device needed)."""
     A = A.tocsc()
     n = A.shape[0]
     cp, rv = A.indptr.astype(np.int64), A.indices.astype(np.int64)
     perm, parent, cc, st = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.int32), np.zeros(8)
-    check(lib.nepb_lu_analyse_pattern(n, ptr(cp), ptr(rv), 0, ordering, relax_leaf, max_np, ptr(perm), ptr(parent), ptr(cc), ptr(st)))
+    sn_ptr, sn_rows, sn_level = np.zeros(n + 1, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    check(lib.nepb_lu_analyse_pattern(n, ptr(cp), ptr(rv), 0, ordering, relax_leaf, max_np, ptr(perm), ptr(parent), ptr(cc), ptr(st),
+                                      ptr(sn_ptr), ptr(sn_rows), ptr(sn_level)))
     keys = ("nnz_factor", "front_entries", "nfronts", "nlevels", "max_front", "max_np", "flops", "solve_rows")
-    return perm, parent, cc, dict(zip(keys, st))
+    info = dict(zip(keys, st))
+    if fronts:
+        ns = int(info["nfronts"])
+        info["np"] = np.diff(sn_ptr[:ns + 1])
+        info["nf"] = sn_rows[:ns].copy()
+        info["level"] = sn_level[:ns].copy()
+    return perm, parent, cc, info
 
 
 # ---------------------------------------------------------------------------------------------
