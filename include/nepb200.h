@@ -101,6 +101,9 @@ void* nepb_block_dev_ptr(nepb_block* b);
 /* same product with operands already in HBM: no host traffic, asynchronous on the library stream */
 int nepb_spmf_apply_block(const nepb_spmf* h, int mode, const nepb_block* V, int q, const double* C,
                           nepb_block* Z);
+/* the same on column windows: Z[:, zcol0 : zcol0+q) = sum_i A_i (V[:, vcol0 : vcol0+k) C_i) */
+int nepb_spmf_apply_block_ex(const nepb_spmf* h, int mode, const nepb_block* V, int vcol0, int k, int q, const double* C,
+                             nepb_block* Z, int zcol0);
 /* algorithmic HBM bytes of one nepb_spmf_apply_block call (SURVEY.md 8(d) formula) */
 int64_t nepb_spmf_apply_bytes(const nepb_spmf* h, int mode, int k, int q);
 
@@ -136,6 +139,30 @@ int nepb_lu_status(const nepb_lu* lu, int shift, int* flags, int* nperturbed, do
  * receives the final normwise backward error. */
 int nepb_lu_solve(nepb_lu* lu, int shift, int nrhs, const double* B, int64_t ldb, double* X, int64_t ldx, int refine_steps,
                   double* berr_out);
+
+/* device-resident lin_solve: X[:, xcol0 : xcol0+nrhs) = alpha * M(sigma_shift)^-1 B[:, bcol0 : bcol0+nrhs), alpha complex
+ * (NULL = 1); used by iar / tiar / resinv loops that keep their vectors in HBM (y[:,1] = -lin_solve(..), method_iar.jl:103) */
+int nepb_lu_solve_block(nepb_lu* lu, int shift, const nepb_block* B, int bcol0, int nrhs, nepb_block* X, int xcol0,
+                        const double* alpha);
+
+/* ---- a11: dense tall-skinny blocks of iar / tiar (src/method_iar.jl:100-116, src/method_tiar.jl:119,128,187-189) ---
+ * orthogonalize_and_normalize!(V[:, 0:k), w, h, DGKS()) with w = W[:, wcol] (V and W may be the same block), over the
+ * first `rows` rows (0 = all): classical Gram-Schmidt, re-orthogonalised while ||w|| < ||h||/sqrt(2), w normalised in
+ * place; h[k] (host complex) receives the accumulated coefficients, *nrm_out the norm before normalisation. */
+int nepb_orth_dgks(const nepb_block* V, int k, nepb_block* W, int wcol, int64_t rows, double* h, double* nrm_out, int* sweeps);
+/* Y[:, ycol0 : ycol0+q) = A[:, acol0 : acol0+ka) * C, C host column-major ka x q complex (leading dimension ldc),
+ * FP64 tensor cores (DMMA); Z*a', VV*W, Q = V*Z of the Arnoldi callers */
+int nepb_block_gemm(const nepb_block* A, int acol0, int ka, const double* C, int64_t ldc, int q, nepb_block* Y, int ycol0,
+                    int64_t rows);
+/* dst[:, d0 : d0+nc) = alpha * src[:, s0 : s0+nc) (alpha complex, NULL = 1) */
+int nepb_block_copy_cols(const nepb_block* src, int s0, int nc, nepb_block* dst, int d0, const double* alpha, int64_t rows);
+
+/* iar's block shift and re-packing (src/method_iar.jl:100-101,105) on a basis block of n*(m+1) rows:
+ * expand: Y[i, ycol0+b] = V[b*n+i, vcol] / (b+1 if scale_by_index)   pack: V[b*n+i, vcol] = Y[i, ycol0+b],  b < nb */
+int nepb_iar_expand(const nepb_block* V, int vcol, int64_t n, int nb, nepb_block* Y, int ycol0, int scale_by_index);
+int nepb_iar_pack(const nepb_block* Y, int ycol0, int nb, int64_t n, nepb_block* V, int vcol);
+/* out[c] = ||A[0:rows, c0+c]||_2 (residual norms of all Ritz pairs, src/method_iar.jl:134-135) */
+int nepb_block_colnorms(const nepb_block* A, int c0, int nc, int64_t rows, double* out);
 
 /* ---- a9,a10: contour quadrature, sharded over ranks (src/method_contour_common.jl:61-94) ---------------------
  * S[:,:,j] = sum_i w[i,j] * M(lambda_i)^-1 Vh over the quadrature nodes this rank owns.  coef is nnodes x p complex

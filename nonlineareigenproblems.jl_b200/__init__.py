@@ -18,3 +18,5 @@ from .linsolve import (B200LU, B200FactorizeLinSolver, B200BackslashLinSolver, B
 from .solvers import (contour_beyn, ContourIntegrator, beyn_extract, iar, tiar, resinv, compute_rf, dgks_host,  # noqa: F401
                       ResidualErrmeasure, StandardSPMFErrmeasure, DefaultErrmeasure, NoConvergenceException,
                       LostOrthogonalityException)
+from .dense import (dgks, block_gemm, copy_cols, colnorms, solve_block, mlincomb_block, residual_errors,  # noqa: F401
+                    tiar_device, iar_device)

@@ -97,6 +97,14 @@ SIGNATURES = {
     "nepb_comm_destroy": (c_int, []),
     "nepb_comm_info": (c_int, [P(c_int), P(c_int), P(c_int)]),
     "nepb_comm_allreduce_sum_dev": (c_int, [vp, c_i64]),
+    "nepb_spmf_apply_block_ex": (c_int, [vp, c_int, vp, c_int, c_int, c_int, vp, vp, c_int]),
+    "nepb_lu_solve_block": (c_int, [vp, c_int, vp, c_int, c_int, vp, c_int, vp]),
+    "nepb_orth_dgks": (c_int, [vp, c_int, vp, c_int, c_i64, vp, P(c_dbl), P(c_int)]),
+    "nepb_block_gemm": (c_int, [vp, c_int, c_int, vp, c_i64, c_int, vp, c_int, c_i64]),
+    "nepb_block_copy_cols": (c_int, [vp, c_int, c_int, vp, c_int, vp, c_i64]),
+    "nepb_iar_expand": (c_int, [vp, c_int, c_i64, c_int, vp, c_int, c_int]),
+    "nepb_iar_pack": (c_int, [vp, c_int, c_int, c_i64, vp, c_int]),
+    "nepb_block_colnorms": (c_int, [vp, c_int, c_int, c_i64, vp]),
     "nepb_msws_init": (c_int, [C.c_uint64, C.c_uint64, vp]),
     "nepb_msws_fill": (c_int, [vp, c_i64, vp]),
 }

@@ -905,6 +905,20 @@ __global__ void contour_accumulate_kernel(size_t nk, int nb, int mg, const doubl
     }
 }
 
+// gather / scatter of column windows between a wide row-major block and the contiguous solve buffers
+__global__ void __launch_bounds__(256) cols_gather_kernel(int64_t n, int nc, const double2* __restrict__ src, int lds, double2* __restrict__ dst) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * nc) return;
+    dst[idx] = src[(size_t)(idx / nc) * lds + idx % nc];
+}
+__global__ void __launch_bounds__(256) cols_scatter_kernel(int64_t n, int nc, const double2* __restrict__ src, double2* __restrict__ dst, int ldd,
+                                                           double2 alpha) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * nc) return;
+    const double2 v = src[idx];
+    dst[(size_t)(idx / nc) * ldd + idx % nc] = make_double2(alpha.x * v.x - alpha.y * v.y, alpha.x * v.y + alpha.y * v.x);
+}
+
 // R = B - R  (residual from M*X), elementwise
 __global__ void __launch_bounds__(256) residual_kernel(size_t count, const double2* __restrict__ Bm, double2* __restrict__ R) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1437,6 +1451,29 @@ int nepb_lu_solve(nepb_lu* lu, int shift, int nrhs, const double* B, int64_t ldb
         if (rc) return rc;
     }
     if (berr_out) *berr_out = worst;
+    return NEPB_OK;
+}
+
+// Device-resident lin_solve: X[:, xcol0 : xcol0+nrhs) = alpha * M(sigma_shift)^-1 B[:, bcol0 : bcol0+nrhs); nothing crosses PCIe.
+int nepb_lu_solve_block(nepb_lu* lu, int shift, const nepb_block* B, int bcol0, int nrhs, nepb_block* X, int xcol0, const double* alpha) {
+    NEPB_CHECK_ARG(lu && B && X, "NULL argument");
+    NEPB_CHECK_ARG(shift >= 0 && shift < lu->nb, "shift index out of range");
+    const int64_t n = lu->op->n;
+    NEPB_CHECK_ARG(B->n == n && X->n == n, "block row count differs from the operator size");
+    NEPB_CHECK_ARG(nrhs >= 1 && nrhs <= 64 && bcol0 >= 0 && bcol0 + nrhs <= B->k && xcol0 >= 0 && xcol0 + nrhs <= X->k, "bad column windows");
+    if (lu->h_info[shift].flags & 2) {
+        set_error("non-finite pivot in the factorisation of shift %d", shift);
+        return NEPB_E_SINGULAR;
+    }
+    NEPB_CUDA(lu->rhs.reserve((size_t)2 * n * nrhs));
+    NEPB_CUDA(lu->sol.reserve((size_t)2 * n * nrhs));
+    const unsigned gb = (unsigned)((n * nrhs + 255) / 256);
+    NEPB_LAUNCH(cols_gather_kernel, gb, 256, 0, n, nrhs, (const double2*)B->d.p + bcol0, B->k, (double2*)lu->rhs.p);
+    int rc = lu_solve_device(lu, shift, 1, nrhs, (const double2*)lu->rhs.p, 0, (double2*)lu->sol.p);
+    if (rc) return rc;
+    const double2 a = alpha ? make_double2(alpha[0], alpha[1]) : make_double2(1.0, 0.0);
+    NEPB_LAUNCH(cols_scatter_kernel, gb, 256, 0, n, nrhs, (const double2*)lu->sol.p, (double2*)X->d.p + xcol0, X->k, a);
+    NEPB_LAUNCH_CHECK();
     return NEPB_OK;
 }
 

@@ -532,7 +532,13 @@ static int launch_stacked(const nepb_spmf* h, int q, const double2* X, double2* 
 }
 
 // Z = sum_i A_i (V C_i) with device row-major operands (dV: n x k, ld k ; dZ: n x q, ld q)
+int spmf_apply_device_ld(const nepb_spmf* h, int mode, int k, int q, const double2* dV, int ldv, const double* C, double2* dZ, int ldz);
 int spmf_apply_device(const nepb_spmf* h, int mode, int k, int q, const double2* dV, const double* C, double2* dZ) {
+    return spmf_apply_device_ld(h, mode, k, q, dV, k, C, dZ, q);
+}
+
+// operands with explicit leading dimensions (column windows of wider row-major blocks)
+int spmf_apply_device_ld(const nepb_spmf* h, int mode, int k, int q, const double2* dV, int ldv, const double* C, double2* dZ, int ldz) {
     NEPB_CHECK_ARG(h && dV && dZ && C, "NULL argument");
     NEPB_CHECK_ARG(k >= 1 && q >= 1, "k and q must be positive (k=%d q=%d)", k, q);
     const int p = h->p;
@@ -551,7 +557,7 @@ int spmf_apply_device(const nepb_spmf* h, int mode, int k, int q, const double2*
         }
         for (int k0 = 0; k0 < k; k0 += 32) {
             const int kt = std::min(32, k - k0);
-            int rc = launch_fused(h, mode == NEPB_COEF_DIAG, kt, k, k, dV + k0, dZ + k0, cp, cdiag ? cdiag + (size_t)p * k0 : nullptr);
+            int rc = launch_fused(h, mode == NEPB_COEF_DIAG, kt, ldv, ldz, dV + k0, dZ + k0, cp, cdiag ? cdiag + (size_t)p * k0 : nullptr);
             if (rc) return rc;
         }
         return NEPB_OK;
@@ -572,10 +578,10 @@ int spmf_apply_device(const nepb_spmf* h, int mode, int k, int q, const double2*
     NEPB_CUDA(cudaMemcpyAsync(h->d_coef.p, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice, stream()));
     NEPB_CUDA(cudaStreamSynchronize(stream()));  // cs is a local buffer
     NEPB_CUDA(h->d_tmp_x.reserve((size_t)2 * h->n * w));
-    NEPB_LAUNCH(panel_gemm_kernel, (int)((h->n + PANEL_R - 1) / PANEL_R), 256, 0, (int)h->n, k, w, dV, k,
+    NEPB_LAUNCH(panel_gemm_kernel, (int)((h->n + PANEL_R - 1) / PANEL_R), 256, 0, (int)h->n, k, w, dV, ldv,
                 (const double2*)h->d_coef.p, (double2*)h->d_tmp_x.p);
     NEPB_LAUNCH_CHECK();
-    return launch_stacked(h, q, (const double2*)h->d_tmp_x.p, dZ, q);
+    return launch_stacked(h, q, (const double2*)h->d_tmp_x.p, dZ, ldz);
 }
 
 int upload_colmajor(int64_t n, int kc, const double* host, int64_t ld, DevBuf<double>& stage, double* dst, int ldd, int k0) {
@@ -771,6 +777,15 @@ int nepb_spmf_apply_block(const nepb_spmf* h, int mode, const nepb_block* V, int
     NEPB_CHECK_ARG(Z->k == q, "Z has %d columns, expected q=%d", Z->k, q);
     NEPB_CHECK_ARG(V->d.p != Z->d.p, "V and Z must not alias");
     return spmf_apply_device(h, mode, V->k, q, (const double2*)V->d.p, C, (double2*)Z->d.p);
+}
+
+int nepb_spmf_apply_block_ex(const nepb_spmf* h, int mode, const nepb_block* V, int vcol0, int k, int q, const double* C, nepb_block* Z,
+                             int zcol0) {
+    NEPB_CHECK_ARG(h && V && Z && C, "NULL argument");
+    NEPB_CHECK_ARG(V->n == h->n && Z->n == h->n, "block row count differs from the operator size");
+    NEPB_CHECK_ARG(vcol0 >= 0 && k >= 1 && vcol0 + k <= V->k && zcol0 >= 0 && q >= 1 && zcol0 + q <= Z->k, "bad column windows");
+    NEPB_CHECK_ARG(!(V == Z && zcol0 < vcol0 + k && vcol0 < zcol0 + q), "input and output columns overlap");
+    return spmf_apply_device_ld(h, mode, k, q, (const double2*)V->d.p + vcol0, V->k, C, (double2*)Z->d.p + zcol0, Z->k);
 }
 
 int64_t nepb_spmf_apply_bytes(const nepb_spmf* h, int mode, int k, int q) {

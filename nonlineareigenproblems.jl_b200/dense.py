@@ -1,0 +1,198 @@
+"""Device-resident dense blocks for the infinite-Arnoldi callers (host-side mirror).
+
+Mirrors the orthogonalisation hook `orthogonalize_and_normalize!(V, w, h, method)` that iar / tiar / nleigs dispatch on
+(src/method_iar.jl:107, src/method_tiar.jl:128; a user subtype is the documented extension point, test/iar.jl:7-17) and
+the tall-skinny products of src/method_tiar.jl:119,187-189 and src/method_iar.jl:114-115, with the Krylov basis kept in
+HBM (nepb_block) so that no basis vector crosses PCIe inside the solver loop.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, ptr
+from .neptypes import Block, B200SPMF
+from .linsolve import B200LinSolverCreator
+from .solvers import DefaultErrmeasure, NoConvergenceException, LostOrthogonalityException
+
+
+def dgks(V: Block, k: int, W: Block, wcol: int, rows: int = 0):
+    """B200DGKS: returns (h, norm, sweeps); w = W[:, wcol] is orthogonalised against V[:, :k] and normalised in HBM."""
+    h = np.zeros(max(k, 1), dtype=np.complex128)
+    nrm, sweeps = C.c_double(), C.c_int()
+    check(lib.nepb_orth_dgks(V._h, k, W._h, wcol, rows, ptr(h), C.byref(nrm), C.byref(sweeps)))
+    return h[:k], nrm.value, sweeps.value
+
+
+def block_gemm(A: Block, acol0: int, ka: int, Cm, Y: Block, ycol0: int, rows: int = 0):
+    Cm = np.asfortranarray(np.asarray(Cm, dtype=np.complex128))
+    if Cm.ndim == 1:
+        Cm = Cm.reshape(-1, 1, order="F")
+    assert Cm.shape[0] == ka
+    check(lib.nepb_block_gemm(A._h, acol0, ka, ptr(Cm), Cm.shape[0], Cm.shape[1], Y._h, ycol0, rows))
+
+
+def copy_cols(src: Block, s0: int, nc: int, dst: Block, d0: int, alpha=1.0, rows: int = 0):
+    a = np.array([complex(alpha)], dtype=np.complex128)
+    check(lib.nepb_block_copy_cols(src._h, s0, nc, dst._h, d0, ptr(a), rows))
+
+
+def colnorms(A: Block, c0: int, nc: int, rows: int = 0):
+    out = np.zeros(nc)
+    check(lib.nepb_block_colnorms(A._h, c0, nc, rows, ptr(out)))
+    return out
+
+
+def solve_block(lu, Bb: Block, bcol0: int, nrhs: int, Xb: Block, xcol0: int, alpha=1.0, shift=0):
+    a = np.array([complex(alpha)], dtype=np.complex128)
+    check(lib.nepb_lu_solve_block(lu._h, shift, Bb._h, bcol0, nrhs, Xb._h, xcol0, ptr(a)))
+
+
+def mlincomb_block(nep: B200SPMF, lam, Vb: Block, vcol0: int, k: int, a, Zb: Block, zcol0: int):
+    """compute_Mlincomb!(nep, lam, V[:, vcol0:vcol0+k], a) -> Z[:, zcol0], operands in HBM."""
+    Cm, _ = nep.lincomb_coefficients(lam, np.asarray(a, dtype=np.complex128))
+    Cm = np.ascontiguousarray(Cm.reshape(nep.p, k))
+    check(lib.nepb_spmf_apply_block_ex(nep._h, _lib.COEF_GENERAL, Vb._h, vcol0, k, 1, ptr(Cm), Zb._h, zcol0))
+
+
+def residual_errors(nep: B200SPMF, errmeasure, lams, Qb: Block, k: int, Rb: Block):
+    """estimate_error for all k Ritz pairs at once: one multi-lambda SpMM + column norms, everything in HBM."""
+    lams = np.asarray(lams, dtype=np.complex128)
+    Cd = np.empty((nep.p, k), dtype=np.complex128)
+    for i, f in enumerate(nep.fi):
+        Cd[i, :] = [complex(f(complex(s))) for s in lams]
+    Cf = np.asfortranarray(Cd).reshape(-1, order="F")
+    check(lib.nepb_spmf_apply_block_ex(nep._h, _lib.COEF_DIAG, Qb._h, 0, k, k, ptr(Cf), Rb._h, 0))
+    r = colnorms(Rb, 0, k) / colnorms(Qb, 0, k)
+    if hasattr(errmeasure, "_denom"):
+        r = r / np.array([errmeasure._denom(l) for l in lams])
+    return r
+
+
+# ---------------------------------------------------------------------------------------------
+# tiar with Z, y in HBM (src/method_tiar.jl:53-257)
+# ---------------------------------------------------------------------------------------------
+def tiar_device(nep: B200SPMF, maxit=30, linsolvercreator=None, tol=np.finfo(float).eps * 10000, neigs=6, errmeasure=None, sigma=0.0,
+                gamma=1.0, v=None, check_error_every=1):
+    n, m = nep.n, maxit
+    if n < m:
+        raise LostOrthogonalityException("Loss of orthogonality in the matrix Z. The problem size is too small, use iar instead.")
+    sigma = complex(sigma)
+    errmeasure = errmeasure or DefaultErrmeasure(nep)
+    a = np.zeros((m + 1, m + 1, m + 1), dtype=np.complex128)
+    t = np.zeros(m + 1, dtype=np.complex128)
+    H = np.zeros((m + 1, m), dtype=np.complex128)
+    alpha = np.asarray(gamma, dtype=np.complex128) ** np.arange(m + 1)
+    alpha[0] = 0
+    M0inv = (linsolvercreator or B200LinSolverCreator()).create_linsolver(nep, sigma)
+    lu = M0inv.lu
+    Zb, yb, tb = Block(n, m + 1), Block(n, m + 1), Block(n, 1)
+    Qb, Rb = Block(n, m), Block(n, m)
+    v = np.random.default_rng(0).standard_normal(n) if v is None else np.asarray(v, dtype=np.complex128)
+    Zb.upload(v / np.linalg.norm(v), 0)
+    a[0, 0, 0] = 1
+    err = np.full((m + 1, m + 1), np.nan)
+    lam = np.zeros(0, dtype=np.complex128)
+    hist = np.zeros(m + 1, dtype=int)
+    k, conv_eig = 1, 0
+    idx = None
+    while k <= m and conv_eig < neigs:
+        # y[:, 1:k+1] = Z[:, :k] * a[:k, k-1, :k].T ./ (1:k)'   (tensor-core ZGEMM, column scaling folded into C)
+        Cm = a[:k, k - 1, :k].T / np.arange(1, k + 1)[None, :]
+        block_gemm(Zb, 0, k, Cm, yb, 1)
+        mlincomb_block(nep, sigma, yb, 0, k + 1, alpha[:k + 1], tb, 0)
+        solve_block(lu, tb, 0, 1, Zb, k, alpha=-1.0)  # Z[:, k] = -lin_solve(M0inv, y1)
+        h0, t[k], _ = dgks(Zb, k, Zb, k)
+        t[:k] = h0
+        g = np.zeros((k + 1, k + 1), dtype=np.complex128)
+        g[1:, :] = a[:k, k - 1, :k + 1] / np.arange(1, k + 1)[:, None]
+        g[0, :] = t[:k + 1]
+        h = np.einsum("ijl,il->j", a[:k, :k, :k].conj(), g[:k, :k])
+        f = g
+        f[:, :k] -= np.einsum("ijl,j->il", a[:k + 1, :k, :k], h)
+        hh = np.einsum("ijl,il->j", a[:k, :k, :k].conj(), f[:k, :k])
+        f[:, :k] -= np.einsum("ijl,j->il", a[:k + 1, :k, :k], hh)
+        h = h + hh
+        beta = np.linalg.norm(f)
+        H[:k, k - 1] = h
+        H[k, k - 1] = beta
+        a[:k + 1, k, :k + 1] = f / beta
+        if k % check_error_every == 0 or k == m:
+            D, W = np.linalg.eig(H[:k, :k])
+            block_gemm(Zb, 0, k, a[0, :k, :k].T @ W, Qb, 0)  # Q = (Z a') W in one product
+            lam = sigma + gamma / D
+            e = residual_errors(nep, errmeasure, lam, Qb, k, Rb)
+            err[k - 1, :k] = e
+            conv_eig = int(np.count_nonzero(e < tol))
+            idx = np.argsort(err[k - 1, :k], kind="stable")
+            err[k - 1, :k] = err[k - 1, idx]
+            hist[k - 1] = conv_eig
+        k += 1
+    k -= 1
+    Q = Qb.download(0, len(lam)) if len(lam) else np.zeros((n, 0), complex)
+    nrof = int(min(len(lam), neigs)) if idx is not None else 0
+    if idx is not None:
+        lam, Q = lam[idx[:nrof]], Q[:, idx[:nrof]]
+    if conv_eig < neigs and neigs != np.inf:
+        raise NoConvergenceException(lam, Q, err[k - 1], "Number of iterations exceeded. maxit=%d." % maxit)
+    lam = lam[:min(len(lam), conv_eig)]
+    Q = Q[:, :min(Q.shape[1], conv_eig)]
+    return lam, Q, Zb.download(0, k), hist
+
+
+# ---------------------------------------------------------------------------------------------
+# iar with the n(m+1) x (m+1) basis in HBM (src/method_iar.jl:47-184)
+# ---------------------------------------------------------------------------------------------
+def iar_device(nep: B200SPMF, maxit=30, linsolvercreator=None, tol=np.finfo(float).eps * 10000, neigs=6, errmeasure=None, sigma=0.0,
+               gamma=1.0, v=None, check_error_every=1, return_basis=True):
+    n, m = nep.n, maxit
+    sigma = complex(sigma)
+    errmeasure = errmeasure or DefaultErrmeasure(nep)
+    H = np.zeros((m + 1, m), dtype=np.complex128)
+    alpha = np.asarray(gamma, dtype=np.complex128) ** np.arange(m + 1)
+    alpha[0] = 0
+    M0inv = (linsolvercreator or B200LinSolverCreator()).create_linsolver(nep, sigma)
+    lu = M0inv.lu
+    Vb = Block(n * (m + 1), m + 1)
+    yb, tb = Block(n, m + 1), Block(n, 1)
+    Qb, Rb = Block(n, m), Block(n, m)
+    v = np.random.default_rng(0).standard_normal(n) if v is None else np.asarray(v, dtype=np.complex128)
+    v0 = np.zeros(n * (m + 1), dtype=np.complex128)
+    v0[:n] = v / np.linalg.norm(v)
+    Vb.upload(v0, 0)
+    err = np.full((m, m), np.nan)
+    lam = np.zeros(0, dtype=np.complex128)
+    idx = None
+    k, conv_eig = 1, 0
+    while k <= m and conv_eig < neigs:
+        check(lib.nepb_iar_expand(Vb._h, k - 1, n, k, yb._h, 1, 1))  # y[:, 1:k+1] = reshape(VV[1:n*k, k], n, k) ./ (1:k)'
+        mlincomb_block(nep, sigma, yb, 0, k + 1, alpha[:k + 1], tb, 0)
+        solve_block(lu, tb, 0, 1, yb, 0, alpha=-1.0)
+        check(lib.nepb_iar_pack(yb._h, 0, k + 1, n, Vb._h, k))  # vv = vec(y[:, 1:k+1])
+        h, nrm, _ = dgks(Vb, k, Vb, k, rows=n * (k + 1))
+        H[:k, k - 1] = h
+        H[k, k - 1] = nrm
+        if k % check_error_every == 0 or k == m:
+            D, Zm = np.linalg.eig(H[:k, :k])
+            block_gemm(Vb, 0, k, Zm, Qb, 0, rows=n)  # Q = V[1:n, 1:k] * Z
+            lam = sigma + gamma / D
+            e = residual_errors(nep, errmeasure, lam, Qb, k, Rb)
+            err[k - 1, :k] = e
+            conv_eig = int(np.count_nonzero(e < tol))
+            idx = np.argsort(err[k - 1, :k], kind="stable")
+            err[k - 1, :k] = err[k - 1, idx]
+        k += 1
+    k -= 1
+    Q = Qb.download(0, len(lam)) if len(lam) else np.zeros((n, 0), complex)
+    if idx is not None:
+        nrof = int(min(len(lam), neigs))
+        Q = Q[:, idx[:len(lam)]]
+        lam = lam[idx[:nrof]]
+    if conv_eig < neigs and neigs != np.inf:
+        raise NoConvergenceException(lam, Q, err[k - 1, :k], "Number of iterations exceeded. maxit=%d." % maxit)
+    lam = lam[:min(len(lam), conv_eig)]
+    Q = Q[:, :min(Q.shape[1], conv_eig)]
+    V = Vb.download(0, k) if return_basis else None
+    return lam, Q, V
