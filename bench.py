@@ -507,7 +507,13 @@ def main():
     }
     if spmm:
         head = spmm[1]
-        line["roofline"] = {"bound": "hbm", "achieved": head["gbs"], "peak": peak, "unit": "GB/s", "frac": head["frac"], "traffic": None,
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_spmm_traffic.json")) as f:
+                traffic = json.load(f)["traffic_bytes_per_launch"]  # dram read+write per launch from the committed ncu --set full capture
+        except Exception:
+            pass
+        line["roofline"] = {"bound": "hbm", "achieved": head["gbs"], "peak": peak, "unit": "GB/s", "frac": head["frac"], "traffic": traffic,
                             "peak_source": peak_src, "kernel": "spmm_fused_kernel<VW=4,real,SCALAR> (config C4, k=1)",
                             "algorithmic_bytes_per_launch": head["bytes"], "us_per_launch": head["ms"] * 1e3}
         line["spmm"] = {str(k): {kk: v[kk] for kk in ("ms", "gbs", "frac", "bytes", "e2e_ms")} for k, v in spmm.items()}

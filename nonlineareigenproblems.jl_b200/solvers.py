@@ -135,6 +135,20 @@ def beyn_extract(A0, A1, sigma, radius, k, neigs, tol, rank_drop_tol, errmeasure
     return lam[idx], Vv[:, idx], info
 
 
+def beyn_quadrature(N, radius, sigma, rank=0, world=1):
+    """Nodes and weights of the trapezoid rule on the ellipse (method_beyncontour.jl:69-70, method_contour_common.jl:62-93)
+    owned by `rank` of `world` (round-robin i = rank mod world).  Returns (indices, lambda_i = g(t_i) + sigma, W) with
+    W[i, :] = (gp_i, gp_i g_i) * h / (2 pi i), so that A_j = sum_i W[i, j] M(lambda_i)^-1 Vh summed over all ranks."""
+    radius = (radius, radius) if np.isscalar(radius) else tuple(radius)
+    h = 2 * np.pi / N
+    t = h * np.arange(N)
+    g = radius[0] * np.cos(t) + 1j * radius[1] * np.sin(t)
+    gp = -radius[0] * np.sin(t) + 1j * radius[1] * np.cos(t)
+    W = np.stack([gp * h / (2j * np.pi), gp * g * h / (2j * np.pi)], axis=1)
+    mine = np.arange(rank, N, world)
+    return mine, g[mine] + sigma, W[mine]
+
+
 def contour_beyn(nep: B200SPMF, Vh=None, sigma=0.0, radius=1.0, N=1000, neigs=2, k=None, tol=np.sqrt(np.finfo(float).eps),
                  errmeasure=None, sanity_check=True, rank_drop_tol=None, batch=32, rank=0, world=1, integrator=None,
                  return_moments=False, seed=10):
@@ -151,17 +165,11 @@ def contour_beyn(nep: B200SPMF, Vh=None, sigma=0.0, radius=1.0, N=1000, neigs=2,
     if Vh is None:  # the reference draws randn(n,k) after Random.seed!(10); any fixed Gaussian probe is equivalent
         Vh = np.random.default_rng(seed).standard_normal((n, k))
     errmeasure = errmeasure or DefaultErrmeasure(nep)
-    h = 2 * np.pi / N
-    t = h * np.arange(N)
-    g = radius[0] * np.cos(t) + 1j * radius[1] * np.sin(t)
-    gp = -radius[0] * np.sin(t) + 1j * radius[1] * np.cos(t)
-    # weights: temp*G[i,j] with temp = X_i*gp_i, summed, times h, divided by 2 pi i (method_contour_common.jl:86-93, beyn :110-111)
-    W = np.stack([gp * h / (2j * np.pi), gp * g * h / (2j * np.pi)], axis=1)
-    mine = np.arange(rank, N, world)
+    mine, lams, Wm = beyn_quadrature(N, radius, sigma, rank, world)
     own = integrator is None
     integ = integrator or ContourIntegrator(nep, k, 2, min(batch, max(1, len(mine))))
     try:
-        S, flags = integ.integrate(g[mine] + sigma, W[mine], Vh, reduce=world > 1)
+        S, flags = integ.integrate(lams, Wm, Vh, reduce=world > 1)
     finally:
         if own:
             integ.close()
