@@ -14,7 +14,10 @@
 namespace nepb {
 
 void set_error(const char* fmt, ...);
-cudaStream_t stream();
+cudaStream_t stream();       // stream the calling thread currently enqueues on
+cudaStream_t main_stream();  // the library stream (timer events, host-facing copies)
+void set_current_stream(cudaStream_t s);
+void reset_current_stream();
 extern std::atomic<int64_t> g_launches;
 int sm_count();
 

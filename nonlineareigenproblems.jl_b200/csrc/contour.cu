@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "common.h"
@@ -140,86 +141,216 @@ int nepb_comm_allreduce_sum_dev(void* dev_ptr, int64_t count) {
     return NEPB_OK;
 }
 
-struct nepb_contour {
-    const nepb_spmf* op = nullptr;
+// One group = one stream + one batched factorisation workspace + its own moment accumulator.
+struct ContourGroup {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
     nepb_lu* lu = nullptr;
-    int batch = 0, k = 0, mg = 0;
-    DevBuf<double> vh, x, s, wgt, stage;
-    std::vector<int> node_flags;
-    int64_t nodes_done = 0;
+    DevBuf<double> x, s, wgt;
+    int cap = 0;
+    // pinned staging + one instantiated CUDA graph per batch share (the launch sequence depends only on the count)
+    double* h_coef = nullptr;
+    double* h_wgt = nullptr;
+    LuInfo* h_info = nullptr;
+    std::map<int, std::pair<cudaGraphExec_t, int>> graphs;  // count -> (exec, kernels in the graph)
+    ~ContourGroup() {
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second.first);
+        if (h_coef) cudaFreeHost(h_coef);
+        if (h_wgt) cudaFreeHost(h_wgt);
+        if (h_info) cudaFreeHost(h_info);
+        delete lu;
+        if (done) cudaEventDestroy(done);
+        if (st) cudaStreamDestroy(st);
+    }
 };
 
+struct nepb_contour {
+    const nepb_spmf* op = nullptr;
+    int batch = 0, k = 0, mg = 0;
+    std::vector<ContourGroup*> groups;
+    DevBuf<double> vh, s, stage;
+    std::vector<int> node_flags;
+    int64_t nodes_done = 0;
+    ~nepb_contour() {
+        for (auto* g : groups) delete g;
+    }
+};
+
+namespace nepb {
+__global__ void __launch_bounds__(256) sum_groups_kernel(size_t count, int ng, const double* const* __restrict__ parts, double* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    double t = 0.0;
+    for (int g = 0; g < ng; ++g) t += parts[g][idx];  // fixed order: reproducible
+    out[idx] = t;
+}
+}  // namespace nepb
+
+// `batch` nodes are in flight at a time, spread over NEPB_CONTOUR_STREAMS (default 4) groups; each group factorises and
+// solves its share as one batched launch sequence on its own stream.
 int nepb_contour_create(const nepb_spmf* h, int k, int mg, int batch, nepb_contour** out) {
     NEPB_CHECK_ARG(h && out, "NULL argument");
     NEPB_CHECK_ARG(k >= 1 && k <= 256 && mg >= 1 && mg <= 64 && batch >= 1 && batch <= 4096, "bad sizes (k=%d mg=%d batch=%d)", k, mg, batch);
     *out = nullptr;
+    LuSymbolicDev* sd = nullptr;
+    int rc = lu_symbolic_get(h, &sd);
+    if (rc) return rc;
+    int ng = 4;
+    if (const char* e = getenv("NEPB_CONTOUR_STREAMS")) ng = std::max(1, std::min(16, atoi(e)));
+    ng = std::min(ng, batch);
     nepb_contour* c = new nepb_contour();
     c->op = h;
     c->batch = batch;
     c->k = k;
     c->mg = mg;
-    // dummy coefficients: the handle is (re)factorised per batch
-    std::vector<double> coef((size_t)2 * batch * h->p, 0.0);
-    for (int b = 0; b < batch; ++b) coef[(size_t)2 * b * h->p] = 1.0;
-    LuSymbolicDev* sd = nullptr;
-    int rc = lu_symbolic_get(h, &sd);
-    if (rc) { delete c; return rc; }
-    nepb_lu* lu = new nepb_lu();
-    lu->op = h;
-    lu->sym = sd;
-    lu->nb = lu->cap = batch;
     const size_t nk = (size_t)h->n * k;
-    cudaError_t e = lu->fronts.alloc((size_t)2 * batch * sd->S.front_total);
-    if (e == cudaSuccess) e = lu->piv.alloc((size_t)batch * h->n);
-    if (e == cudaSuccess) e = lu->info.alloc(batch);
-    if (e == cudaSuccess) e = lu->coef.alloc((size_t)2 * batch * h->p);
-    if (e == cudaSuccess) e = c->vh.alloc(2 * nk);
-    if (e == cudaSuccess) e = c->x.alloc(2 * nk * batch);
+    cudaError_t e = c->vh.alloc(2 * nk);
     if (e == cudaSuccess) e = c->s.alloc(2 * nk * mg);
-    if (e == cudaSuccess) e = c->wgt.alloc((size_t)2 * batch * mg);
+    for (int g = 0; g < ng && e == cudaSuccess; ++g) {
+        ContourGroup* G = new ContourGroup();
+        c->groups.push_back(G);
+        G->cap = (batch + ng - 1 - g) / ng;  // group sizes differ by at most one
+        if (G->cap == 0) G->cap = 1;
+        e = cudaStreamCreateWithFlags(&G->st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&G->done, cudaEventDisableTiming);
+        nepb_lu* lu = new nepb_lu();
+        G->lu = lu;
+        lu->op = h;
+        lu->sym = sd;
+        lu->nb = lu->cap = G->cap;
+        if (e == cudaSuccess) e = lu->fronts.alloc((size_t)2 * G->cap * sd->S.front_total);
+        if (e == cudaSuccess) e = lu->piv.alloc((size_t)G->cap * h->n);
+        if (e == cudaSuccess) e = lu->info.alloc(G->cap);
+        if (e == cudaSuccess) e = lu->coef.alloc((size_t)2 * G->cap * h->p);
+        if (e == cudaSuccess) e = G->x.alloc(2 * nk * G->cap);
+        if (e == cudaSuccess) e = G->s.alloc(2 * nk * mg);
+        if (e == cudaSuccess) e = G->wgt.alloc((size_t)2 * G->cap * mg);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&G->h_coef, sizeof(double) * 2 * G->cap * h->p);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&G->h_wgt, sizeof(double) * 2 * G->cap * mg);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&G->h_info, sizeof(LuInfo) * G->cap);
+        if (e == cudaSuccess && lu_solve_reserve(lu, G->cap, k) != NEPB_OK) e = cudaErrorMemoryAllocation;
+    }
     if (e != cudaSuccess) {
         set_error("contour workspace (batch %d, %.1f MB of fronts per node) does not fit: %s", batch, sd->S.front_total * 16e-6, cudaGetErrorString(e));
-        delete lu;
         delete c;
         return e == cudaErrorMemoryAllocation ? NEPB_E_NOMEM : NEPB_E_CUDA;
     }
-    c->lu = lu;
     *out = c;
     return NEPB_OK;
 }
 
 int nepb_contour_destroy(nepb_contour* c) {
-    if (c) {
-        delete c->lu;
-        delete c;
-    }
+    delete c;
     return NEPB_OK;
 }
 
-// Device part of one integration: S_dev = sum over this rank's nodes; asynchronous except for the per-batch status fetch.
-int nepb_contour_integrate_dev(nepb_contour* c, int nnodes, const double* coef, const double* weights, int reduce) {
-    NEPB_CHECK_ARG(c && (nnodes == 0 || (coef && weights)) && nnodes >= 0, "bad arguments");
+// The per-group pipeline for `cnt` nodes: coefficients / weights H2D (pinned), batched factorisation, batched solve with
+// the shared probe, accumulate into the group's moments, status D2H.  Device work only -> captured once per count into a
+// CUDA graph and replayed (one graph launch instead of ~400 kernel launches per group and step).
+static int contour_group_enqueue(nepb_contour* c, ContourGroup* G, int cnt) {
     const nepb_spmf* h = c->op;
     const size_t nk = (size_t)h->n * c->k;
-    NEPB_CUDA(cudaMemsetAsync(c->s.p, 0, sizeof(double) * 2 * nk * c->mg, stream()));
-    c->node_flags.assign(nnodes, 0);
-    for (int i0 = 0; i0 < nnodes; i0 += c->batch) {
-        const int nb = std::min(c->batch, nnodes - i0);
-        int rc = lu_refactor(c->lu, nb, coef + (size_t)2 * i0 * h->p);
-        if (rc) return rc;
-        NEPB_CUDA(cudaMemcpyAsync(c->wgt.p, weights + (size_t)2 * i0 * c->mg, sizeof(double) * 2 * nb * c->mg, cudaMemcpyHostToDevice, stream()));
-        rc = lu_solve_device(c->lu, 0, nb, c->k, (const double2*)c->vh.p, 0, (double2*)c->x.p);
-        if (rc) return rc;
-        NEPB_LAUNCH(contour_accumulate_kernel, (unsigned)((nk + 255) / 256), 256, 0, nk, nb, c->mg, (const double2*)c->x.p, nk,
-                    (const double2*)c->wgt.p, (double2*)c->s.p);
-        NEPB_LAUNCH_CHECK();
-        rc = lu_fetch_info(c->lu);  // also fences the host weight / coefficient buffers of this batch
-        if (rc) return rc;
-        for (int b = 0; b < nb; ++b) c->node_flags[i0 + b] = c->lu->h_info[b].flags | (c->lu->h_info[b].nperturbed ? 4 : 0);
+    G->lu->nb = cnt;
+    NEPB_CUDA(cudaMemcpyAsync(G->lu->coef.p, G->h_coef, sizeof(double) * 2 * cnt * h->p, cudaMemcpyHostToDevice, G->st));
+    NEPB_CUDA(cudaMemcpyAsync(G->wgt.p, G->h_wgt, sizeof(double) * 2 * cnt * c->mg, cudaMemcpyHostToDevice, G->st));
+    int rc = lu_factor_device(G->lu);
+    if (rc) return rc;
+    rc = lu_solve_device(G->lu, 0, cnt, c->k, (const double2*)c->vh.p, 0, (double2*)G->x.p);
+    if (rc) return rc;
+    NEPB_LAUNCH(contour_accumulate_kernel, (unsigned)((nk + 255) / 256), 256, 0, nk, cnt, c->mg, (const double2*)G->x.p, nk,
+                (const double2*)G->wgt.p, (double2*)G->s.p);
+    NEPB_LAUNCH_CHECK();
+    NEPB_CUDA(cudaMemcpyAsync(G->h_info, G->lu->info.p, sizeof(LuInfo) * cnt, cudaMemcpyDeviceToHost, G->st));
+    return NEPB_OK;
+}
+
+static int contour_group_run(nepb_contour* c, ContourGroup* G, int cnt) {
+    static const bool use_graph = !(getenv("NEPB_CONTOUR_GRAPH") && atoi(getenv("NEPB_CONTOUR_GRAPH")) == 0);
+    if (!use_graph) return contour_group_enqueue(c, G, cnt);
+    auto it = G->graphs.find(cnt);
+    if (it == G->graphs.end()) {
+        const int64_t l0 = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        NEPB_CUDA(cudaStreamBeginCapture(G->st, cudaStreamCaptureModeThreadLocal));
+        int rc = contour_group_enqueue(c, G, cnt);
+        cudaError_t e = cudaStreamEndCapture(G->st, &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        NEPB_CUDA(e);
+        const int nkern = (int)(g_launches.load() - l0);
+        g_launches.fetch_sub(nkern);  // counted when the graph actually runs
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        NEPB_CUDA(e);
+        it = G->graphs.emplace(cnt, std::make_pair(exec, nkern)).first;
     }
+    NEPB_CUDA(cudaGraphLaunch(it->second.first, G->st));
+    g_launches.fetch_add(it->second.second);
+    return NEPB_OK;
+}
+
+// Device part of one integration: S_dev = sum over this rank's nodes (+ all-reduce).  Returns after the work finished.
+static int contour_integrate_groups(nepb_contour* c, int nnodes, const double* coef, const double* weights) {
+    const nepb_spmf* h = c->op;
+    const size_t nk = (size_t)h->n * c->k;
+    const int ng = (int)c->groups.size();
+    // the probe upload (main stream) must be visible to every group stream
+    NEPB_CUDA(cudaStreamSynchronize(main_stream()));
+    for (auto* G : c->groups) NEPB_CUDA(cudaMemsetAsync(G->s.p, 0, sizeof(double) * 2 * nk * c->mg, G->st));
+    c->node_flags.assign(nnodes, 0);
+    int rc = NEPB_OK;
+    for (int i0 = 0; i0 < nnodes && !rc; i0 += c->batch) {
+        const int nb = std::min(c->batch, nnodes - i0);
+        // contiguous share of the batch per group
+        std::vector<int> first(ng + 1, 0);
+        for (int g = 0; g < ng; ++g) first[g + 1] = first[g] + std::min(c->groups[g]->cap, std::max(0, (nb + ng - 1 - g) / ng));
+        for (int g = 0; g < ng && !rc; ++g) {
+            ContourGroup* G = c->groups[g];
+            const int cnt = first[g + 1] - first[g];
+            if (cnt <= 0) continue;
+            const int j0 = i0 + first[g];
+            set_current_stream(G->st);
+            memcpy(G->h_coef, coef + (size_t)2 * j0 * h->p, sizeof(double) * 2 * cnt * h->p);
+            memcpy(G->h_wgt, weights + (size_t)2 * j0 * c->mg, sizeof(double) * 2 * cnt * c->mg);
+            rc = contour_group_run(c, G, cnt);
+        }
+        // status of this batch (also fences the host coefficient / weight buffers before the next batch reuses a group)
+        for (int g = 0; g < ng && !rc; ++g) {
+            ContourGroup* G = c->groups[g];
+            const int cnt = first[g + 1] - first[g];
+            if (cnt <= 0) continue;
+            cudaError_t e = cudaStreamSynchronize(G->st);
+            if (e != cudaSuccess) { set_error("CUDA error in the contour pipeline: %s", cudaGetErrorString(e)); rc = NEPB_E_CUDA; break; }
+            for (int bidx = 0; bidx < cnt; ++bidx)
+                c->node_flags[i0 + first[g] + bidx] = G->h_info[bidx].flags | (G->h_info[bidx].nperturbed ? 4 : 0);
+        }
+    }
+    reset_current_stream();
+    if (rc) return rc;
+    // S = sum of the group accumulators, on the main stream (all group streams are idle: lu_fetch_info synchronised them)
+    std::vector<const double*> parts;
+    for (auto* G : c->groups) parts.push_back(G->s.p);
+    static DevBuf<const double*> d_parts;
+    NEPB_CUDA(d_parts.reserve(parts.size()));
+    NEPB_CUDA(cudaMemcpyAsync(d_parts.p, parts.data(), sizeof(double*) * parts.size(), cudaMemcpyHostToDevice, main_stream()));
+    const size_t cnt = 2 * nk * c->mg;
+    NEPB_LAUNCH(sum_groups_kernel, (unsigned)((cnt + 255) / 256), 256, 0, cnt, ng, (const double* const*)d_parts.p, c->s.p);
+    NEPB_LAUNCH_CHECK();
+    NEPB_CUDA(cudaStreamSynchronize(main_stream()));  // `parts` is a local buffer
     c->nodes_done += nnodes;
+    return NEPB_OK;
+}
+
+int nepb_contour_integrate_dev(nepb_contour* c, int nnodes, const double* coef, const double* weights, int reduce) {
+    NEPB_CHECK_ARG(c && (nnodes == 0 || (coef && weights)) && nnodes >= 0, "bad arguments");
+    int rc = contour_integrate_groups(c, nnodes, coef, weights);
+    reset_current_stream();
+    if (rc) return rc;
     if (reduce) {
-        int rc = nepb_comm_allreduce_sum_dev(c->s.p, (int64_t)(2 * nk * c->mg));
+        rc = nepb_comm_allreduce_sum_dev(c->s.p, (int64_t)(2 * (size_t)c->op->n * c->k * c->mg));
         if (rc) return rc;
     }
     return NEPB_OK;

@@ -42,14 +42,23 @@ __device__ __forceinline__ void cfma2(double2& acc, const double2 a, const doubl
     acc.y = fma(a.x, b.y, acc.y);
     acc.y = fma(a.y, b.x, acc.y);
 }
+// 1/x from the hardware approximation + two Newton steps (full double accuracy for normal x; IEEE division costs an
+// order of magnitude more instructions and sits on the serial path of the pivot-block factorisation)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
 __device__ __forceinline__ double2 crecip(double2 a) {
-    // 1/a with scaling (Smith): no overflow of |a|^2
-    if (fabs(a.x) >= fabs(a.y)) {
-        const double r = a.y / a.x, d = a.x + a.y * r;
-        return make_double2(1.0 / d, -r / d);
-    }
-    const double r = a.x / a.y, d = a.x * r + a.y;
-    return make_double2(r / d, -1.0 / d);
+    // 1/a = conj(a)/|a|^2 with the operand scaled by a power of two first: no overflow / underflow of |a|^2
+    const double m = fmax(fabs(a.x), fabs(a.y));
+    const int e = (int)((__double2hiint(m) >> 20) & 0x7ff) - 1023;              // exponent of the larger component
+    const double sc = __hiloint2double((1023 - e) << 20, 0);                    // 2^-e (e in the normal range)
+    const double xs = a.x * sc, ys = a.y * sc;
+    const double r = fast_rcp(fma(xs, xs, ys * ys)) * sc;
+    return make_double2(xs * r, -ys * r);
 }
 __device__ __forceinline__ double cabs1(double2 a) { return fabs(a.x) + fabs(a.y); }
 
@@ -118,341 +127,245 @@ __global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev d, const int4*
 }
 
 // ---------------------------------------------------------------------------------------------
-// diag: LU with partial pivoting of the pivot block, one CTA per (front, shift)
+// diag: partial-pivoted LU of the (at most 32 x 32) pivot block AND the explicit inverses of its triangular factors.
+// One CTA of 4 warps per (front, shift): lane = row, warp w owns columns 8w..8w+7 in registers.  One block barrier per
+// elimination step (pivot row index + multiplier column go through double-buffered shared memory), row exchanges and
+// the rank-1 update use shuffles.  The inverses turn every later triangular solve with this block (panel, forward,
+// backward) into a small dense product without a sequential dependency chain.
+// Output in place of F11: strict lower part = inv(L11) (unit diagonal implied), upper part = inv(U11);
+// piv[t] = original row (within the block) that ended up in position t.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lu_diag_kernel(LuDev d, const int* __restrict__ items, double2* __restrict__ fronts,
-                                                      int* __restrict__ piv, LuInfo* __restrict__ info) {
-    extern __shared__ double2 sA[];  // np x np, column-major, ld = np + 1
-    __shared__ int s_piv;
-    __shared__ double2 s_rp;
+__device__ __forceinline__ double2 shfl_c(double2 v, int src) {
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+constexpr int DNP = 32, DCW = 8;
+__global__ void __launch_bounds__(128) lu_diag_inv_kernel(LuDev d, const int* __restrict__ items, double2* __restrict__ fronts,
+                                                          int* __restrict__ piv, LuInfo* __restrict__ info) {
+    __shared__ double2 s_l[2][DNP];
+    __shared__ int s_bi[2];
+    __shared__ double2 s_rp[DNP];
+    __shared__ double2 s_LU[DNP][DNP + 1];  // s_LU[c][r] = (L\U)[r][c]
     const int s = items[blockIdx.x];
     const int b = blockIdx.y;
-    const int nf = d.ld[s], np = d.np[s], ld = np + 1;  // nf: leading dimension of the front storage
+    const int np = d.np[s], ld = d.ld[s];
     double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
     int* pv = piv + (size_t)b * d.n + d.sn_ptr[s];
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < np * np; idx += blockDim.x) {
-        const int i = idx % np, j = idx / np;
-        sA[i + j * ld] = F[(size_t)i + (size_t)j * nf];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double2 a[DCW];
+#pragma unroll
+    for (int c = 0; c < DCW; ++c) {
+        const int cg = DCW * w + c;
+        a[c] = (lane < np && cg < np) ? F[(size_t)lane + (size_t)cg * ld] : make_double2(lane == cg ? 1.0 : 0.0, 0.0);
     }
-    __syncthreads();
     const double amax = __longlong_as_double(info[b].amax_bits);
     const double tiny = 2.220446049250313e-16 * amax;
+    double minpiv = INFINITY;
+    int nperturbed = 0, flags = 0, orig = lane;
+#pragma unroll 1
     for (int j = 0; j < np; ++j) {
-        if (tid < 32) {
-            // pivot search over rows j..np-1 of column j (np <= 64: two rounds at most)
-            double best = -1.0;
-            int bi = j;
-            for (int i = j + tid; i < np; i += 32) {
-                const double a = cabs1(sA[i + j * ld]);
-                if (a > best || !(a == a)) { best = (a == a) ? a : INFINITY; bi = i; }
-            }
+        const int wo = j >> 3, jl = j & 7, par = j & 1;
+        if (w == wo) {  // warp-uniform: the owner of column j finds the pivot, exchanges its rows and forms the multipliers
+            double2 aj = a[0];
+#pragma unroll
+            for (int c = 1; c < DCW; ++c)
+                if (c == jl) aj = a[c];
+            const double mine = cabs1(aj);
+            double best = (lane >= j && lane < np) ? ((mine == mine) ? mine : INFINITY) : -1.0;
+            int bi = lane;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 const double ob = __shfl_xor_sync(0xffffffffu, best, off);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
                 if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
-            if (tid == 0) {
-                const double dj = cabs1(sA[j + j * ld]);
-                if (dj >= 0.1 * best && dj == dj) bi = j;  // threshold pivoting that prefers the diagonal
-                double2 pvt = sA[bi + j * ld];
-                const double pa = cabs1(pvt);
-                if (!(pa <= 1.79e308) || !(best <= 1.79e308)) {  // NaN / Inf
-                    atomicOr(&info[b].flags, 2);
-                    pvt = make_double2(1.0, 0.0);
-                } else if (pa == 0.0) {
-                    atomicOr(&info[b].flags, 1);  // exactly singular within the front
-                    atomicAdd(&info[b].nperturbed, 1);
-                    pvt = make_double2(tiny > 0.0 ? tiny : 1.0, 0.0);
-                } else if (pa < tiny) {
-                    atomicAdd(&info[b].nperturbed, 1);
-                    const double sc = tiny / pa;
-                    pvt = make_double2(pvt.x * sc, pvt.y * sc);
+            const double dj = __shfl_sync(0xffffffffu, mine, j);
+            if (dj >= 0.1 * best && dj == dj) bi = j;  // threshold pivoting that prefers the diagonal
+            if (bi != j) {
+                const int src = (lane == j) ? bi : j;
+#pragma unroll
+                for (int c = 0; c < DCW; ++c) {
+                    const double2 o = shfl_c(a[c], src);
+                    if (lane == j || lane == bi) a[c] = o;
                 }
-                sA[bi + j * ld] = pvt;
-                s_piv = bi;
-                s_rp = crecip(pvt);
-                pv[j] = bi;
-                // smallest pivot relative to amax, for diagnostics
-                const double ratio = amax > 0.0 ? pa / amax : 0.0;
-                atomicMin((unsigned long long*)&info[b].minpiv_bits, (unsigned long long)__double_as_longlong(ratio));
+                const double2 o = shfl_c(aj, src);
+                if (lane == j || lane == bi) aj = o;
+            }
+            double2 pvt = shfl_c(aj, j);
+            const double pa = cabs1(pvt);
+            if (!(pa <= 1.79e308) || !(best <= 1.79e308)) {
+                flags |= 2;
+                pvt = make_double2(1.0, 0.0);
+            } else if (pa == 0.0) {
+                flags |= 1;
+                ++nperturbed;
+                pvt = make_double2(tiny > 0.0 ? tiny : 1.0, 0.0);
+            } else if (pa < tiny) {
+                ++nperturbed;
+                const double sc = tiny / pa;
+                pvt = make_double2(pvt.x * sc, pvt.y * sc);
+            }
+            minpiv = fmin(minpiv, pa);
+            const double2 rp = crecip(pvt);
+            if (lane == j) aj = pvt;
+            if (lane > j) aj = cmul(aj, rp);
+#pragma unroll
+            for (int c = 0; c < DCW; ++c)
+                if (c == jl) a[c] = aj;
+            s_l[par][lane] = (lane > j && lane < np) ? aj : make_double2(0.0, 0.0);
+            if (lane == 0) {
+                s_bi[par] = bi;
+                s_rp[j] = rp;
             }
         }
         __syncthreads();
-        const int pr = s_piv;
-        if (pr != j && tid < np) {
-            const double2 t = sA[j + tid * ld];
-            sA[j + tid * ld] = sA[pr + tid * ld];
-            sA[pr + tid * ld] = t;
-        }
-        __syncthreads();
-        const double2 rp = s_rp;
-        for (int i = j + 1 + tid; i < np; i += blockDim.x) sA[i + j * ld] = cmul(sA[i + j * ld], rp);
-        __syncthreads();
-        const int m = np - j - 1;
-        for (int idx = tid; idx < m * m; idx += blockDim.x) {
-            const int i = j + 1 + idx % m, k = j + 1 + idx / m;
-            cfms(sA[i + k * ld], sA[i + j * ld], sA[j + k * ld]);
-        }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < np * np; idx += blockDim.x) {
-        const int i = idx % np, j = idx / np;
-        F[(size_t)i + (size_t)j * nf] = sA[i + j * ld];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// diag, pivot blocks of at most 32 columns: ONE WARP per (front, shift), lane = row, the whole block in registers.
-// No shared memory and no block barriers: pivot search is a warp arg-max, row exchange and the rank-1 update use
-// shuffles.  Same pivoting rule and the same arithmetic order per entry as lu_diag_kernel.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double2 shfl_c(double2 v, int src) {
-    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
-}
-
-__global__ void __launch_bounds__(32) lu_diag_warp_kernel(LuDev d, const int* __restrict__ items, double2* __restrict__ fronts,
-                                                          int* __restrict__ piv, LuInfo* __restrict__ info) {
-    constexpr int NP = 32;
-    const int s = items[blockIdx.x];
-    const int b = blockIdx.y;
-    const int np = d.np[s], ld = d.ld[s];
-    double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
-    int* pv = piv + (size_t)b * d.n + d.sn_ptr[s];
-    const int lane = threadIdx.x;
-    double2 a[NP];
-#pragma unroll
-    for (int c = 0; c < NP; ++c) a[c] = (lane < np && c < np) ? F[(size_t)lane + (size_t)c * ld] : make_double2(lane == c ? 1.0 : 0.0, 0.0);
-    const double amax = __longlong_as_double(info[b].amax_bits);
-    const double tiny = 2.220446049250313e-16 * amax;
-    double minratio = INFINITY;
-    int nperturbed = 0, flags = 0;
-    // j is a run-time loop (a fully unrolled elimination is instruction-fetch bound); the register array is only ever
-    // indexed by the unrolled c, column j is picked / written back with predicated moves.
-#pragma unroll 1
-    for (int j = 0; j < np; ++j) {
-        double2 aj = a[0];
-#pragma unroll
-        for (int c = 1; c < NP; ++c)
-            if (c == j) aj = a[c];
-        const double mine = cabs1(aj);
-        double best = (lane >= j && lane < np) ? ((mine == mine) ? mine : INFINITY) : -1.0;
-        int bi = lane;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
-        const double dj = __shfl_sync(0xffffffffu, mine, j);
-        if (dj >= 0.1 * best && dj == dj) bi = j;  // threshold pivoting that prefers the diagonal
+        const int bi = s_bi[par];
         if (bi != j) {
-            const int src = (lane == j) ? bi : j;
+            if (w != wo) {
+                const int src = (lane == j) ? bi : j;
 #pragma unroll
-            for (int c = 0; c < NP; ++c) {
-                const double2 o = shfl_c(a[c], src);
-                if (lane == j || lane == bi) a[c] = o;
+                for (int c = 0; c < DCW; ++c) {
+                    const double2 o = shfl_c(a[c], src);
+                    if (lane == j || lane == bi) a[c] = o;
+                }
             }
-            const double2 o = shfl_c(aj, src);
-            if (lane == j || lane == bi) aj = o;
+            const int oo = __shfl_sync(0xffffffffu, orig, (lane == j) ? bi : j);
+            if (lane == j || lane == bi) orig = oo;
         }
-        double2 pvt = shfl_c(aj, j);
-        const double pa = cabs1(pvt);
-        if (!(pa <= 1.79e308) || !(best <= 1.79e308)) {
-            flags |= 2;
-            pvt = make_double2(1.0, 0.0);
-        } else if (pa == 0.0) {
-            flags |= 1;
-            ++nperturbed;
-            pvt = make_double2(tiny > 0.0 ? tiny : 1.0, 0.0);
-        } else if (pa < tiny) {
-            ++nperturbed;
-            const double sc = tiny / pa;
-            pvt = make_double2(pvt.x * sc, pvt.y * sc);
-        }
-        if (lane == 0) pv[j] = bi;
-        minratio = fmin(minratio, amax > 0.0 ? pa / amax : 0.0);
-        const double2 rp = crecip(pvt);
-        if (lane == j) aj = pvt;
-        if (lane > j) aj = cmul(aj, rp);  // multiplier l_ij
+        const double2 l = s_l[par][lane];
 #pragma unroll
-        for (int c = 0; c < NP; ++c) {
-            if (c == j) a[c] = aj;
-            if (c > j) {  // warp-uniform
+        for (int c = 0; c < DCW; ++c) {
+            if (DCW * w + c > j) {  // warp-uniform
                 const double2 rj = shfl_c(a[c], j);
-                if (lane > j) cfms(a[c], aj, rj);
+                if (lane > j) cfms(a[c], l, rj);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < DCW; ++c) s_LU[DCW * w + c][lane] = a[c];
+    __syncthreads();
+    // inv(L11): forward elimination applied to the identity; inv(U11): backward.  Shared memory is read-only here.
+    double2 xl[DCW], xu[DCW];
+#pragma unroll
+    for (int c = 0; c < DCW; ++c) xl[c] = xu[c] = make_double2(lane == DCW * w + c ? 1.0 : 0.0, 0.0);
+#pragma unroll 1
+    for (int j = 0; j < np - 1; ++j) {
+        const double2 l = s_LU[j][lane];
+#pragma unroll
+        for (int c = 0; c < DCW; ++c) {
+            if (DCW * w + c <= j) {
+                const double2 xj = shfl_c(xl[c], j);
+                if (lane > j && lane < np) cfms(xl[c], l, xj);
+            }
+        }
+    }
+#pragma unroll 1
+    for (int j = np - 1; j >= 0; --j) {
+        const double2 rp = s_rp[j];
+        const double2 u = s_LU[j][lane];
+#pragma unroll
+        for (int c = 0; c < DCW; ++c) {
+            if (DCW * w + c >= j) {
+                if (lane == j) xu[c] = cmul(xu[c], rp);
+                const double2 xj = shfl_c(xu[c], j);
+                if (lane < j) cfms(xu[c], u, xj);
             }
         }
     }
     if (lane < np) {
 #pragma unroll
-        for (int c = 0; c < NP; ++c)
-            if (c < np) F[(size_t)lane + (size_t)c * ld] = a[c];
+        for (int c = 0; c < DCW; ++c) {
+            const int cg = DCW * w + c;
+            if (cg < np) F[(size_t)lane + (size_t)cg * ld] = (cg >= lane) ? xu[c] : xl[c];
+        }
+        if (w == 0) pv[lane] = orig;
     }
     if (lane == 0) {
         if (flags) atomicOr(&info[b].flags, flags);
         if (nperturbed) atomicAdd(&info[b].nperturbed, nperturbed);
-        atomicMin((unsigned long long*)&info[b].minpiv_bits, (unsigned long long)__double_as_longlong(minratio));
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// panel for pivot blocks of at most 32 columns: the thread's column (row) lives in registers and both triangular
-// solves are fully unrolled, L11 / U11 come from shared memory as warp-wide broadcasts.
-// ---------------------------------------------------------------------------------------------
-constexpr size_t PANEL32_SMEM = (32 * 33 + 64 * 33 + 32) * 16;
-__global__ void __launch_bounds__(64) lu_panel32_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts,
-                                                        const int* __restrict__ piv) {
-    constexpr int NP = 32, LD = NP + 1, TW = 64;
-    extern __shared__ double2 sm[];
-    double2* sLU = sm;            // NP x LD
-    double2* sT = sLU + NP * LD;  // TW x LD
-    double2* srp = sT + TW * LD;  // NP
-    const int4 it = items[blockIdx.x];
-    const int s = it.x, kind = it.y, t0 = it.z;
-    const int b = blockIdx.y;
-    const int nf = d.ld[s], np = d.np[s], ncb = d.nf[s] - np;
-    double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
-    const int* pv = piv + (size_t)b * d.n + d.sn_ptr[s];
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < NP * NP; idx += 64) {
-        const int i = idx % NP, j = idx / NP;
-        sLU[i + j * LD] = (i < np && j < np) ? F[(size_t)i + (size_t)j * nf] : make_double2(i == j ? 1.0 : 0.0, 0.0);
-    }
-    const int tw = min(TW, ncb - t0);
-    if (kind == 0) {
-        for (int idx = tid; idx < tw * NP; idx += 64) {
-            const int i = idx % NP, c = idx / NP;
-            sT[i + c * LD] = (i < np) ? F[(size_t)i + (size_t)(np + t0 + c) * nf] : make_double2(0.0, 0.0);
-        }
-        __syncthreads();
-        if (tid < tw) {
-            double2* xs = sT + tid * LD;
-            for (int j = 0; j < np; ++j) {
-                const int pr = pv[j];
-                if (pr != j) { const double2 t = xs[j]; xs[j] = xs[pr]; xs[pr] = t; }
-            }
-            double2 x[NP];
-#pragma unroll
-            for (int i = 0; i < NP; ++i) x[i] = xs[i];
-#pragma unroll 1
-            for (int j = 0; j < np - 1; ++j) {  // run-time j, static register indices (see lu_diag_warp_kernel)
-                double2 xj = x[0];
-#pragma unroll
-                for (int i = 1; i < NP; ++i)
-                    if (i == j) xj = x[i];
-#pragma unroll
-                for (int i = 1; i < NP; ++i)
-                    if (i > j) cfms(x[i], sLU[i + j * LD], xj);
-            }
-#pragma unroll
-            for (int i = 0; i < NP; ++i) xs[i] = x[i];
-        }
-        __syncthreads();
-        for (int idx = tid; idx < tw * np; idx += 64) {
-            const int i = idx % np, c = idx / np;
-            F[(size_t)i + (size_t)(np + t0 + c) * nf] = sT[i + c * LD];
-        }
-    } else {
-        for (int idx = tid; idx < TW * NP; idx += 64) {
-            const int r = idx % TW, j = idx / TW;
-            sT[r + j * TW] = (r < tw && j < np) ? F[(size_t)(np + t0 + r) + (size_t)j * nf] : make_double2(0.0, 0.0);
-        }
-        __syncthreads();
-        if (tid < NP) srp[tid] = crecip(sLU[tid + tid * LD]);
-        __syncthreads();
-        if (tid < tw) {
-            double2 x[NP];
-#pragma unroll
-            for (int j = 0; j < NP; ++j) x[j] = sT[tid + j * TW];
-            // right-looking: once x_t is final, subtract x_t U[t, j] from every later column j
-#pragma unroll 1
-            for (int t = 0; t < np; ++t) {
-                double2 xt = x[0];
-#pragma unroll
-                for (int j = 1; j < NP; ++j)
-                    if (j == t) xt = x[j];
-                xt = cmul(xt, srp[t]);
-#pragma unroll
-                for (int j = 0; j < NP; ++j) {
-                    if (j == t) x[j] = xt;
-                    if (j > t) cfms(x[j], xt, sLU[t + j * LD]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < NP; ++j) sT[tid + j * TW] = x[j];
-        }
-        __syncthreads();
-        for (int idx = tid; idx < tw * np; idx += 64) {
-            const int r = idx % tw, j = idx / tw;
-            F[(size_t)(np + t0 + r) + (size_t)j * nf] = sT[r + j * TW];
+        if (minpiv < INFINITY) {
+            const double ratio = amax > 0.0 ? minpiv / amax : 0.0;
+            atomicMin((unsigned long long*)&info[b].minpiv_bits, (unsigned long long)__double_as_longlong(ratio));
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// panel: item = (front s, kind 0 = U tile / 1 = L tile, tile start t0); 64 columns (rows) per tile
+// panel: item = (front s, kind 0 = U tile / 1 = L tile, tile start t0), 64 columns (rows) per tile, as dense products
+// with the inverted pivot block:  U12 = inv(L11) (P F12),  L21 = F21 inv(U11).
 // ---------------------------------------------------------------------------------------------
 constexpr int PANEL_T = 64;
-__global__ void __launch_bounds__(128) lu_panel_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts,
-                                                       const int* __restrict__ piv) {
+constexpr size_t PANEL_SMEM = ((size_t)DNP * (DNP + 1) + (size_t)DNP * (PANEL_T + 1)) * 16;
+__global__ void __launch_bounds__(256) lu_panel_inv_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts,
+                                                           const int* __restrict__ piv) {
     extern __shared__ double2 sm[];
+    double2* sI = sm;                    // [t][i], stride DNP+1: inv(L11) (kind 0, unit diagonal) or inv(U11) (kind 1)
+    double2* sB = sm + DNP * (DNP + 1);  // kind 0: [t][c] stride PANEL_T+1 ; kind 1: [t][r] stride PANEL_T
     const int4 it = items[blockIdx.x];
     const int s = it.x, kind = it.y, t0 = it.z;
     const int b = blockIdx.y;
-    const int nf = d.ld[s], np = d.np[s], ncb = d.nf[s] - np, ld = np + 1;  // nf: leading dimension of the front storage
-    double2* sLU = sm;                   // np x np, ld = np+1
-    double2* sT = sm + (size_t)np * ld;  // tile: U kind [PANEL_T][np+1] (column c at sT + c*ld); L kind [np][PANEL_T]
+    const int ld = d.ld[s], np = d.np[s], ncb = d.nf[s] - np;
     double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
     const int* pv = piv + (size_t)b * d.n + d.sn_ptr[s];
     const int tid = threadIdx.x;
-    for (int idx = tid; idx < np * np; idx += blockDim.x) {
-        const int i = idx % np, j = idx / np;
-        sLU[i + j * ld] = F[(size_t)i + (size_t)j * nf];
-    }
     const int tw = min(PANEL_T, ncb - t0);
     if (kind == 0) {
-        // U12 tile: columns np+t0 .. np+t0+tw-1, rows 0..np-1 (contiguous per column)
-        for (int idx = tid; idx < tw * np; idx += blockDim.x) {
-            const int i = idx % np, c = idx / np;
-            sT[i + c * ld] = F[(size_t)i + (size_t)(np + t0 + c) * nf];
+        // sI[t][i] = inv(L11)[i][t]
+        for (int idx = tid; idx < DNP * DNP; idx += 256) {
+            const int i = idx % DNP, t = idx / DNP;
+            double2 v = make_double2(i == t ? 1.0 : 0.0, 0.0);
+            if (i < np && t < i) v = F[(size_t)i + (size_t)t * ld];
+            sI[t * (DNP + 1) + i] = v;
+        }
+        for (int idx = tid; idx < np * PANEL_T; idx += 256) {
+            const int t = idx % np, c = idx / np;
+            sB[t * (PANEL_T + 1) + c] = (c < tw) ? F[(size_t)pv[t] + (size_t)(np + t0 + c) * ld] : make_double2(0.0, 0.0);
         }
         __syncthreads();
-        if (tid < tw) {
-            double2* x = sT + tid * ld;
-            for (int j = 0; j < np; ++j) {  // row swaps of the pivot block
-                const int pr = pv[j];
-                if (pr != j) { const double2 t = x[j]; x[j] = x[pr]; x[pr] = t; }
-            }
-            for (int j = 0; j < np; ++j) {  // unit lower solve
-                const double2 xj = x[j];
-                for (int i = j + 1; i < np; ++i) cfms(x[i], sLU[i + j * ld], xj);
-            }
+        const int i = tid & 31, cs = tid >> 5;
+        double2 acc[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) acc[m] = make_double2(0.0, 0.0);
+        for (int t = 0; t < np; ++t) {
+            const double2 l = sI[t * (DNP + 1) + i];
+            const double2* bb = sB + t * (PANEL_T + 1) + cs;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) cfma2(acc[m], l, bb[8 * m]);
         }
-        __syncthreads();
-        for (int idx = tid; idx < tw * np; idx += blockDim.x) {
-            const int i = idx % np, c = idx / np;
-            F[(size_t)i + (size_t)(np + t0 + c) * nf] = sT[i + c * ld];
+        if (i < np) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int c = cs + 8 * m;
+                if (c < tw) F[(size_t)i + (size_t)(np + t0 + c) * ld] = acc[m];
+            }
         }
     } else {
-        // L21 tile: rows np+t0 .. , columns 0..np-1 ; x U11 = f  ->  x_j = (f_j - sum_{t<j} x_t U[t,j]) / U[j,j]
-        for (int idx = tid; idx < tw * np; idx += blockDim.x) {
-            const int r = idx % tw, j = idx / tw;
-            sT[r + j * PANEL_T] = F[(size_t)(np + t0 + r) + (size_t)j * nf];
+        // sI[t][c] = inv(U11)[t][c] (zero below the diagonal)
+        for (int idx = tid; idx < DNP * DNP; idx += 256) {
+            const int t = idx % DNP, c = idx / DNP;
+            double2 v = make_double2(0.0, 0.0);
+            if (c < np && t <= c) v = F[(size_t)t + (size_t)c * ld];
+            sI[t * (DNP + 1) + c] = v;
+        }
+        for (int idx = tid; idx < np * PANEL_T; idx += 256) {
+            const int r = idx % PANEL_T, t = idx / PANEL_T;
+            sB[t * PANEL_T + r] = (r < tw) ? F[(size_t)(np + t0 + r) + (size_t)t * ld] : make_double2(0.0, 0.0);
         }
         __syncthreads();
-        if (tid < tw) {
-            for (int j = 0; j < np; ++j) {
-                double2 x = sT[tid + j * PANEL_T];
-                for (int t = 0; t < j; ++t) cfms(x, sT[tid + t * PANEL_T], sLU[t + j * ld]);
-                sT[tid + j * PANEL_T] = cmul(x, crecip(sLU[j + j * ld]));
-            }
+        const int r = tid & 63, cg = (tid >> 6) * 8;
+        double2 acc[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) acc[m] = make_double2(0.0, 0.0);
+        for (int t = 0; t < np; ++t) {
+            const double2 f = sB[t * PANEL_T + r];
+            const double2* uu = sI + t * (DNP + 1) + cg;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) cfma2(acc[m], f, uu[m]);
         }
-        __syncthreads();
-        for (int idx = tid; idx < tw * np; idx += blockDim.x) {
-            const int r = idx % tw, j = idx / tw;
-            F[(size_t)(np + t0 + r) + (size_t)j * nf] = sT[r + j * PANEL_T];
+        if (r < tw) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+                if (cg + m < np) F[(size_t)(np + t0 + r) + (size_t)(cg + m) * ld] = acc[m];
         }
     }
 }
@@ -783,23 +696,21 @@ __global__ void __launch_bounds__(256) lu_forward_kernel(LuDev d, const int* __r
         }
         __syncthreads();
     }
-    // 2. row swaps, 3. unit lower solve on the pivot rows (L11 staged in shared memory)
-    if (tid < k) {
-        for (int j = 0; j < np; ++j) {
-            const int pr = pv[j];
-            if (pr != j) { const double2 t = sy[j * k + tid]; sy[j * k + tid] = sy[pr * k + tid]; sy[pr * k + tid] = t; }
-        }
+    // 2.+3. y1 = inv(L11) (P b1): one small dense product, no dependency chain (inv(L11) is stored by lu_diag_inv_kernel)
+    double2* sTmp = sT + (size_t)max_np * SOLVE_TILE;  // the sX region: np x k permuted right-hand side
+    for (int idx = tid; idx < np * k; idx += blockDim.x) sTmp[idx] = sy[pv[idx / k] * k + idx % k];
+    for (int idx = tid; idx < np * np; idx += blockDim.x) {
+        const int i = idx % np, t = idx / np;
+        sT[idx] = (t < i) ? F[(size_t)i + (size_t)t * ld] : make_double2(i == t ? 1.0 : 0.0, 0.0);  // sT[t*np + i] = inv(L11)[i][t]
     }
-    for (int idx = tid; idx < np * np; idx += blockDim.x) sT[idx] = F[(size_t)(idx % np) + (size_t)(idx / np) * ld];
     __syncthreads();
-    for (int j = 0; j < np - 1; ++j) {
-        const int m = np - j - 1;
-        for (int idx = tid; idx < m * k; idx += blockDim.x) {
-            const int i = j + 1 + idx / k, col = idx % k;
-            cfms(sy[i * k + col], sT[i + j * np], sy[j * k + col]);
-        }
-        __syncthreads();
+    for (int idx = tid; idx < np * k; idx += blockDim.x) {
+        const int i = idx / k, col = idx % k;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int t = 0; t <= i; ++t) cfma2(acc, sT[t * np + i], sTmp[t * k + col]);
+        sy[idx] = acc;
     }
+    __syncthreads();
     for (int idx = tid; idx < np * k; idx += blockDim.x) Xb[(size_t)c0 * k + idx] = sy[idx];
     // 4. update rows; big fronts leave this to lu_forward_update_kernel (several CTAs per front)
     if (ncb > SOLVE_BIG) return;
@@ -879,17 +790,20 @@ __global__ void __launch_bounds__(256) lu_backward_kernel(LuDev d, const int* __
         bwd_product<CK>(F, ld, np, 0, ncb, rows, Xb, k, sy, sT, sX, true);
     }
     __syncthreads();
-    for (int idx = tid; idx < np * np; idx += blockDim.x) sT[idx] = F[(size_t)(idx % np) + (size_t)(idx / np) * ld];
-    __syncthreads();
-    for (int j = np - 1; j >= 0; --j) {
-        if (tid < k) sy[j * k + tid] = cmul(sy[j * k + tid], crecip(sT[j + j * np]));
-        __syncthreads();
-        for (int idx = tid; idx < j * k; idx += blockDim.x) {
-            const int i = idx / k, col = idx % k;
-            cfms(sy[i * k + col], sT[i + j * np], sy[j * k + col]);
-        }
-        __syncthreads();
+    // x1 = inv(U11) * sy
+    for (int idx = tid; idx < np * np; idx += blockDim.x) {
+        const int i = idx % np, t = idx / np;
+        sT[idx] = (t >= i) ? F[(size_t)i + (size_t)t * ld] : make_double2(0.0, 0.0);  // sT[t*np + i] = inv(U11)[i][t]
     }
+    for (int idx = tid; idx < np * k; idx += blockDim.x) sX[idx] = sy[idx];
+    __syncthreads();
+    for (int idx = tid; idx < np * k; idx += blockDim.x) {
+        const int i = idx / k, col = idx % k;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int t = i; t < np; ++t) cfma2(acc, sT[t * np + i], sX[t * k + col]);
+        sy[idx] = acc;
+    }
+    __syncthreads();
     for (int idx = tid; idx < np * k; idx += blockDim.x) Xb[(size_t)c0 * k + idx] = sy[idx];
 }
 
@@ -964,10 +878,10 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     NEPB_CHECK_ARG(h->n < (int64_t)1 << 31, "n too large");
     LuSymbolicDev* sd = new LuSymbolicDev();
     LuOptions opt = hm->lu_opt_set ? hm->lu_opt : g_default_opt;
-    if (const char* e = getenv("NEPB_LU_MAXNP")) opt.max_np = std::max(1, std::min(64, atoi(e)));
+    if (const char* e = getenv("NEPB_LU_MAXNP")) opt.max_np = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("NEPB_LU_RELAX")) opt.relax_leaf = std::max(1, atoi(e));
     if (const char* e = getenv("NEPB_LU_ORDERING")) opt.ordering = atoi(e);
-    opt.max_np = std::max(1, std::min(64, opt.max_np));
+    opt.max_np = std::max(1, std::min(32, opt.max_np));  // the pivot-block kernels hold a 32 x 32 block in one warp's lanes
     int rc = lu_symbolic_analyse((int)h->n, h->h_rowptr, h->h_colind, hm->lu_user_perm.empty() ? nullptr : hm->lu_user_perm.data(), opt, sd->S);
     if (rc) {
         delete sd;
@@ -1104,10 +1018,8 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     sd->smem_schur_pipe = (size_t)mnp * (3 * SCHUR_T + 2) * 16;
     sd->schur_pipe = sd->smem_schur_pipe <= 110 * 1024 && !getenv("NEPB_LU_SCHUR_SIMPLE");
     cudaFuncSetAttribute(lu_schur_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_schur_pipe);
-    cudaFuncSetAttribute(lu_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_diag);
-    cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_panel);
+    cudaFuncSetAttribute(lu_panel_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM);
     cudaFuncSetAttribute(lu_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_schur);
-    cudaFuncSetAttribute(lu_panel32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL32_SMEM);
 #define NEPB_SOLVE_ATTR(CK_)                                                                                    \
     cudaFuncSetAttribute(lu_forward_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);       \
     cudaFuncSetAttribute(lu_backward_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);       \
@@ -1122,21 +1034,24 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
 
 void lu_symbolic_release(void* p) { delete (LuSymbolicDev*)p; }
 
-// numeric factorisation of lu->nb shifts into lu->fronts (coefficients already on the device)
-static int lu_factor_device(nepb_lu* lu) {
+__global__ void lu_info_init_kernel(int nb, LuInfo* __restrict__ info) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    info[b].amax_bits = 0;
+    info[b].minpiv_bits = 0x7ff0000000000000ULL;  // +inf
+    info[b].flags = 0;
+    info[b].nperturbed = 0;
+}
+
+// numeric factorisation of lu->nb shifts into lu->fronts (coefficients already on the device); device work only, so the
+// sequence can be captured into a CUDA graph
+int lu_factor_device(nepb_lu* lu) {
     const nepb_spmf* h = lu->op;
     LuSymbolicDev* sd = lu->sym;
     const LuSymbolic& S = sd->S;
     const int nb = lu->nb;
     NEPB_CUDA(cudaMemsetAsync(lu->fronts.p, 0, sizeof(double) * 2 * (size_t)nb * S.front_total, stream()));
-    lu->h_info.resize(nb);
-    for (auto& x : lu->h_info) {
-        x.amax_bits = 0;
-        x.minpiv_bits = 0x7ff0000000000000ULL;  // +inf
-        x.flags = 0;
-        x.nperturbed = 0;
-    }
-    NEPB_CUDA(cudaMemcpyAsync(lu->info.p, lu->h_info.data(), sizeof(LuInfo) * nb, cudaMemcpyHostToDevice, stream()));
+    NEPB_LAUNCH(lu_info_init_kernel, (nb + 127) / 128, 128, 0, nb, lu->info.p);
     {
         dim3 grid((unsigned)((h->nnz + 255) / 256), nb);
         NEPB_LAUNCH(lu_assemble_kernel, grid, 256, 0, h->nnz, h->p, h->is_complex, sd->a_pos.p, h->d_vals.p, (const double2*)lu->coef.p,
@@ -1146,13 +1061,8 @@ static int lu_factor_device(nepb_lu* lu) {
     for (int l = 0; l < S.nlevels; ++l) {
         const auto& L = sd->lv[l];
         if (L.ea_count) NEPB_LAUNCH(lu_extend_add_kernel, dim3(L.ea_count, nb), 256, 0, sd->dev, sd->ea_items.p + L.ea_begin, F);
-        if (S.max_np <= 32) {
-            NEPB_LAUNCH(lu_diag_warp_kernel, dim3(L.front_count, nb), 32, 0, sd->dev, sd->fr_items.p + L.front_begin, F, lu->piv.p, lu->info.p);
-            if (L.pn_count) NEPB_LAUNCH(lu_panel32_kernel, dim3(L.pn_count, nb), 64, PANEL32_SMEM, sd->dev, sd->pn_items.p + L.pn_begin, F, lu->piv.p);
-        } else {
-            NEPB_LAUNCH(lu_diag_kernel, dim3(L.front_count, nb), 256, sd->smem_diag, sd->dev, sd->fr_items.p + L.front_begin, F, lu->piv.p, lu->info.p);
-            if (L.pn_count) NEPB_LAUNCH(lu_panel_kernel, dim3(L.pn_count, nb), 128, sd->smem_panel, sd->dev, sd->pn_items.p + L.pn_begin, F, lu->piv.p);
-        }
+        NEPB_LAUNCH(lu_diag_inv_kernel, dim3(L.front_count, nb), 128, 0, sd->dev, sd->fr_items.p + L.front_begin, F, lu->piv.p, lu->info.p);
+        if (L.pn_count) NEPB_LAUNCH(lu_panel_inv_kernel, dim3(L.pn_count, nb), 256, PANEL_SMEM, sd->dev, sd->pn_items.p + L.pn_begin, F, lu->piv.p);
         if (L.sc_count && sd->schur_pipe)
             NEPB_LAUNCH(lu_schur_pipe_kernel, dim3(L.sp_count, nb), 256, sd->smem_schur_pipe, sd->dev, sd->sp_items.p + L.sp_begin, F);
         else if (L.sc_count)
@@ -1164,6 +1074,16 @@ static int lu_factor_device(nepb_lu* lu) {
 
 // Solve for the shifts [shift0, shift0+nb): Bdev holds right-hand sides [b][n][k] row-major (rhs_stride = n*k) or one
 // shared block (rhs_stride = 0); Xdev [b][n][k].  Asynchronous on the library stream.
+// grow the solve scratch for nb shifts x k right-hand sides (must happen outside graph capture)
+int lu_solve_reserve(nepb_lu* lu, int nb, int k) {
+    LuSymbolicDev* sd = lu->sym;
+    const LuSymbolic& S = sd->S;
+    NEPB_CUDA(lu->xp.reserve((size_t)2 * nb * S.n * k));
+    NEPB_CUDA(lu->w.reserve((size_t)2 * nb * S.w_total * k));
+    NEPB_CUDA(lu->part.reserve((size_t)2 * nb * std::max(sd->part_slots, 1) * S.max_np * k));
+    return NEPB_OK;
+}
+
 int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev, size_t rhs_stride, double2* Xdev) {
     LuSymbolicDev* sd = lu->sym;
     const LuSymbolic& S = sd->S;
@@ -1330,7 +1250,7 @@ int nepb_lu_analyse_pattern(int64_t n, const int64_t* colptr, const int64_t* row
     LuOptions opt;
     if (ordering >= 0) opt.ordering = ordering;
     if (relax_leaf > 0) opt.relax_leaf = relax_leaf;
-    if (max_np > 0) opt.max_np = std::min(64, max_np);
+    if (max_np > 0) opt.max_np = std::min(32, max_np);
     LuSymbolic S;
     // the analysis symmetrises the pattern, so CSC and CSR input are equivalent
     int rc = lu_symbolic_analyse((int)n, rp.data(), ci.data(), nullptr, opt, S);

@@ -82,6 +82,8 @@ namespace nepb {
 int lu_create(const nepb_spmf* h, int nshift, const double* coef, nepb_lu** out);
 // factorise shifts already described by lu->coef (device); used by the contour loop to recycle the storage
 int lu_refactor(nepb_lu* lu, int nshift, const double* coef);
+int lu_factor_device(nepb_lu* lu);                 // device work only (capturable); coefficients already in lu->coef
+int lu_solve_reserve(nepb_lu* lu, int nb, int k);  // grow scratch outside capture
 // solve for shifts [shift0, shift0+nb): Bdev [b][n][k] (rhs_stride = n*k) or shared (0); Xdev [b][n][k]
 int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev, size_t rhs_stride, double2* Xdev);
 }  // namespace nepb

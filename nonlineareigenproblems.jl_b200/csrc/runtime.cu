@@ -20,7 +20,24 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static thread_local cudaStream_t t_override = nullptr;
+static thread_local bool t_has_override = false;
+
+// Work of the calling thread goes to `s` until reset_current_stream(): the contour loop spreads groups of quadrature
+// nodes over several streams so that latency-bound levels of one group overlap throughput-bound levels of another.
+void set_current_stream(cudaStream_t s) {
+    t_override = s;
+    t_has_override = true;
+}
+void reset_current_stream() { t_has_override = false; }
+cudaStream_t main_stream();
+
 cudaStream_t stream() {
+    if (t_has_override) return t_override;
+    return main_stream();
+}
+
+cudaStream_t main_stream() {
     if (!g_stream) {
         if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) == cudaSuccess) g_stream_owned = true;
     }

@@ -47,10 +47,17 @@ WORKER = textwrap.dedent("""
 def test_world_size_2_gloo_sharded_contour(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", str(script)]
+    import socket
     env = dict(os.environ, OMP_NUM_THREADS="1")
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    for attempt in range(3):  # the gloo rendezvous on a loaded CI box occasionally times out: retry on a fresh port
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), str(script)]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+        if r.returncode == 0:
+            break
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("ok 32 nodes") == 2
 
