@@ -442,6 +442,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
+// C -= v as a fire-and-forget reduction performed in L2: no load, so the epilogue never waits on HBM.  Every element of
+// the trailing matrix receives exactly one such update per level, so the result does not depend on any ordering.
+__device__ __forceinline__ void red_sub_c(double2* addr, double2 v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(&addr->x), "d"(-v.x) : "memory");
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(&addr->y), "d"(-v.y) : "memory");
+}
+
 constexpr int SCHUR_GROUP = 4;  // column tiles per item
 __global__ void __launch_bounds__(256, 2) lu_schur_pipe_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts) {
     extern __shared__ double2 sm[];
@@ -505,17 +512,9 @@ __global__ void __launch_bounds__(256, 2) lu_schur_pipe_kernel(LuDev d, const in
             const int cc = ty + 16 * c;
             if (cc < tw) {
                 double2* col = F + (size_t)(np + i0) + (size_t)(np + j0 + cc) * nf;
-                double2 o[4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
-                    if (tx + 16 * r < th) o[r] = col[tx + 16 * r];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    if (tx + 16 * r < th) {
-                        o[r].x -= acc[r][c].x;
-                        o[r].y -= acc[r][c].y;
-                        col[tx + 16 * r] = o[r];
-                    }
+                    if (tx + 16 * r < th) red_sub_c(col + tx + 16 * r, acc[r][c]);
             }
         }
         __syncthreads();  // the buffer of tile q is refilled in iteration q + 1
@@ -952,6 +951,8 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
         sd->part_slots = std::max(sd->part_slots, slots);
         L.fu_count = (int)fu_items.size() - L.fu_begin;
         L.bp_count = (int)bp_items.size() - L.bp_begin;
+        L.max_np = 1;
+        for (int s2 : fl) L.max_np = std::max(L.max_np, (int)np[s2]);
         L.front_count = (int)fr_items.size() - L.front_begin;
         L.ea_count = (int)ea_items.size() - L.ea_begin;
         L.pn_count = (int)pn_items.size() - L.pn_begin;
@@ -1100,23 +1101,27 @@ int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev,
     const int* piv = lu->piv.p + (size_t)shift0 * n;
     dim3 pg((unsigned)(((size_t)n * k + 255) / 256), nb);
     NEPB_LAUNCH(lu_permute_in_kernel, pg, 256, 0, n, k, sd->perm.p, Bdev, rhs_stride, Xp);
+    // shared memory is carved with the level's own largest pivot block: the many small fronts at the bottom of the tree
+    // then fit more CTAs per SM
 #define NEPB_SOLVE_LEVELS(CK_)                                                                                                           \
     do {                                                                                                                                  \
         for (int l = 0; l < S.nlevels; ++l) {                                                                                             \
             const auto& L = sd->lv[l];                                                                                                    \
-            NEPB_LAUNCH((lu_forward_kernel<CK_>), dim3(L.front_count, nb), 256, smem, sd->dev, sd->fr_items.p + L.front_begin, F, piv, Xp, \
-                        W, k, S.max_np);                                                                                                          \
+            const size_t sml = solve_smem_bytes(L.max_np, k);                                                                             \
+            NEPB_LAUNCH((lu_forward_kernel<CK_>), dim3(L.front_count, nb), 256, sml, sd->dev, sd->fr_items.p + L.front_begin, F, piv, Xp,  \
+                        W, k, L.max_np);                                                                                                  \
             if (L.fu_count)                                                                                                               \
-                NEPB_LAUNCH((lu_forward_update_kernel<CK_>), dim3(L.fu_count, nb), 128, smem, sd->dev, sd->fu_items.p + L.fu_begin, F,     \
-                            (const double2*)Xp, W, k, S.max_np);                                                                                 \
+                NEPB_LAUNCH((lu_forward_update_kernel<CK_>), dim3(L.fu_count, nb), 128, sml, sd->dev, sd->fu_items.p + L.fu_begin, F,      \
+                            (const double2*)Xp, W, k, L.max_np);                                                                          \
         }                                                                                                                                 \
         for (int l = S.nlevels - 1; l >= 0; --l) {                                                                                        \
             const auto& L = sd->lv[l];                                                                                                    \
+            const size_t sml = solve_smem_bytes(L.max_np, k);                                                                             \
             if (L.bp_count)                                                                                                               \
-                NEPB_LAUNCH((lu_backward_partial_kernel<CK_>), dim3(L.bp_count, nb), 128, smem, sd->dev, sd->bp_items.p + L.bp_begin, F,   \
-                            (const double2*)Xp, part, sd->part_slots, S.max_np, k);                                                       \
-            NEPB_LAUNCH((lu_backward_kernel<CK_>), dim3(L.front_count, nb), 256, smem, sd->dev, sd->fr_items.p + L.front_begin, F, Xp,     \
-                        (const double2*)part, sd->part_slots, S.max_np, k);                                                               \
+                NEPB_LAUNCH((lu_backward_partial_kernel<CK_>), dim3(L.bp_count, nb), 128, sml, sd->dev, sd->bp_items.p + L.bp_begin, F,    \
+                            (const double2*)Xp, part, sd->part_slots, L.max_np, k);                                                       \
+            NEPB_LAUNCH((lu_backward_kernel<CK_>), dim3(L.front_count, nb), 256, sml, sd->dev, sd->fr_items.p + L.front_begin, F, Xp,      \
+                        (const double2*)part, sd->part_slots, L.max_np, k);                                                               \
         }                                                                                                                                 \
     } while (0)
     NEPB_CUDA(lu->part.reserve((size_t)2 * nb * std::max(sd->part_slots, 1) * S.max_np * k));

@@ -35,7 +35,7 @@ struct LuInfo {
 };
 
 struct LuLevel {
-    int front_begin = 0, front_count = 0;
+    int front_begin = 0, front_count = 0, max_np = 1;
     int ea_begin = 0, ea_count = 0;
     int pn_begin = 0, pn_count = 0;
     int sc_begin = 0, sc_count = 0;
