@@ -20,3 +20,4 @@ from .solvers import (contour_beyn, ContourIntegrator, beyn_extract, beyn_quadra
                       LostOrthogonalityException)
 from .dense import (dgks, block_gemm, copy_cols, colnorms, solve_block, mlincomb_block, residual_errors,  # noqa: F401
                     tiar_device, iar_device)
+from .nleigs import nleigs_backslash, backslash_coefficients, DeviceLinSolverCache  # noqa: F401
