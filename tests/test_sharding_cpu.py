@@ -39,7 +39,7 @@ WORKER = textwrap.dedent("""
     assert np.linalg.norm(S[:, :, 1] - A1) < 1e-13 * np.linalg.norm(A1)
     lam, V, inf2 = nepb200.beyn_extract(S[:, :, 0], S[:, :, 1], sigma, (radius, radius), 4, 3, 1e-8, 1e-8, None, False)
     assert len(lam) == len(lo) and max(min(abs(lam - x)) for x in lo) < 1e-12
-    open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "rank%d.ok" % rank), "w").write("%d" % len(mine))
+    open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "rank" + str(rank) + ".ok"), "w").write(str(len(mine)))
     td.destroy_process_group()
 """) % ROOT
 
