@@ -355,3 +355,55 @@ def tiar(nep, maxit=30, linsolvercreator=None, tol=np.finfo(float).eps * 10000, 
     lam = lam[:min(len(lam), conv_eig)]
     Q = Q[:, :min(Q.shape[1], conv_eig)]
     return lam, Q, Z[:, :k], hist
+
+
+# ---------------------------------------------------------------------------------------------
+# contour_block_SS (src/method_block_SS.jl:46-215, Shat_mode = :native): same quadrature seam, 2K moments
+# ---------------------------------------------------------------------------------------------
+def block_ss_quadrature(N, radius, sigma, K, rank=0, world=1):
+    """Nodes / weights for the 2K moments Shat_j = (1/2 pi i) oint z^j M(z+sigma)^-1 V dz (method_block_SS.jl:135-152)."""
+    radius = (radius, radius) if np.isscalar(radius) else tuple(radius)
+    h = 2 * np.pi / N
+    t = h * np.arange(N)
+    g = radius[0] * np.cos(t) + 1j * radius[1] * np.sin(t)
+    gp = -radius[0] * np.sin(t) + 1j * radius[1] * np.cos(t)
+    W = np.stack([gp * g ** j * h / (2j * np.pi) for j in range(2 * K)], axis=1)
+    mine = np.arange(rank, N, world)
+    return mine, g[mine] + sigma, W[mine]
+
+
+def block_ss_extract(Shat, U, sigma, K, rank_drop_tol):
+    """method_block_SS.jl:156-214 (host: (K k) x (K k) Hankel matrices, SVD, generalised eigenproblem)."""
+    import scipy.linalg as sla
+    n, L, _ = Shat.shape
+    Mhat = [U.conj().T @ Shat[:, :, j] for j in range(2 * K)]
+    Hhat = np.block([[Mhat[i + j] for j in range(K)] for i in range(K)])
+    Hhat2 = np.block([[Mhat[i + j + 1] for j in range(K)] for i in range(K)])
+    UU, SS, VVh = np.linalg.svd(Hhat)
+    mprime = int(np.count_nonzero(SS / SS[0] > rank_drop_tol))
+    UU1, VV1 = UU[:, :mprime], VVh.conj().T[:, :mprime]
+    xi, X = sla.eig(UU1.conj().T @ Hhat2 @ VV1, UU1.conj().T @ Hhat @ VV1)
+    S = np.concatenate([Shat[:, :, j] for j in range(K)], axis=1)
+    return sigma + xi, S @ VV1 @ X, mprime
+
+
+def contour_block_SS(nep: B200SPMF, U=None, V=None, sigma=0.0, radius=1.0, N=1000, k=3, K=3, tol=np.sqrt(np.finfo(float).eps),
+                     rank_drop_tol=None, batch=32, rank=0, world=1, return_moments=False, seed=10):
+    n = nep.n
+    rank_drop_tol = tol if rank_drop_tol is None else rank_drop_tol
+    rng = np.random.default_rng(seed)
+    U = rng.random((n, k)) if U is None else np.asarray(U)
+    V = rng.random((n, k)) if V is None else np.asarray(V)
+    k = V.shape[1]
+    mine, lams, W = block_ss_quadrature(N, radius, sigma, K, rank, world)
+    integ = ContourIntegrator(nep, k, 2 * K, min(batch, max(1, len(mine))))
+    try:
+        Shat, flags = integ.integrate(lams, W, V, reduce=world > 1)
+    finally:
+        integ.close()
+    if np.any(flags & 2):
+        raise _lib.SingularException(_lib.NEPB_E_SINGULAR, "non-finite pivot at a quadrature node: an eigenvalue lies on the contour")
+    lam, Vec, mprime = block_ss_extract(Shat, np.asarray(U, dtype=np.complex128), sigma, K, rank_drop_tol)
+    if return_moments:
+        return lam, Vec, Shat, mprime
+    return lam, Vec

@@ -349,3 +349,48 @@ def tiar(nep, maxit=30, linsolvercreator=None, tol=np.finfo(float).eps * 10000, 
     lam = lam[:min(len(lam), conv_eig)]
     Q = Q[:, :min(Q.shape[1], conv_eig)]
     return lam, Q, Z[:, :k], conv_hist
+
+
+# --------------------------------------------------------------------------------------------
+# contour_block_SS (src/method_block_SS.jl:46-215, Shat_mode = :native)
+# --------------------------------------------------------------------------------------------
+def block_ss_extract(Shat, U, sigma, K, rank_drop_tol):
+    """method_block_SS.jl:156-214: Hankel moment matrices, SVD rank cut, generalised eigenproblem, eigenvectors."""
+    n, L, _ = Shat.shape
+    Mhat = np.stack([U.conj().T @ Shat[:, :, j] for j in range(2 * K)], axis=2)
+    m = K * L
+    Hhat = np.zeros((m, m), dtype=np.complex128)
+    Hhat2 = np.zeros((m, m), dtype=np.complex128)
+    for i in range(K):
+        for j in range(K):
+            Hhat[i * L:(i + 1) * L, j * L:(j + 1) * L] = Mhat[:, :, i + j]
+            Hhat2[i * L:(i + 1) * L, j * L:(j + 1) * L] = Mhat[:, :, i + j + 1]
+    UU, SS, VVh = np.linalg.svd(Hhat)
+    VV = VVh.conj().T
+    mprime = int(np.count_nonzero(SS / SS[0] > rank_drop_tol))
+    UU1, VV1 = UU[:, :mprime], VV[:, :mprime]
+    import scipy.linalg as L_
+    xi, X = L_.eig(UU1.conj().T @ Hhat2 @ VV1, UU1.conj().T @ Hhat @ VV1)
+    S = np.concatenate([Shat[:, :, j] for j in range(K)], axis=1)
+    return sigma + xi, S @ VV1 @ X, mprime
+
+
+def contour_block_SS(nep, U, V, sigma=0.0, radius=1.0, N=1000, K=3, tol=np.sqrt(np.finfo(float).eps), linsolvercreator=None,
+                     rank_drop_tol=None, return_moments=False):
+    """U, V (n x k) are supplied by the caller (the reference draws them with Julia's rand after Random.seed!(10))."""
+    radius = (radius, radius) if np.isscalar(radius) else tuple(radius)
+    rank_drop_tol = tol if rank_drop_tol is None else rank_drop_tol
+    creator = linsolvercreator or BackslashLinSolverCreator()
+    V = np.asarray(V, dtype=np.complex128)
+    g = lambda t: complex(radius[0] * np.cos(t), radius[1] * np.sin(t))
+    gp = lambda t: complex(-radius[0] * np.sin(t), radius[1] * np.cos(t))
+
+    def f(t):
+        return creator.create_linsolver(nep, g(t) + sigma).lin_solve(V) * gp(t) / (2j * np.pi)
+
+    gv = [(lambda s, kk=kk: g(s) ** kk) for kk in range(2 * K)]
+    Shat = integrate_interval_trapezoidal(f, gv, 0.0, 2 * np.pi, N)
+    lam, Vec, mprime = block_ss_extract(Shat, np.asarray(U, dtype=np.complex128), sigma, K, rank_drop_tol)
+    if return_moments:
+        return lam, Vec, Shat, mprime
+    return lam, Vec

@@ -144,3 +144,13 @@ def test_oracle_iar_tiar_dep0():
     lam2, Q2, Z, hist = s.tiar(nep, sigma=0.0, gamma=1.0, neigs=3, maxit=60, v=v0, tol=1e-10)
     assert np.allclose(np.sort_complex(lam), np.sort_complex(lam2), atol=1e-6)
     assert np.linalg.norm(Z.conj().T @ Z - np.eye(Z.shape[1])) < 1e-6
+
+
+def test_oracle_block_SS_dep0():
+    # test/contour_block_SS.jl:9-17
+    from oracle import solvers as s
+    nep = o.nep_gallery("dep0", 3)
+    U, V = g.gen_rng_mat(g.MSWS_RNG(1), 3, 3), g.gen_rng_mat(g.MSWS_RNG(2), 3, 3)
+    for radius in (1.0, (1.0, 2.0)):
+        lam, Vec = s.contour_block_SS(nep, U, V, radius=radius, N=1000, sigma=0.1, K=3)
+        assert np.linalg.norm(o.compute_Mlincomb(nep, lam[0], Vec[:, 0])) < np.sqrt(np.finfo(float).eps)

@@ -143,3 +143,18 @@ def test_iar_gun_short_run_matches_oracle():
     assert np.max(np.abs(a - b) / np.abs(b)) < 1e-8
     for l, q in zip(lam, Q.T):
         assert np.linalg.norm(o.compute_Mlincomb(onep, l, q)) / np.linalg.norm(q) < 1e-6 * abs(l)
+
+
+def test_contour_block_SS_dep0():
+    # test/contour_block_SS.jl:9-17 (circle and ellipse, n = 3, k = 3, K = 3)
+    A0, A1, tauv = g.dep0_matrices(3)
+    dnep = B200SPMF.from_nep(nepb200.DEP([A0, A1], tauv))
+    onep = o.nep_gallery("dep0", 3)
+    U, V = msws_probe(3, 3, seed=1), msws_probe(3, 3, seed=2)
+    for radius in (1.0, (1.0, 2.0)):
+        lam, Vec, Shat, mp = nepb200.contour_block_SS(dnep, U, V, radius=radius, N=1000, sigma=0.1, k=3, K=3, batch=250, return_moments=True)
+        lo, Veco, Shato, mpo = osol.contour_block_SS(onep, U, V, radius=radius, N=1000, sigma=0.1, K=3, return_moments=True)
+        assert np.linalg.norm(Shat - Shato) <= 1e-11 * np.linalg.norm(Shato)
+        assert mp == mpo
+        assert np.linalg.norm(o.compute_Mlincomb(onep, lam[0], Vec[:, 0])) < np.sqrt(np.finfo(float).eps)
+        assert max(min(abs(lam - x)) for x in lo) < 1e-8 * max(1.0, np.max(abs(lo)))
