@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(256) lu_permute_out_kernel(int n, int k, const
 }
 
 constexpr int SOLVE_BIG = 192;    // fronts with more update rows than this get several CTAs in the solves
-constexpr int SOLVE_CHUNK = 128;  // update rows per CTA for those
+constexpr int SOLVE_CHUNK = 64;   // update rows per CTA for those
 constexpr int SOLVE_TILE = 64;    // update rows staged in shared memory at a time
 
 // shared memory of the solve kernels: sy [np*k] | sT [np*SOLVE_TILE] | sX [SOLVE_TILE*k]

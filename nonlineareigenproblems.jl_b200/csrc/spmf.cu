@@ -428,18 +428,22 @@ static TileCfg default_cfg(int kt) {
     if (kt <= 1) return {1, 8, 1, 4};
     if (kt <= 2) return {2, 4, 1, 4};
     if (kt <= 4) return {4, 2, 1, 4};
-    if (kt <= 8) return {4, 2, 2, 4};
-    if (kt <= 16) return {4, 2, 4, 2};
-    if (kt <= 20) return {4, 2, 5, 2};
+    // multi-column shapes: measured on config C4 (profiles/r1_spmm_tile_sweep.txt): shallow unrolling wins, the kernel is
+    // occupancy / gather-latency bound rather than HBM bound once k*16 B rows are gathered through L1/L2
+    if (kt <= 8) return {4, 4, 2, 2};
+    if (kt <= 16) return {4, 2, 4, 1};
+    if (kt <= 20) return {4, 2, 5, 1};
     return {8, 1, 4, 4};
 }
 
 #define NEPB_TILE_LIST(X) \
-    X(1, 8, 1, 4) X(2, 4, 1, 4) X(4, 2, 1, 4) X(4, 2, 2, 4) X(4, 2, 4, 2) X(4, 2, 5, 2) X(8, 1, 4, 4)
+    X(1, 8, 1, 4) X(2, 4, 1, 4) X(4, 2, 1, 4) X(4, 4, 2, 2) X(4, 2, 4, 1) X(4, 2, 5, 1) X(8, 1, 4, 4)
 // extra shapes kept for on-device tuning of the benchmark case (p=4 real, SCALAR)
 #define NEPB_TUNE_LIST(X)                                                                              \
     X(1, 4, 1, 6) X(1, 8, 1, 3) X(1, 16, 1, 2) X(1, 32, 1, 1) X(1, 4, 1, 8) X(8, 1, 1, 4) X(8, 2, 1, 4) \
-    X(4, 4, 2, 2) X(8, 1, 1, 8) X(4, 1, 5, 4) X(4, 4, 5, 1) X(4, 2, 5, 4) X(8, 1, 3, 4) X(8, 2, 3, 2) X(2, 4, 10, 2)
+    X(8, 1, 1, 8) X(4, 1, 5, 4) X(4, 4, 5, 1) X(4, 2, 5, 4) X(8, 1, 3, 4) X(8, 2, 3, 2) X(2, 4, 10, 2) X(4, 2, 2, 4) X(4, 2, 4, 2) X(4, 2, 5, 2) \
+    X(2, 8, 4, 2) X(4, 4, 2, 4) X(4, 8, 2, 1) X(8, 4, 1, 2) X(4, 8, 2, 2) X(2, 16, 4, 1) X(4, 4, 2, 1) X(8, 4, 1, 1) \
+    X(4, 4, 5, 2) X(4, 8, 5, 1) X(2, 8, 10, 1) X(8, 4, 3, 1) X(8, 2, 3, 1) X(4, 8, 5, 2)
 
 template <int VW, bool CA, bool DIAG>
 static int launch_fused_vw(const nepb_spmf* h, TileCfg cfg, int kt, int ldv, int ldz, const double2* V, double2* Z,

@@ -14,9 +14,11 @@ dnep, mats, st = build_c4(grid)
 lib = _lib.lib
 peak, _ = load_peaks()
 coef = dnep.coefficients(0.3 + 0.2j)
-CFGS = ["1,8,1,4", "1,4,1,6", "1,8,1,3", "1,16,1,2", "1,32,1,1", "1,4,1,8", "2,4,1,4", "4,2,1,4", "8,1,1,4", "8,2,1,4", "4,2,2,4", "4,4,2,2", "8,1,1,8",
+CFGS = ["2,8,4,2", "4,4,2,4", "4,8,2,1", "8,4,1,2", "4,8,2,2", "2,16,4,1", "4,4,2,1", "8,4,1,1", "4,4,5,2", "4,8,5,1", "2,8,10,1", "4,2,5,1", "8,4,3,1", "8,2,3,1", "4,8,5,2",
+        "4,4,2,2", "4,2,2,4", "4,2,5,2", "4,4,5,1"]
+OLD = ["1,8,1,4", "1,4,1,6", "1,8,1,3", "1,16,1,2", "1,32,1,1", "1,4,1,8", "2,4,1,4", "4,2,1,4", "8,1,1,4", "8,2,1,4", "4,2,2,4", "4,4,2,2", "8,1,1,8",
         "4,2,4,2", "4,2,5,2", "4,1,5,4", "4,4,5,1", "4,2,5,4", "8,1,3,4", "8,2,3,2", "2,4,10,2", "8,1,4,4"]
-for k in (1, 8, 20):
+for k in (8, 20):
     V = synthetic.stencil_block(_lib.msws_state(1), dnep.n, k)
     Vb, Zb = Block.from_host(V), Block(dnep.n, k)
     nbytes = dnep.apply_bytes(0, k, k)
