@@ -1137,6 +1137,45 @@ int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev,
     return NEPB_OK;
 }
 
+// lu->sol = M(sigma_shift)^-1 lu->rhs for k right-hand sides.  The ~4 launches per tree level are captured once per
+// (shift, k) into a CUDA graph and replayed: the single-shift solve of iar / tiar / resinv is launch-bound otherwise.
+int lu_solve_staged(nepb_lu* lu, int shift, int k) {
+    static const bool use_graph = !(getenv("NEPB_SOLVE_GRAPH") && atoi(getenv("NEPB_SOLVE_GRAPH")) == 0);
+    int rc = lu_solve_reserve(lu, 1, k);
+    if (rc) return rc;
+    if (!use_graph) return lu_solve_device(lu, shift, 1, k, (const double2*)lu->rhs.p, 0, (double2*)lu->sol.p);
+    const auto key = std::make_pair(shift, k);
+    auto it = lu->solve_graphs.find(key);
+    if (it == lu->solve_graphs.end() || it->second.rhs != lu->rhs.p || it->second.sol != lu->sol.p) {
+        if (it != lu->solve_graphs.end()) {
+            cudaGraphExecDestroy(it->second.exec);
+            lu->solve_graphs.erase(it);
+        }
+        const int64_t l0 = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        NEPB_CUDA(cudaStreamBeginCapture(stream(), cudaStreamCaptureModeThreadLocal));
+        rc = lu_solve_device(lu, shift, 1, k, (const double2*)lu->rhs.p, 0, (double2*)lu->sol.p);
+        cudaError_t e = cudaStreamEndCapture(stream(), &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        NEPB_CUDA(e);
+        nepb_lu::SolveGraph g;
+        g.kernels = (int)(g_launches.load() - l0);
+        g_launches.fetch_sub(g.kernels);
+        g.rhs = lu->rhs.p;
+        g.sol = lu->sol.p;
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        NEPB_CUDA(e);
+        it = lu->solve_graphs.emplace(key, g).first;
+    }
+    NEPB_CUDA(cudaGraphLaunch(it->second.exec, stream()));
+    g_launches.fetch_add(it->second.kernels);
+    return NEPB_OK;
+}
+
 int spmf_apply_device(const nepb_spmf* h, int mode, int k, int q, const double2* dV, const double* C, double2* dZ);
 int upload_colmajor(int64_t n, int kc, const double* host, int64_t ld, DevBuf<double>& stage, double* dst, int ldd, int k0);
 int download_colmajor(int64_t n, int kc, const double* src, int lds, int k0, DevBuf<double>& stage, double* host, int64_t ld);
@@ -1327,7 +1366,7 @@ int nepb_lu_solve(nepb_lu* lu, int shift, int nrhs, const double* B, int64_t ldb
         NEPB_CUDA(lu->sol.reserve((size_t)2 * n * k));
         int rc = upload_colmajor(n, k, B + 2 * (size_t)c0 * ldb, ldb, lu->stage, lu->rhs.p, k, 0);
         if (rc) return rc;
-        rc = lu_solve_device(lu, shift, 1, k, (const double2*)lu->rhs.p, 0, (double2*)lu->sol.p);
+        rc = lu_solve_staged(lu, shift, k);
         if (rc) return rc;
         if (refine_steps > 0 || berr_out) {
             NEPB_CUDA(lu->res.reserve((size_t)2 * n * k));
@@ -1394,7 +1433,7 @@ int nepb_lu_solve_block(nepb_lu* lu, int shift, const nepb_block* B, int bcol0, 
     NEPB_CUDA(lu->sol.reserve((size_t)2 * n * nrhs));
     const unsigned gb = (unsigned)((n * nrhs + 255) / 256);
     NEPB_LAUNCH(cols_gather_kernel, gb, 256, 0, n, nrhs, (const double2*)B->d.p + bcol0, B->k, (double2*)lu->rhs.p);
-    int rc = lu_solve_device(lu, shift, 1, nrhs, (const double2*)lu->rhs.p, 0, (double2*)lu->sol.p);
+    int rc = lu_solve_staged(lu, shift, nrhs);
     if (rc) return rc;
     const double2 a = alpha ? make_double2(alpha[0], alpha[1]) : make_double2(1.0, 0.0);
     NEPB_LAUNCH(cols_scatter_kernel, gb, 256, 0, n, nrhs, (const double2*)lu->sol.p, (double2*)X->d.p + xcol0, X->k, a);

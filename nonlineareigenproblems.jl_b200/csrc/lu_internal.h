@@ -1,5 +1,7 @@
 // Internal layouts shared by lu.cu and contour.cu.
 #pragma once
+#include <map>
+#include <utility>
 #include <vector>
 
 #include "common.h"
@@ -76,6 +78,17 @@ struct nepb_lu {
     // scratch
     nepb::DevBuf<double> xp, w, part, rhs, sol, res, cor, stage;
     nepb::DevBuf<unsigned long long> colmax;
+    // captured single-shift solves, keyed by (shift, right-hand sides); valid while the staging buffers keep their address
+    struct SolveGraph {
+        cudaGraphExec_t exec = nullptr;
+        int kernels = 0;
+        const double* rhs = nullptr;
+        const double* sol = nullptr;
+    };
+    std::map<std::pair<int, int>, SolveGraph> solve_graphs;
+    ~nepb_lu() {
+        for (auto& kv : solve_graphs) cudaGraphExecDestroy(kv.second.exec);
+    }
 };
 
 namespace nepb {

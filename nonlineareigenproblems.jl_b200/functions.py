@@ -40,7 +40,9 @@ class ScalarFunction:
         out[0] = t[0]
         for j in range(1, k):
             prod = prod * s[j - 1]
-            out[j] = t[j] * prod
+            # a vanishing Taylor coefficient (polynomial terms beyond their degree) must give exactly zero even when the
+            # running product of the scalings has overflowed (gamma^j * j! for deep Krylov spaces)
+            out[j] = t[j] * prod if t[j] != 0 else 0.0
         return out
 
     def derivative(self, lam, j):
