@@ -449,7 +449,7 @@ __device__ __forceinline__ void red_sub_c(double2* addr, double2 v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(&addr->y), "d"(-v.y) : "memory");
 }
 
-constexpr int SCHUR_GROUP = 4;  // column tiles per item
+constexpr int SCHUR_GROUP = 2;  // column tiles per item
 __global__ void __launch_bounds__(256, 2) lu_schur_pipe_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts) {
     extern __shared__ double2 sm[];
     const int4 it = items[blockIdx.x];
