@@ -650,13 +650,10 @@ __device__ __forceinline__ void bwd_product(const double2* __restrict__ F, int l
 
 // forward: one CTA per (front, shift).  CK = right-hand-side columns held in registers per pass.
 template <int CK>
-__global__ void __launch_bounds__(256) lu_forward_kernel(LuDev d, const int* __restrict__ items, const double2* __restrict__ fronts,
-                                                         const int* __restrict__ piv, double2* __restrict__ Xp, double2* __restrict__ W, int k,
-                                                         int max_np) {
-    extern __shared__ double2 sy[];  // np x k pivot rows | L21 tile
+__device__ __forceinline__ void forward_front(const LuDev& d, int s, int b, const double2* __restrict__ fronts, const int* __restrict__ piv,
+                                              double2* __restrict__ Xp, double2* __restrict__ W, int k, int max_np, double2* sy,
+                                              bool update_all) {
     double2* sT = sy + (size_t)max_np * k;
-    const int s = items[blockIdx.x];
-    const int b = blockIdx.y;
     const int nf = d.nf[s], np = d.np[s], ncb = nf - np, ld = d.ld[s];
     const double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
     const int* pv = piv + (size_t)b * d.n + d.sn_ptr[s];
@@ -711,9 +708,33 @@ __global__ void __launch_bounds__(256) lu_forward_kernel(LuDev d, const int* __r
     }
     __syncthreads();
     for (int idx = tid; idx < np * k; idx += blockDim.x) Xb[(size_t)c0 * k + idx] = sy[idx];
-    // 4. update rows; big fronts leave this to lu_forward_update_kernel (several CTAs per front)
-    if (ncb > SOLVE_BIG) return;
+    // 4. update rows; big fronts leave this to lu_forward_update_kernel (several CTAs per front) unless the caller owns
+    //    the whole chain (lu_forward_chain_kernel)
+    if (ncb > SOLVE_BIG && !update_all) return;
     fwd_update_rows<CK>(F, ld, np, 0, ncb, sy, k, Ws, sT);
+}
+
+template <int CK>
+__global__ void __launch_bounds__(256) lu_forward_kernel(LuDev d, const int* __restrict__ items, const double2* __restrict__ fronts,
+                                                         const int* __restrict__ piv, double2* __restrict__ Xp, double2* __restrict__ W, int k,
+                                                         int max_np) {
+    extern __shared__ double2 sy[];  // np x k pivot rows | L21 tile | staging
+    forward_front<CK>(d, items[blockIdx.x], blockIdx.y, fronts, piv, Xp, W, k, max_np, sy, false);
+}
+
+// A chain of in-place fronts (the links of a split supernode, e.g. the dense root) handled by ONE CTA per shift: links 2..m
+// of the chain are walked inside the kernel, so m-1 levels cost one launch and no inter-CTA synchronisation.
+// item = (first index into chain_fronts, number of links)
+template <int CK>
+__global__ void __launch_bounds__(256) lu_forward_chain_kernel(LuDev d, const int2* __restrict__ items, const int* __restrict__ chain_fronts,
+                                                               const double2* __restrict__ fronts, const int* __restrict__ piv,
+                                                               double2* __restrict__ Xp, double2* __restrict__ W, int k, int max_np) {
+    extern __shared__ double2 sy[];
+    const int2 it = items[blockIdx.x];
+    for (int q = 0; q < it.y; ++q) {
+        forward_front<CK>(d, chain_fronts[it.x + q], blockIdx.y, fronts, piv, Xp, W, k, max_np, sy, true);
+        __syncthreads();  // the next link reads the work rows this one just updated
+    }
 }
 
 // forward, big fronts: item = (front s, first update row r0, end r1); W[np + r, :] -= L21[r, :] * y1 with y1 from Xp
@@ -757,21 +778,18 @@ __global__ void __launch_bounds__(128) lu_backward_partial_kernel(LuDev d, const
 
 // backward: x1 = U11^-1 (y1 - U12 x2), one CTA per (front, shift)
 template <int CK>
-__global__ void __launch_bounds__(256) lu_backward_kernel(LuDev d, const int* __restrict__ items, const double2* __restrict__ fronts,
-                                                          double2* __restrict__ Xp, const double2* __restrict__ part, int part_slots,
-                                                          int max_np, int k) {
-    extern __shared__ double2 sy[];
+__device__ __forceinline__ void backward_front(const LuDev& d, int s, int b, const double2* __restrict__ fronts, double2* __restrict__ Xp,
+                                               const double2* __restrict__ part, int part_slots, int max_np, int k, double2* sy,
+                                               bool product_here) {
     double2* sT = sy + (size_t)max_np * k;
     double2* sX = sT + (size_t)max_np * SOLVE_TILE;
-    const int s = items[blockIdx.x];
-    const int b = blockIdx.y;
     const int nf = d.nf[s], np = d.np[s], ncb = nf - np, ld = d.ld[s];
     const double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
     double2* Xb = Xp + (size_t)b * d.n * k;
     const int* rows = d.rows + d.row_ptr[s] + np;
     const int c0 = d.sn_ptr[s];
     const int tid = threadIdx.x;
-    if (ncb > SOLVE_BIG) {
+    if (ncb > SOLVE_BIG && !product_here) {
         // the products were formed by lu_backward_partial_kernel: subtract the partial sums slot after slot
         const int nslots = (ncb + SOLVE_CHUNK - 1) / SOLVE_CHUNK;
         const double2* pp = part + ((size_t)b * part_slots + d.bw_slot[s]) * (size_t)max_np * k;
@@ -804,6 +822,26 @@ __global__ void __launch_bounds__(256) lu_backward_kernel(LuDev d, const int* __
     }
     __syncthreads();
     for (int idx = tid; idx < np * k; idx += blockDim.x) Xb[(size_t)c0 * k + idx] = sy[idx];
+}
+
+template <int CK>
+__global__ void __launch_bounds__(256) lu_backward_kernel(LuDev d, const int* __restrict__ items, const double2* __restrict__ fronts,
+                                                          double2* __restrict__ Xp, const double2* __restrict__ part, int part_slots,
+                                                          int max_np, int k) {
+    extern __shared__ double2 sy[];
+    backward_front<CK>(d, items[blockIdx.x], blockIdx.y, fronts, Xp, part, part_slots, max_np, k, sy, false);
+}
+
+// the same chain, top-down: links m..2 inside one CTA per shift
+template <int CK>
+__global__ void __launch_bounds__(256) lu_backward_chain_kernel(LuDev d, const int2* __restrict__ items, const int* __restrict__ chain_fronts,
+                                                                const double2* __restrict__ fronts, double2* __restrict__ Xp, int max_np, int k) {
+    extern __shared__ double2 sy[];
+    const int2 it = items[blockIdx.x];
+    for (int q = it.y - 1; q >= 0; --q) {
+        backward_front<CK>(d, chain_fronts[it.x + q], blockIdx.y, fronts, Xp, nullptr, 0, max_np, k, sy, true);
+        __syncthreads();  // the next (lower) link gathers the solution rows written here
+    }
 }
 
 // S[j] += sum_b wgt[b*mg + j] * X[b]   (contour moments, method_contour_common.jl:86-90), elementwise n*k
@@ -907,6 +945,27 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     std::vector<int4> ea_items, pn_items, sc_items, sp_items, fu_items, bp_items;
     std::vector<int32_t> bw_slot(ns, 0);
     sd->part_slots = 0;
+    // chains of in-place fronts: the tail links (2..m) are walked by one CTA per shift in the solves
+    std::vector<char> in_tail(ns, 0);
+    std::vector<int32_t> chain_fronts, sfr_items;
+    std::vector<std::vector<int2>> fc_of_level(S.nlevels), bc_of_level(S.nlevels);
+    // measured on gun (profiles/): a single CTA per shift cannot stream a big chain's factors fast enough (16.0 -> 25.3 ms for
+    // 16 nodes), so the chain walk is opt-in (NEPB_LU_CHAINS=1) until it is double-buffered / cluster-wide
+    static const bool use_chains = getenv("NEPB_LU_CHAINS") && atoi(getenv("NEPB_LU_CHAINS")) != 0;
+    for (int s = 0; s < ns && use_chains; ++s) {
+        if (!S.in_place_child[s] || S.has_in_place_child[s]) continue;  // not the first link of a chain
+        const int first = (int)chain_fronts.size();
+        int cur = s;
+        while (S.in_place_child[cur]) {
+            cur = S.sn_parent[cur];
+            chain_fronts.push_back(cur);
+            in_tail[cur] = 1;
+        }
+        const int cnt = (int)chain_fronts.size() - first;
+        fc_of_level[S.level[chain_fronts[first]]].push_back(make_int2(first, cnt));
+        bc_of_level[S.level[chain_fronts[first + cnt - 1]]].push_back(make_int2(first, cnt));
+    }
+    std::vector<int2> fc_items, bc_items;
     for (int l = 0; l < S.nlevels; ++l) {
         auto& L = sd->lv[l];
         L.front_begin = (int)fr_items.size();
@@ -916,6 +975,13 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
         L.sp_begin = (int)sp_items.size();
         L.fu_begin = (int)fu_items.size();
         L.bp_begin = (int)bp_items.size();
+        L.sfr_begin = (int)sfr_items.size();
+        L.fc_begin = (int)fc_items.size();
+        L.bc_begin = (int)bc_items.size();
+        for (auto& x : fc_of_level[l]) fc_items.push_back(x);
+        for (auto& x : bc_of_level[l]) bc_items.push_back(x);
+        L.fc_count = (int)fc_items.size() - L.fc_begin;
+        L.bc_count = (int)bc_items.size() - L.bc_begin;
         int slots = 0;
         std::vector<int32_t> fl(S.level_list.begin() + S.level_ptr[l], S.level_list.begin() + S.level_ptr[l + 1]);
         std::stable_sort(fl.begin(), fl.end(), [&](int a, int b) { return nf[a] > nf[b]; });  // big fronts first
@@ -940,7 +1006,8 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
             for (int j0 = 0; j0 < ncb; j0 += SCHUR_T * SCHUR_GROUP)
                 for (int i0 = 0; i0 < ncb; i0 += SCHUR_T)
                     sp_items.push_back(make_int4(s, i0, j0, std::min(SCHUR_GROUP, (ncb - j0 + SCHUR_T - 1) / SCHUR_T)));
-            if (ncb > SOLVE_BIG) {
+            if (!in_tail[s]) sfr_items.push_back(s);
+            if (ncb > SOLVE_BIG && !in_tail[s]) {
                 bw_slot[s] = slots;
                 for (int r0 = 0; r0 < ncb; r0 += SOLVE_CHUNK) {
                     fu_items.push_back(make_int4(s, r0, std::min(ncb, r0 + SOLVE_CHUNK), 0));
@@ -950,6 +1017,7 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
         }
         sd->part_slots = std::max(sd->part_slots, slots);
         L.fu_count = (int)fu_items.size() - L.fu_begin;
+        L.sfr_count = (int)sfr_items.size() - L.sfr_begin;
         L.bp_count = (int)bp_items.size() - L.bp_begin;
         L.max_np = 1;
         for (int s2 : fl) L.max_np = std::max(L.max_np, (int)np[s2]);
@@ -985,6 +1053,10 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     UP(sd->fu_items, fu_items);
     UP(sd->bp_items, bp_items);
     UP(sd->bw_slot, bw_slot);
+    UP(sd->sfr_items, sfr_items);
+    UP(sd->chain_fronts, chain_fronts);
+    UP(sd->fc_items, fc_items);
+    UP(sd->bc_items, bc_items);
     UP(sd->has_ip, S.has_in_place_child);
 #undef UP
     if (e != cudaSuccess) {
@@ -1025,6 +1097,8 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     cudaFuncSetAttribute(lu_forward_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);       \
     cudaFuncSetAttribute(lu_backward_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);       \
     cudaFuncSetAttribute(lu_forward_update_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+    cudaFuncSetAttribute(lu_forward_chain_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  \
+    cudaFuncSetAttribute(lu_backward_chain_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
     cudaFuncSetAttribute(lu_backward_partial_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     NEPB_SOLVE_ATTR(1) NEPB_SOLVE_ATTR(4) NEPB_SOLVE_ATTR(8) NEPB_SOLVE_ATTR(10) NEPB_SOLVE_ATTR(16)
 #undef NEPB_SOLVE_ATTR
@@ -1108,20 +1182,28 @@ int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev,
         for (int l = 0; l < S.nlevels; ++l) {                                                                                             \
             const auto& L = sd->lv[l];                                                                                                    \
             const size_t sml = solve_smem_bytes(L.max_np, k);                                                                             \
-            NEPB_LAUNCH((lu_forward_kernel<CK_>), dim3(L.front_count, nb), 256, sml, sd->dev, sd->fr_items.p + L.front_begin, F, piv, Xp,  \
-                        W, k, L.max_np);                                                                                                  \
+            if (L.sfr_count)                                                                                                              \
+                NEPB_LAUNCH((lu_forward_kernel<CK_>), dim3(L.sfr_count, nb), 256, sml, sd->dev, sd->sfr_items.p + L.sfr_begin, F, piv, Xp, \
+                            W, k, L.max_np);                                                                                              \
             if (L.fu_count)                                                                                                               \
                 NEPB_LAUNCH((lu_forward_update_kernel<CK_>), dim3(L.fu_count, nb), 128, sml, sd->dev, sd->fu_items.p + L.fu_begin, F,      \
                             (const double2*)Xp, W, k, L.max_np);                                                                          \
+            if (L.fc_count)                                                                                                               \
+                NEPB_LAUNCH((lu_forward_chain_kernel<CK_>), dim3(L.fc_count, nb), 256, smem, sd->dev, sd->fc_items.p + L.fc_begin,         \
+                            sd->chain_fronts.p, F, piv, Xp, W, k, S.max_np);                                                              \
         }                                                                                                                                 \
         for (int l = S.nlevels - 1; l >= 0; --l) {                                                                                        \
             const auto& L = sd->lv[l];                                                                                                    \
             const size_t sml = solve_smem_bytes(L.max_np, k);                                                                             \
+            if (L.bc_count)                                                                                                               \
+                NEPB_LAUNCH((lu_backward_chain_kernel<CK_>), dim3(L.bc_count, nb), 256, smem, sd->dev, sd->bc_items.p + L.bc_begin,        \
+                            sd->chain_fronts.p, F, Xp, S.max_np, k);                                                                      \
             if (L.bp_count)                                                                                                               \
                 NEPB_LAUNCH((lu_backward_partial_kernel<CK_>), dim3(L.bp_count, nb), 128, sml, sd->dev, sd->bp_items.p + L.bp_begin, F,    \
                             (const double2*)Xp, part, sd->part_slots, L.max_np, k);                                                       \
-            NEPB_LAUNCH((lu_backward_kernel<CK_>), dim3(L.front_count, nb), 256, sml, sd->dev, sd->fr_items.p + L.front_begin, F, Xp,      \
-                        (const double2*)part, sd->part_slots, L.max_np, k);                                                               \
+            if (L.sfr_count)                                                                                                              \
+                NEPB_LAUNCH((lu_backward_kernel<CK_>), dim3(L.sfr_count, nb), 256, sml, sd->dev, sd->sfr_items.p + L.sfr_begin, F, Xp,     \
+                            (const double2*)part, sd->part_slots, L.max_np, k);                                                           \
         }                                                                                                                                 \
     } while (0)
     NEPB_CUDA(lu->part.reserve((size_t)2 * nb * std::max(sd->part_slots, 1) * S.max_np * k));

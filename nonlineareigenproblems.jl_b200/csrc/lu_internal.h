@@ -44,6 +44,9 @@ struct LuLevel {
     int sp_begin = 0, sp_count = 0;  // pipelined schur items
     int fu_begin = 0, fu_count = 0;  // forward update items (big fronts)
     int bp_begin = 0, bp_count = 0;  // backward partial-product items (big fronts)
+    int sfr_begin = 0, sfr_count = 0;  // fronts handled per level in the solves (chain tails excluded)
+    int fc_begin = 0, fc_count = 0;    // chains whose tail starts at this level (forward)
+    int bc_begin = 0, bc_count = 0;    // chains whose tail ends at this level (backward)
 };
 
 struct LuSymbolicDev {
@@ -52,7 +55,8 @@ struct LuSymbolicDev {
     std::vector<LuLevel> lv;
     DevBuf<int64_t> front_off, row_ptr, rel_ptr, w_off, a_pos;
     DevBuf<uint8_t> in_place, has_ip;
-    DevBuf<int32_t> bw_slot;
+    DevBuf<int32_t> bw_slot, sfr_items, chain_fronts;
+    DevBuf<int2> fc_items, bc_items;
     int part_slots = 0;
     DevBuf<int32_t> nf, np, ld, rows, rel, sn_ptr, child_ptr, child_list, perm, iperm, fr_items;
     DevBuf<int4> ea_items, pn_items, sc_items, sp_items, fu_items, bp_items;
