@@ -144,6 +144,8 @@ int nepb_comm_allreduce_sum_dev(void* dev_ptr, int64_t count) {
 // One group = one stream + one batched factorisation workspace + its own moment accumulator.
 struct ContourGroup {
     cudaStream_t st = nullptr;
+    cudaStream_t side = nullptr;      // forward substitution runs here, beside the factorisation (lu_factor_solve_pipelined)
+    std::vector<cudaEvent_t> ev;      // fork / per-level / join events of that pipeline
     cudaEvent_t done = nullptr;
     nepb_lu* lu = nullptr;
     DevBuf<double> x, s, wgt;
@@ -160,6 +162,8 @@ struct ContourGroup {
         if (h_info) cudaFreeHost(h_info);
         delete lu;
         if (done) cudaEventDestroy(done);
+        for (auto e : ev) cudaEventDestroy(e);
+        if (side) cudaStreamDestroy(side);
         if (st) cudaStreamDestroy(st);
     }
 };
@@ -213,6 +217,12 @@ int nepb_contour_create(const nepb_spmf* h, int k, int mg, int batch, nepb_conto
         if (G->cap == 0) G->cap = 1;
         e = cudaStreamCreateWithFlags(&G->st, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&G->done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&G->side, cudaStreamNonBlocking);
+        for (int i = 0; i < sd->S.nlevels + 2 && e == cudaSuccess; ++i) {
+            cudaEvent_t x = nullptr;
+            e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+            if (e == cudaSuccess) G->ev.push_back(x);
+        }
         nepb_lu* lu = new nepb_lu();
         G->lu = lu;
         lu->op = h;
@@ -253,10 +263,17 @@ static int contour_group_enqueue(nepb_contour* c, ContourGroup* G, int cnt) {
     G->lu->nb = cnt;
     NEPB_CUDA(cudaMemcpyAsync(G->lu->coef.p, G->h_coef, sizeof(double) * 2 * cnt * h->p, cudaMemcpyHostToDevice, G->st));
     NEPB_CUDA(cudaMemcpyAsync(G->wgt.p, G->h_wgt, sizeof(double) * 2 * cnt * c->mg, cudaMemcpyHostToDevice, G->st));
-    int rc = lu_factor_device(G->lu);
-    if (rc) return rc;
-    rc = lu_solve_device(G->lu, 0, cnt, c->k, (const double2*)c->vh.p, 0, (double2*)G->x.p);
-    if (rc) return rc;
+    static const bool pipelined = !(getenv("NEPB_CONTOUR_PIPELINE") && atoi(getenv("NEPB_CONTOUR_PIPELINE")) == 0);
+    int rc;
+    if (pipelined) {
+        rc = lu_factor_solve_pipelined(G->lu, c->k, (const double2*)c->vh.p, 0, (double2*)G->x.p, G->side, G->ev.data());
+        if (rc) return rc;
+    } else {
+        rc = lu_factor_device(G->lu);
+        if (rc) return rc;
+        rc = lu_solve_device(G->lu, 0, cnt, c->k, (const double2*)c->vh.p, 0, (double2*)G->x.p);
+        if (rc) return rc;
+    }
     NEPB_LAUNCH(contour_accumulate_kernel, (unsigned)((nk + 255) / 256), 256, 0, nk, cnt, c->mg, (const double2*)G->x.p, nk,
                 (const double2*)G->wgt.p, (double2*)G->s.p);
     NEPB_LAUNCH_CHECK();

@@ -128,22 +128,30 @@ __global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev d, const int4*
 
 // ---------------------------------------------------------------------------------------------
 // diag: partial-pivoted LU of the (at most 32 x 32) pivot block AND the explicit inverses of its triangular factors.
-// One CTA of 4 warps per (front, shift): lane = row, warp w owns columns 8w..8w+7 in registers.  One block barrier per
-// elimination step (pivot row index + multiplier column go through double-buffered shared memory), row exchanges and
-// the rank-1 update use shuffles.  The inverses turn every later triangular solve with this block (panel, forward,
-// backward) into a small dense product without a sequential dependency chain.
+// One CTA of 4 warps per (front, shift).  Both phases are short rolled loops (the kernel sits on the critical path of
+// every tree level, and straight-line code of this size is bound by instruction fetch, not by arithmetic).
+//   LU phase   lane = physical row (rows are never exchanged: a row remembers the step at which it became the pivot
+//              row); warp w owns the columns w, w+4, ... in a register window whose first entry is always its next
+//              column to eliminate (the window is rotated after use, so all register indices are static).  Per step:
+//              the owner warp picks the pivot with one redux.max over float-rounded magnitudes + ballot (threshold 0.1
+//              in favour of row j), forms the multipliers and publishes them through double-buffered shared memory;
+//              one block barrier; every warp applies the rank-1 update to its remaining columns with the pivot row
+//              broadcast by shuffles.
+//   inverses   warp 0: inv(L11), warp 1: inv(U11); lane = column of the inverse, right-looking substitution on a
+//              rotating register window; factor entries are shared-memory broadcasts.  No inter-lane dependency.
+// The inverses turn every later triangular solve with this block (panel, forward, backward) into a small dense product.
 // Output in place of F11: strict lower part = inv(L11) (unit diagonal implied), upper part = inv(U11);
-// piv[t] = original row (within the block) that ended up in position t.
+// piv[t] = original row (within the block) that became pivot row t.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double2 shfl_c(double2 v, int src) {
     return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
 }
 
-constexpr int DNP = 32, DCW = 8;
+constexpr int DNP = 32, DCW = 8, DNW = 4;
 __global__ void __launch_bounds__(128) lu_diag_inv_kernel(LuDev d, const int* __restrict__ items, double2* __restrict__ fronts,
                                                           int* __restrict__ piv, LuInfo* __restrict__ info) {
     __shared__ double2 s_l[2][DNP];
-    __shared__ int s_bi[2];
+    __shared__ int s_p[2];
     __shared__ double2 s_rp[DNP];
     __shared__ double2 s_LU[DNP][DNP + 1];  // s_LU[c][r] = (L\U)[r][c]
     const int s = items[blockIdx.x];
@@ -152,48 +160,34 @@ __global__ void __launch_bounds__(128) lu_diag_inv_kernel(LuDev d, const int* __
     double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
     int* pv = piv + (size_t)b * d.n + d.sn_ptr[s];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double2 a[DCW];
+    double2 a[DCW];  // window over the columns w, w+4, ..: a[0] is the next column this warp eliminates
 #pragma unroll
     for (int c = 0; c < DCW; ++c) {
-        const int cg = DCW * w + c;
+        const int cg = DNW * c + w;
         a[c] = (lane < np && cg < np) ? F[(size_t)lane + (size_t)cg * ld] : make_double2(lane == cg ? 1.0 : 0.0, 0.0);
     }
+    if (w == 0) s_rp[lane] = make_double2(1.0, 0.0);
     const double amax = __longlong_as_double(info[b].amax_bits);
     const double tiny = 2.220446049250313e-16 * amax;
     double minpiv = INFINITY;
-    int nperturbed = 0, flags = 0, orig = lane;
+    int nperturbed = 0, flags = 0;
+    int pos = (lane < np) ? -1 : lane;  // step at which this row became the pivot row
 #pragma unroll 1
     for (int j = 0; j < np; ++j) {
-        const int wo = j >> 3, jl = j & 7, par = j & 1;
-        if (w == wo) {  // warp-uniform: the owner of column j finds the pivot, exchanges its rows and forms the multipliers
+        const int par = j & 1, owner = j & (DNW - 1);
+        if (w == owner) {  // warp-uniform: the owner of column j picks the pivot row and forms the multipliers
             double2 aj = a[0];
-#pragma unroll
-            for (int c = 1; c < DCW; ++c)
-                if (c == jl) aj = a[c];
             const double mine = cabs1(aj);
-            double best = (lane >= j && lane < np) ? ((mine == mine) ? mine : INFINITY) : -1.0;
-            int bi = lane;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-            }
-            const double dj = __shfl_sync(0xffffffffu, mine, j);
-            if (dj >= 0.1 * best && dj == dj) bi = j;  // threshold pivoting that prefers the diagonal
-            if (bi != j) {
-                const int src = (lane == j) ? bi : j;
-#pragma unroll
-                for (int c = 0; c < DCW; ++c) {
-                    const double2 o = shfl_c(a[c], src);
-                    if (lane == j || lane == bi) a[c] = o;
-                }
-                const double2 o = shfl_c(aj, src);
-                if (lane == j || lane == bi) aj = o;
-            }
-            double2 pvt = shfl_c(aj, j);
+            const bool cand = pos < 0;
+            const float mf = (mine == mine) ? (float)mine : INFINITY;
+            const unsigned key = cand ? __float_as_uint(mf) + 1u : 0u;  // non-negative floats order like their bit patterns
+            const unsigned best = __reduce_max_sync(0xffffffffu, key);
+            int bi = __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;
+            const unsigned kj = __shfl_sync(0xffffffffu, key, j);
+            if (kj != 0u && __uint_as_float(kj - 1u) >= 0.1f * __uint_as_float(best - 1u)) bi = j;  // prefer the diagonal
+            double2 pvt = shfl_c(aj, bi);
             const double pa = cabs1(pvt);
-            if (!(pa <= 1.79e308) || !(best <= 1.79e308)) {
+            if (!(pa <= 1.79e308)) {
                 flags |= 2;
                 pvt = make_double2(1.0, 0.0);
             } else if (pa == 0.0) {
@@ -207,78 +201,74 @@ __global__ void __launch_bounds__(128) lu_diag_inv_kernel(LuDev d, const int* __
             }
             minpiv = fmin(minpiv, pa);
             const double2 rp = crecip(pvt);
-            if (lane == j) aj = pvt;
-            if (lane > j) aj = cmul(aj, rp);
-#pragma unroll
-            for (int c = 0; c < DCW; ++c)
-                if (c == jl) a[c] = aj;
-            s_l[par][lane] = (lane > j && lane < np) ? aj : make_double2(0.0, 0.0);
+            double2 l = make_double2(0.0, 0.0);
+            if (lane == bi) {
+                aj = pvt;
+                pos = j;
+            } else if (cand) {
+                l = cmul(aj, rp);
+                aj = l;
+            }
+            s_LU[j][lane] = aj;  // column j is final: multipliers below the pivot, U entries in the rows chosen earlier
+            s_l[par][lane] = l;
             if (lane == 0) {
-                s_bi[par] = bi;
+                s_p[par] = bi;
                 s_rp[j] = rp;
             }
+#pragma unroll
+            for (int c = 0; c < DCW - 1; ++c) a[c] = a[c + 1];
         }
         __syncthreads();
-        const int bi = s_bi[par];
-        if (bi != j) {
-            if (w != wo) {
-                const int src = (lane == j) ? bi : j;
-#pragma unroll
-                for (int c = 0; c < DCW; ++c) {
-                    const double2 o = shfl_c(a[c], src);
-                    if (lane == j || lane == bi) a[c] = o;
-                }
-            }
-            const int oo = __shfl_sync(0xffffffffu, orig, (lane == j) ? bi : j);
-            if (lane == j || lane == bi) orig = oo;
-        }
-        const double2 l = s_l[par][lane];
+        const int p = s_p[par];
+        const double2 l = s_l[par][lane];  // zero for the pivot row and for rows that became pivot rows earlier
+        if (w != owner && lane == p) pos = j;
+        const int first = (j & ~(DNW - 1)) + w + (w > owner ? 0 : DNW);  // first column of this warp beyond j
+        const int rem = (np - first + DNW - 1) / DNW;                    // its columns below np
 #pragma unroll
         for (int c = 0; c < DCW; ++c) {
-            if (DCW * w + c > j) {  // warp-uniform
-                const double2 rj = shfl_c(a[c], j);
-                if (lane > j) cfms(a[c], l, rj);
+            if (c < rem) {  // warp-uniform
+                const double2 rj = shfl_c(a[c], p);
+                cfms(a[c], l, rj);
             }
         }
     }
-#pragma unroll
-    for (int c = 0; c < DCW; ++c) s_LU[DCW * w + c][lane] = a[c];
     __syncthreads();
-    // inv(L11): forward elimination applied to the identity; inv(U11): backward.  Shared memory is read-only here.
-    double2 xl[DCW], xu[DCW];
+    {  // rows into pivot order
+        double2 tmp[DCW];
 #pragma unroll
-    for (int c = 0; c < DCW; ++c) xl[c] = xu[c] = make_double2(lane == DCW * w + c ? 1.0 : 0.0, 0.0);
-#pragma unroll 1
-    for (int j = 0; j < np - 1; ++j) {
-        const double2 l = s_LU[j][lane];
+        for (int c = 0; c < DCW; ++c) tmp[c] = s_LU[DNW * c + w][lane];
+        __syncthreads();
 #pragma unroll
-        for (int c = 0; c < DCW; ++c) {
-            if (DCW * w + c <= j) {
-                const double2 xj = shfl_c(xl[c], j);
-                if (lane > j && lane < np) cfms(xl[c], l, xj);
-            }
-        }
+        for (int c = 0; c < DCW; ++c) s_LU[DNW * c + w][pos] = tmp[c];
+        if (w == 0 && lane < np) pv[pos] = lane;
+        __syncthreads();
     }
+    if (w < 2) {
+        // w = 0: column `lane` of inv(L11): x = e_lane; for t = 0, 1, ..: x_i -= L[i][t] x_t (i > t)
+        // w = 1: column `lane` of inv(U11): for t = np-1, ..: x_t *= 1/u_tt; x_i -= U[i][t] x_t (i < t)
+        // y[m] = x[t + m] (w = 0) or x[t - m] (w = 1): the window moves with t, so y[0] is always the entry being finished
+        const bool up = (w == 1);
+        double2 y[DNP];
+#pragma unroll
+        for (int m = 0; m < DNP; ++m) y[m] = make_double2((up ? np - 1 - m : m) == lane ? 1.0 : 0.0, 0.0);
 #pragma unroll 1
-    for (int j = np - 1; j >= 0; --j) {
-        const double2 rp = s_rp[j];
-        const double2 u = s_LU[j][lane];
+        for (int q = 0; q < np; ++q) {
+            const int t = up ? np - 1 - q : q;
+            double2 xt = y[0];
+            if (up) xt = cmul(xt, s_rp[t]);
+            if (lane < np && (up ? t <= lane : t > lane)) F[(size_t)t + (size_t)lane * ld] = xt;
+            const double2* row = &s_LU[t][0];
 #pragma unroll
-        for (int c = 0; c < DCW; ++c) {
-            if (DCW * w + c >= j) {
-                if (lane == j) xu[c] = cmul(xu[c], rp);
-                const double2 xj = shfl_c(xu[c], j);
-                if (lane < j) cfms(xu[c], u, xj);
+            for (int m = 1; m < DNP; ++m) {
+                const int i = up ? t - m : t + m;
+                double2 f = make_double2(0.0, 0.0);
+                if (i >= 0 && i < DNP) f = row[i];  // warp-uniform
+                double2 r = y[m];
+                cfms(r, f, xt);
+                y[m - 1] = r;
             }
+            y[DNP - 1] = make_double2(0.0, 0.0);
         }
-    }
-    if (lane < np) {
-#pragma unroll
-        for (int c = 0; c < DCW; ++c) {
-            const int cg = DCW * w + c;
-            if (cg < np) F[(size_t)lane + (size_t)cg * ld] = (cg >= lane) ? xu[c] : xl[c];
-        }
-        if (w == 0) pv[lane] = orig;
     }
     if (lane == 0) {
         if (flags) atomicOr(&info[b].flags, flags);
@@ -1120,28 +1110,48 @@ __global__ void lu_info_init_kernel(int nb, LuInfo* __restrict__ info) {
 
 // numeric factorisation of lu->nb shifts into lu->fronts (coefficients already on the device); device work only, so the
 // sequence can be captured into a CUDA graph
-int lu_factor_device(nepb_lu* lu) {
+static int factor_prologue(nepb_lu* lu) {
     const nepb_spmf* h = lu->op;
     LuSymbolicDev* sd = lu->sym;
     const LuSymbolic& S = sd->S;
     const int nb = lu->nb;
     NEPB_CUDA(cudaMemsetAsync(lu->fronts.p, 0, sizeof(double) * 2 * (size_t)nb * S.front_total, stream()));
     NEPB_LAUNCH(lu_info_init_kernel, (nb + 127) / 128, 128, 0, nb, lu->info.p);
-    {
-        dim3 grid((unsigned)((h->nnz + 255) / 256), nb);
-        NEPB_LAUNCH(lu_assemble_kernel, grid, 256, 0, h->nnz, h->p, h->is_complex, sd->a_pos.p, h->d_vals.p, (const double2*)lu->coef.p,
-                    (double2*)lu->fronts.p, S.front_total, lu->info.p);
-    }
+    dim3 grid((unsigned)((h->nnz + 255) / 256), nb);
+    NEPB_LAUNCH(lu_assemble_kernel, grid, 256, 0, h->nnz, h->p, h->is_complex, sd->a_pos.p, h->d_vals.p, (const double2*)lu->coef.p,
+                (double2*)lu->fronts.p, S.front_total, lu->info.p);
+    return NEPB_OK;
+}
+
+// level l up to the panels: after this the factors L, U of the level's fronts are final (the Schur update only touches
+// the contribution blocks)
+static void factor_level_panels(nepb_lu* lu, int l) {
+    LuSymbolicDev* sd = lu->sym;
+    const int nb = lu->nb;
     double2* F = (double2*)lu->fronts.p;
-    for (int l = 0; l < S.nlevels; ++l) {
-        const auto& L = sd->lv[l];
-        if (L.ea_count) NEPB_LAUNCH(lu_extend_add_kernel, dim3(L.ea_count, nb), 256, 0, sd->dev, sd->ea_items.p + L.ea_begin, F);
-        NEPB_LAUNCH(lu_diag_inv_kernel, dim3(L.front_count, nb), 128, 0, sd->dev, sd->fr_items.p + L.front_begin, F, lu->piv.p, lu->info.p);
-        if (L.pn_count) NEPB_LAUNCH(lu_panel_inv_kernel, dim3(L.pn_count, nb), 256, PANEL_SMEM, sd->dev, sd->pn_items.p + L.pn_begin, F, lu->piv.p);
-        if (L.sc_count && sd->schur_pipe)
-            NEPB_LAUNCH(lu_schur_pipe_kernel, dim3(L.sp_count, nb), 256, sd->smem_schur_pipe, sd->dev, sd->sp_items.p + L.sp_begin, F);
-        else if (L.sc_count)
-            NEPB_LAUNCH(lu_schur_kernel, dim3(L.sc_count, nb), 256, sd->smem_schur, sd->dev, sd->sc_items.p + L.sc_begin, F);
+    const auto& L = sd->lv[l];
+    if (L.ea_count) NEPB_LAUNCH(lu_extend_add_kernel, dim3(L.ea_count, nb), 256, 0, sd->dev, sd->ea_items.p + L.ea_begin, F);
+    NEPB_LAUNCH(lu_diag_inv_kernel, dim3(L.front_count, nb), 128, 0, sd->dev, sd->fr_items.p + L.front_begin, F, lu->piv.p, lu->info.p);
+    if (L.pn_count) NEPB_LAUNCH(lu_panel_inv_kernel, dim3(L.pn_count, nb), 256, PANEL_SMEM, sd->dev, sd->pn_items.p + L.pn_begin, F, lu->piv.p);
+}
+
+static void factor_level_schur(nepb_lu* lu, int l) {
+    LuSymbolicDev* sd = lu->sym;
+    const int nb = lu->nb;
+    double2* F = (double2*)lu->fronts.p;
+    const auto& L = sd->lv[l];
+    if (L.sc_count && sd->schur_pipe)
+        NEPB_LAUNCH(lu_schur_pipe_kernel, dim3(L.sp_count, nb), 256, sd->smem_schur_pipe, sd->dev, sd->sp_items.p + L.sp_begin, F);
+    else if (L.sc_count)
+        NEPB_LAUNCH(lu_schur_kernel, dim3(L.sc_count, nb), 256, sd->smem_schur, sd->dev, sd->sc_items.p + L.sc_begin, F);
+}
+
+int lu_factor_device(nepb_lu* lu) {
+    int rc = factor_prologue(lu);
+    if (rc) return rc;
+    for (int l = 0; l < lu->sym->S.nlevels; ++l) {
+        factor_level_panels(lu, l);
+        factor_level_schur(lu, l);
     }
     NEPB_LAUNCH_CHECK();
     return NEPB_OK;
@@ -1159,62 +1169,138 @@ int lu_solve_reserve(nepb_lu* lu, int nb, int k) {
     return NEPB_OK;
 }
 
-int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev, size_t rhs_stride, double2* Xdev) {
+// The solve walks the tree level by level: forward bottom-up, backward top-down.  Shared memory is carved with the level's
+// own largest pivot block: the many small fronts at the bottom of the tree then fit more CTAs per SM.
+struct SolveCtx {
+    LuSymbolicDev* sd;
+    int nb, k;
+    const double2* F;
+    const int* piv;
+    double2 *Xp, *W, *part;
+    size_t smem;
+};
+
+template <int CK>
+static void solve_forward_level(const SolveCtx& c, int l) {
+    LuSymbolicDev* sd = c.sd;
+    const auto& L = sd->lv[l];
+    const size_t sml = solve_smem_bytes(L.max_np, c.k);
+    if (L.sfr_count)
+        NEPB_LAUNCH((lu_forward_kernel<CK>), dim3(L.sfr_count, c.nb), 256, sml, sd->dev, sd->sfr_items.p + L.sfr_begin, c.F, c.piv, c.Xp, c.W, c.k,
+                    L.max_np);
+    if (L.fu_count)
+        NEPB_LAUNCH((lu_forward_update_kernel<CK>), dim3(L.fu_count, c.nb), 128, sml, sd->dev, sd->fu_items.p + L.fu_begin, c.F,
+                    (const double2*)c.Xp, c.W, c.k, L.max_np);
+    if (L.fc_count)
+        NEPB_LAUNCH((lu_forward_chain_kernel<CK>), dim3(L.fc_count, c.nb), 256, c.smem, sd->dev, sd->fc_items.p + L.fc_begin, sd->chain_fronts.p,
+                    c.F, c.piv, c.Xp, c.W, c.k, sd->S.max_np);
+}
+
+template <int CK>
+static void solve_backward_level(const SolveCtx& c, int l) {
+    LuSymbolicDev* sd = c.sd;
+    const auto& L = sd->lv[l];
+    const size_t sml = solve_smem_bytes(L.max_np, c.k);
+    if (L.bc_count)
+        NEPB_LAUNCH((lu_backward_chain_kernel<CK>), dim3(L.bc_count, c.nb), 256, c.smem, sd->dev, sd->bc_items.p + L.bc_begin, sd->chain_fronts.p,
+                    c.F, c.Xp, sd->S.max_np, c.k);
+    if (L.bp_count)
+        NEPB_LAUNCH((lu_backward_partial_kernel<CK>), dim3(L.bp_count, c.nb), 128, sml, sd->dev, sd->bp_items.p + L.bp_begin, c.F,
+                    (const double2*)c.Xp, c.part, sd->part_slots, L.max_np, c.k);
+    if (L.sfr_count)
+        NEPB_LAUNCH((lu_backward_kernel<CK>), dim3(L.sfr_count, c.nb), 256, sml, sd->dev, sd->sfr_items.p + L.sfr_begin, c.F, c.Xp,
+                    (const double2*)c.part, sd->part_slots, L.max_np, c.k);
+}
+
+// right-hand-side columns held in registers per pass
+static int solve_ck(int k) { return k == 1 ? 1 : k <= 4 ? 4 : k <= 8 ? 8 : (k <= 10 || (k > 16 && k <= 20)) ? 10 : 16; }
+static void solve_forward_level(const SolveCtx& c, int l) {
+    switch (solve_ck(c.k)) {
+        case 1: solve_forward_level<1>(c, l); break;
+        case 4: solve_forward_level<4>(c, l); break;
+        case 8: solve_forward_level<8>(c, l); break;
+        case 10: solve_forward_level<10>(c, l); break;
+        default: solve_forward_level<16>(c, l); break;
+    }
+}
+static void solve_backward_level(const SolveCtx& c, int l) {
+    switch (solve_ck(c.k)) {
+        case 1: solve_backward_level<1>(c, l); break;
+        case 4: solve_backward_level<4>(c, l); break;
+        case 8: solve_backward_level<8>(c, l); break;
+        case 10: solve_backward_level<10>(c, l); break;
+        default: solve_backward_level<16>(c, l); break;
+    }
+}
+
+static int solve_ctx(nepb_lu* lu, int shift0, int nb, int k, SolveCtx* c) {
     LuSymbolicDev* sd = lu->sym;
     const LuSymbolic& S = sd->S;
-    const int n = S.n;
     NEPB_CHECK_ARG(shift0 >= 0 && nb >= 1 && shift0 + nb <= lu->nb, "shift window out of range");
     NEPB_CHECK_ARG(k >= 1 && k <= 256, "number of right-hand sides per solve must be in 1..256 (k=%d)", k);
     const size_t smem = solve_smem_bytes(S.max_np, k);
     NEPB_CHECK_ARG(smem <= 200 * 1024, "k=%d right-hand sides with %d pivot columns per front exceed shared memory", k, S.max_np);
-    NEPB_CUDA(lu->xp.reserve((size_t)2 * nb * n * k));
-    NEPB_CUDA(lu->w.reserve((size_t)2 * nb * S.w_total * k));
-    double2* Xp = (double2*)lu->xp.p;
-    double2* W = (double2*)lu->w.p;
-    const double2* F = (const double2*)lu->fronts.p + (size_t)shift0 * S.front_total;
-    const int* piv = lu->piv.p + (size_t)shift0 * n;
+    int rc = lu_solve_reserve(lu, nb, k);
+    if (rc) return rc;
+    c->sd = sd;
+    c->nb = nb;
+    c->k = k;
+    c->F = (const double2*)lu->fronts.p + (size_t)shift0 * S.front_total;
+    c->piv = lu->piv.p + (size_t)shift0 * S.n;
+    c->Xp = (double2*)lu->xp.p;
+    c->W = (double2*)lu->w.p;
+    c->part = (double2*)lu->part.p;
+    c->smem = smem;
+    return NEPB_OK;
+}
+
+int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev, size_t rhs_stride, double2* Xdev) {
+    SolveCtx c;
+    int rc = solve_ctx(lu, shift0, nb, k, &c);
+    if (rc) return rc;
+    const int n = c.sd->S.n, nlev = c.sd->S.nlevels;
     dim3 pg((unsigned)(((size_t)n * k + 255) / 256), nb);
-    NEPB_LAUNCH(lu_permute_in_kernel, pg, 256, 0, n, k, sd->perm.p, Bdev, rhs_stride, Xp);
-    // shared memory is carved with the level's own largest pivot block: the many small fronts at the bottom of the tree
-    // then fit more CTAs per SM
-#define NEPB_SOLVE_LEVELS(CK_)                                                                                                           \
-    do {                                                                                                                                  \
-        for (int l = 0; l < S.nlevels; ++l) {                                                                                             \
-            const auto& L = sd->lv[l];                                                                                                    \
-            const size_t sml = solve_smem_bytes(L.max_np, k);                                                                             \
-            if (L.sfr_count)                                                                                                              \
-                NEPB_LAUNCH((lu_forward_kernel<CK_>), dim3(L.sfr_count, nb), 256, sml, sd->dev, sd->sfr_items.p + L.sfr_begin, F, piv, Xp, \
-                            W, k, L.max_np);                                                                                              \
-            if (L.fu_count)                                                                                                               \
-                NEPB_LAUNCH((lu_forward_update_kernel<CK_>), dim3(L.fu_count, nb), 128, sml, sd->dev, sd->fu_items.p + L.fu_begin, F,      \
-                            (const double2*)Xp, W, k, L.max_np);                                                                          \
-            if (L.fc_count)                                                                                                               \
-                NEPB_LAUNCH((lu_forward_chain_kernel<CK_>), dim3(L.fc_count, nb), 256, smem, sd->dev, sd->fc_items.p + L.fc_begin,         \
-                            sd->chain_fronts.p, F, piv, Xp, W, k, S.max_np);                                                              \
-        }                                                                                                                                 \
-        for (int l = S.nlevels - 1; l >= 0; --l) {                                                                                        \
-            const auto& L = sd->lv[l];                                                                                                    \
-            const size_t sml = solve_smem_bytes(L.max_np, k);                                                                             \
-            if (L.bc_count)                                                                                                               \
-                NEPB_LAUNCH((lu_backward_chain_kernel<CK_>), dim3(L.bc_count, nb), 256, smem, sd->dev, sd->bc_items.p + L.bc_begin,        \
-                            sd->chain_fronts.p, F, Xp, S.max_np, k);                                                                      \
-            if (L.bp_count)                                                                                                               \
-                NEPB_LAUNCH((lu_backward_partial_kernel<CK_>), dim3(L.bp_count, nb), 128, sml, sd->dev, sd->bp_items.p + L.bp_begin, F,    \
-                            (const double2*)Xp, part, sd->part_slots, L.max_np, k);                                                       \
-            if (L.sfr_count)                                                                                                              \
-                NEPB_LAUNCH((lu_backward_kernel<CK_>), dim3(L.sfr_count, nb), 256, sml, sd->dev, sd->sfr_items.p + L.sfr_begin, F, Xp,     \
-                            (const double2*)part, sd->part_slots, L.max_np, k);                                                           \
-        }                                                                                                                                 \
-    } while (0)
-    NEPB_CUDA(lu->part.reserve((size_t)2 * nb * std::max(sd->part_slots, 1) * S.max_np * k));
-    double2* part = (double2*)lu->part.p;
-    if (k == 1) NEPB_SOLVE_LEVELS(1);
-    else if (k <= 4) NEPB_SOLVE_LEVELS(4);
-    else if (k <= 8) NEPB_SOLVE_LEVELS(8);
-    else if (k <= 10 || (k > 16 && k <= 20)) NEPB_SOLVE_LEVELS(10);
-    else NEPB_SOLVE_LEVELS(16);
-#undef NEPB_SOLVE_LEVELS
-    NEPB_LAUNCH(lu_permute_out_kernel, pg, 256, 0, n, k, sd->iperm.p, Xp, Xdev, (size_t)n * k);
+    NEPB_LAUNCH(lu_permute_in_kernel, pg, 256, 0, n, k, c.sd->perm.p, Bdev, rhs_stride, c.Xp);
+    for (int l = 0; l < nlev; ++l) solve_forward_level(c, l);
+    for (int l = nlev - 1; l >= 0; --l) solve_backward_level(c, l);
+    NEPB_LAUNCH(lu_permute_out_kernel, pg, 256, 0, n, k, c.sd->iperm.p, c.Xp, Xdev, (size_t)n * k);
+    NEPB_LAUNCH_CHECK();
+    return NEPB_OK;
+}
+
+// Factorise all lu->nb shifts and solve them against Bdev in one pipelined launch sequence: the forward substitution
+// walks the tree in the same bottom-up order as the factorisation, so level l of the forward solve is enqueued on a
+// second stream as soon as the panels of level l are final and runs beside the Schur update / the next levels of the
+// factorisation.  Only the backward substitution remains on the critical path after the root is factorised.
+// `ev` holds at least nlevels + 2 events (no timing).  Works both eagerly and under stream capture (fork / join).
+int lu_factor_solve_pipelined(nepb_lu* lu, int k, const double2* Bdev, size_t rhs_stride, double2* Xdev, cudaStream_t side,
+                              cudaEvent_t* ev) {
+    SolveCtx c;
+    int rc = solve_ctx(lu, 0, lu->nb, k, &c);
+    if (rc) return rc;
+    const int n = c.sd->S.n, nlev = c.sd->S.nlevels, nb = lu->nb;
+    cudaStream_t s0 = stream();
+    dim3 pg((unsigned)(((size_t)n * k + 255) / 256), nb);
+    NEPB_CUDA(cudaEventRecord(ev[0], s0));  // fork: the side stream starts after everything already queued on s0
+    NEPB_CUDA(cudaStreamWaitEvent(side, ev[0], 0));
+    set_current_stream(side);
+    NEPB_LAUNCH(lu_permute_in_kernel, pg, 256, 0, n, k, c.sd->perm.p, Bdev, rhs_stride, c.Xp);
+    set_current_stream(s0);
+    rc = factor_prologue(lu);
+    if (rc) return rc;
+    for (int l = 0; l < nlev; ++l) {
+        factor_level_panels(lu, l);
+        NEPB_CUDA(cudaEventRecord(ev[l + 1], s0));
+        factor_level_schur(lu, l);
+        NEPB_CUDA(cudaStreamWaitEvent(side, ev[l + 1], 0));
+        set_current_stream(side);
+        solve_forward_level(c, l);
+        set_current_stream(s0);
+    }
+    NEPB_CUDA(cudaEventRecord(ev[nlev + 1], side));  // join
+    NEPB_CUDA(cudaStreamWaitEvent(s0, ev[nlev + 1], 0));
+    for (int l = nlev - 1; l >= 0; --l) solve_backward_level(c, l);
+    NEPB_LAUNCH(lu_permute_out_kernel, pg, 256, 0, n, k, c.sd->iperm.p, c.Xp, Xdev, (size_t)n * k);
     NEPB_LAUNCH_CHECK();
     return NEPB_OK;
 }

@@ -103,4 +103,8 @@ int lu_factor_device(nepb_lu* lu);                 // device work only (capturab
 int lu_solve_reserve(nepb_lu* lu, int nb, int k);  // grow scratch outside capture
 // solve for shifts [shift0, shift0+nb): Bdev [b][n][k] (rhs_stride = n*k) or shared (0); Xdev [b][n][k]
 int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev, size_t rhs_stride, double2* Xdev);
+// factorise lu->nb shifts and solve them in one pipelined sequence: forward substitution of level l on `side` beside the
+// factorisation of the levels above it; ev = nlevels + 2 events
+int lu_factor_solve_pipelined(nepb_lu* lu, int k, const double2* Bdev, size_t rhs_stride, double2* Xdev, cudaStream_t side,
+                              cudaEvent_t* ev);
 }  // namespace nepb

@@ -170,7 +170,9 @@ class B200SPMF:
     @classmethod
     def from_nep(cls, nep):
         """Any AbstractSPMF-like object (get_Av / get_fv): SPMF_NEP, PEP, DEP, SumNEP."""
-        return cls(nep.get_Av(), nep.get_fv())
+        dev = cls(nep.get_Av(), nep.get_fv())
+        dev.source = nep  # the host descriptor (PEP / SumNEP / ...) decides nleigs' polynomial degree, rk_nep.jl:101-126
+        return dev
 
     # -- AbstractSPMF ---------------------------------------------------------------------------
     def get_Av(self):

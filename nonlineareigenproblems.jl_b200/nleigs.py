@@ -84,3 +84,241 @@ def nleigs_backslash(nep: B200SPMF, cache: DeviceLinSolverCache, wc, sigma, k, b
     for b in (wcb, bwb, zb, t):
         b.close()
     return w.reshape(n * m, order="F")
+
+
+# =================================================================================================
+# The nleigs driver with the rational Krylov basis in HBM (src/method_nleigs.jl:60-377)
+# =================================================================================================
+import warnings  # noqa: E402
+
+import scipy.linalg as sla  # noqa: E402
+
+from . import rk_helper as rk  # noqa: E402
+from .dense import dgks, copy_cols, residual_errors  # noqa: E402
+from .solvers import ResidualErrmeasure  # noqa: E402
+
+
+class _Basis:
+    """V of the reference (kn x (l+1), kn growing by n per expansion step) as one row-major device block of
+    n*blocks rows and `cols` columns: growing the row count appends memory, earlier vectors stay zero-padded."""
+
+    def __init__(self, n, cols, blocks=4):
+        self.n, self.cols, self.blocks = n, cols, blocks
+        self.b = Block(n * blocks, cols)
+
+    def ensure(self, blocks, used_cols):
+        if blocks <= self.blocks:
+            return
+        nb = max(blocks, min(2 * self.blocks, self.blocks + 32))
+        new = Block(self.n * nb, self.cols)
+        if used_cols > 0:
+            copy_cols(self.b, 0, used_cols, new, 0, rows=self.n * self.blocks)
+        self.b.close()
+        self.b, self.blocks = new, nb
+
+    def close(self):
+        self.b.close()
+
+
+def _device_backslash(nep, cache, basis, l, wcb, bwb, zb, tb, sigma, k, beta, N, xi, sgdd, add_to_cache):
+    """backslash (:399-518) for continuation vector V[:, l-1]; the result is packed into column l of the basis.
+    Same products as nleigs_backslash, operands resident in HBM."""
+    n, m = nep.n, N + 1
+    shift, CB, CZ, CW = backslash_coefficients(sigma, k, beta, N, xi)
+    check(lib.nepb_iar_expand(basis.b._h, l - 1, n, m, wcb._h, 0, 0))
+    block_gemm(wcb, 0, m, CB, bwb, 0)
+    block_gemm(bwb, 0, m, CZ, zb, 0)
+    Cm = -np.ascontiguousarray(np.asarray(sgdd, dtype=np.complex128)[:, 1:N + 1])
+    check(lib.nepb_spmf_apply_block_ex(nep._h, _lib.COEF_GENERAL, zb._h, 1, N, 1, ptr(Cm), tb._h, 0))
+    solver = cache.get(shift, add_to_cache)
+    solve_block(solver.lu, tb, 0, 1, bwb, 0, alpha=1.0 / beta[0])
+    block_gemm(bwb, 0, m, CW, wcb, 0)
+    check(lib.nepb_iar_pack(wcb._h, 0, m, n, basis.b._h, l))
+    if not add_to_cache:
+        solver.lu.close()
+
+
+def nleigs(nep: B200SPMF, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf,), maxdgr=100, minit=20, maxit=200, tol=1e-10,
+           tollin=None, v=None, errmeasure=None, isfunm=True, static=False, leja=1, nodes=(), reusefact=1, blksize=20,
+           return_details=False, check_error_every=5, umfpack_refinements=0, poly_degree=None):
+    """nleigs for a device SPMF operator: the reference's control flow (:100-377, full-rank SPMF branch `P.spmf &&
+    !computeD`) on the host, every O(n) operation on the device -- the stacked product of `backslash` as one fused SpMM,
+    block recurrences as DMMA products, the cached shifted solves on the device LU, DGKS on the n(N+1)-row basis in HBM,
+    Ritz vectors and residuals of all candidates in one product each.  `errmeasure`: None = ResidualErrmeasure
+    (the reference default), a device error measure, or a host callable (lam, x) -> float as in the reference's gun tests.
+    Returns (lam, X, res, details)."""
+    Sigma = np.asarray(Sigma, dtype=np.complex128)
+    Xi = np.asarray(Xi, dtype=np.float64)
+    n = nep.n
+    tollin = max(tol / 10, 100 * np.finfo(float).eps) if tollin is None else tollin
+    p_poly = rk.rk_structure(nep)[0] if poly_degree is None else poly_degree
+    v = np.random.default_rng(0).standard_normal(n) if v is None else v
+    v = np.asarray(v, dtype=np.complex128)
+    errmeasure = errmeasure or ResidualErrmeasure(nep)
+    host_err = callable(errmeasure) and not hasattr(errmeasure, "estimate_error")
+    nodes = np.asarray(nodes, dtype=np.complex128)
+    if n == 1:
+        maxdgr = maxit + 1
+    # -- nodes, poles, scalings (:120-146) -------------------------------------------------------------------------
+    if leja == 0:
+        if len(nodes) == 0:
+            raise ValueError("Interpolation nodes must be provided via 'nodes' when no Leja-Bagby points ('leja' == 0) are used.")
+        gamma, _ = rk.discretizepolygon(Sigma)
+        max_count = maxit + maxdgr + 2 if static else max(maxit, maxdgr) + 2
+        sigma = np.tile(nodes, -(-max_count // len(nodes)))
+        _, xi, beta = rk.lejabagby(sigma[:maxdgr + 2], Xi, gamma, maxdgr + 2, True, p_poly)
+    elif leja == 1:
+        if len(nodes) == 0:
+            gamma, nodes = rk.discretizepolygon(Sigma, True)
+        else:
+            gamma, _ = rk.discretizepolygon(Sigma)
+        nodes = np.tile(nodes, -(-(maxit + 1) // len(nodes)))
+        sigma, xi, beta = rk.lejabagby(gamma, Xi, gamma, maxdgr + 2, False, p_poly)
+    else:
+        gamma, _ = rk.discretizepolygon(Sigma)
+        max_count = maxit + maxdgr + 2 if static else max(maxit, maxdgr) + 2
+        sigma, xi, beta = rk.lejabagby(gamma, Xi, gamma, max_count, False, p_poly)
+    xi[maxdgr + 1] = np.nan
+    if not isfunm and len(sigma) != len(np.unique(sigma)):
+        raise ValueError("All interpolation nodes must be distinct when no matrix functions are used for computing the "
+                         "generalized divided differences.")
+    head = slice(0, maxdgr + 2)
+    sgdd = rk.scgendivdiffs(sigma[head], xi[head], beta[head], maxdgr, isfunm, nep.get_fv())
+    nrmD = [float(np.abs(sgdd[:, 0]).max())]
+    if not np.isfinite(nrmD[0]):
+        raise ValueError("The generalized divided differences must be finite.")
+
+    # -- rational Krylov (:166-359) ----------------------------------------------------------------------------------
+    kmax = maxit + maxdgr if static else maxit
+    cache = DeviceLinSolverCache(nep, umfpack_refinements)
+    first = cache.get(sigma[0], reusefact == 2)
+    v = first.lin_solve(v / np.linalg.norm(v))
+    if reusefact != 2:
+        first.lu.close()
+    cols = kmax + 1
+    basis = _Basis(n, cols)
+    col0 = np.zeros(n * basis.blocks, dtype=np.complex128)
+    col0[:n] = v / np.linalg.norm(v)
+    basis.b.upload(col0, 0)
+    H = np.zeros((kmax + 1, kmax), dtype=np.complex128)
+    K = np.zeros((kmax + 1, kmax), dtype=np.complex128)
+    Lam = np.zeros((kmax, kmax), dtype=np.complex128)
+    Res = np.zeros((kmax, kmax))
+    work = {"m": 0}
+    Qb, Rb = Block(n, cols), Block(n, cols)
+    tb = Block(n, 1)
+    expand, kconv = True, np.iinfo(np.int64).max // 2
+    kn_blocks, l, N, nbconv, nblamin = 1, 0, 0, 0, 0
+    lam = np.zeros(0, dtype=np.complex128)
+    res = np.zeros(0)
+    conv = np.zeros(0, dtype=bool)
+    nlam_cols = 0
+    launches0 = lib.nepb_launch_count()
+
+    def work_blocks(m):
+        if work["m"] < m:
+            for key in ("wc", "bw", "z"):
+                if key in work:
+                    work[key].close()
+            mm = max(m, min(2 * work["m"], work["m"] + 32))
+            work.update(m=mm, wc=Block(n, mm), bw=Block(n, mm), z=Block(n, mm))
+        return work["wc"], work["bw"], work["z"]
+
+    def check_convergence(all_):
+        nonlocal lam, res, conv, nbconv, nblamin, nlam_cols
+        lambda_, S = sla.eig(K[:l, :l], H[:l, :l])
+        if not all_:
+            lamin = rk.in_sigma(lambda_, Sigma, tol)
+            ilam = np.nonzero(lamin)[0]
+            lam = lambda_[ilam]
+        else:
+            ilam = np.nonzero(np.isfinite(lambda_))[0]
+            lam = lambda_[ilam]
+            lamin = rk.in_sigma(lam, Sigma, tol)
+        nblamin = int(lamin.sum())
+        nlam_cols = len(ilam)
+        if nlam_cols:
+            HS = H[:l + 1, :l] @ S[:, ilam]
+            HS = HS / np.linalg.norm(HS, axis=0)[None, :]
+            block_gemm(basis.b, 0, l + 1, HS, Qb, 0, rows=n)  # X = V[1:n, 1:l+1] * (H * S[:, ilam])
+            if host_err:
+                X = Qb.download(0, nlam_cols)
+                X = X / np.linalg.norm(X, axis=0)[None, :]
+                res = np.array([errmeasure(lam[i], X[:, i]) for i in range(nlam_cols)], dtype=float)
+            else:
+                res = np.asarray(residual_errors(nep, errmeasure, lam, Qb, nlam_cols, Rb), dtype=float)
+        else:
+            res = np.zeros(0)
+        conv = np.abs(res) < tol
+        if all_:
+            resall = np.full(l, np.nan)
+            resall[ilam] = res
+            order = sorted(range(l), key=lambda i: (abs(lambda_[i]), np.angle(lambda_[i])))
+            Res[:l, l - 1] = resall[order]
+            Lam[:l, l - 1] = lambda_[order]
+            conv = conv & lamin
+        nbconv = int(conv.sum()) if len(conv) else 0
+
+    k = 1
+    while k <= kmax:
+        if expand:
+            kn_blocks += 1
+            N += 1
+            nrmD.append(float(np.abs(sgdd[:, k]).max()))
+            if not np.isfinite(nrmD[k]):
+                raise ValueError("The generalized divided differences must be finite.")
+            if n > 1 and 5 <= k < kconv:
+                frozen = False
+                if sum(nrmD[k - 4:k + 1]) < 5 * tollin:
+                    kconv = k - 1
+                    if static:
+                        kmax = maxit + kconv
+                        kn_blocks -= 1
+                    xi, beta, nrmD = xi[:k], beta[:k], nrmD[:k]
+                    frozen = True
+                elif k == maxdgr + 1:
+                    kconv = k
+                    warnings.warn("NLEIGS: Linearization not converged after %d iterations" % maxdgr)
+                    frozen = True
+                if frozen:
+                    expand = False
+                    N -= 1
+                    if leja == 1:
+                        if len(sigma) < kmax + 1:
+                            sigma = np.concatenate([sigma, np.zeros(kmax + 1 - len(sigma), dtype=np.complex128)])
+                        sigma[k:kmax + 1] = nodes[:kmax - k + 1]
+        l = k - N if static else k
+        if not static or not expand:
+            basis.ensure(kn_blocks, l)
+            wcb, bwb, zb = work_blocks(N + 1)
+            add_to_cache = ((not expand or k > kconv) and reusefact == 1) or reusefact == 2
+            _device_backslash(nep, cache, basis, l, wcb, bwb, zb, tb, sigma, k, beta, N, xi, sgdd, add_to_cache)
+            h, nrm, _ = dgks(basis.b, l, basis.b, l, rows=n * kn_blocks)
+            H[:l, l - 1] = h
+            H[l, l - 1] = nrm
+            K[:l, l - 1] = h * sigma[k]
+            K[l - 1, l - 1] += 1.0
+            K[l, l - 1] = nrm * sigma[k]
+        if not return_details and ((not expand and k >= N + minit and (k - (N + minit)) % check_error_every == 0) or
+                                   (k >= kconv + minit and (k - (kconv + minit)) % check_error_every == 0) or k == kmax):
+            check_convergence(False)
+        elif return_details and (not static or not expand):
+            check_convergence(True)
+        if ((not expand and k >= N + minit) or k >= kconv + minit) and nblamin == nbconv:
+            break
+        k += 1
+
+    X = Qb.download(0, nlam_cols) if nlam_cols else np.zeros((n, 0), dtype=np.complex128)
+    if nlam_cols:
+        X = X / np.linalg.norm(X, axis=0)[None, :]
+    details = {"Lam": Lam[:l, :l], "Res": Res[:l, :l], "sigma": sigma[:min(k, len(sigma))], "xi": xi[:k] if expand else xi,
+               "beta": beta[:k] if expand else beta, "nrmD": nrmD[:k] if expand else nrmD, "kconv": kconv, "iterations": min(k, kmax),
+               "factorizations": len(cache.solvers), "N": N, "l": l, "H": H[:l + 1, :l], "K": K[:l + 1, :l],
+               "gpu_launches": int(lib.nepb_launch_count() - launches0)}
+    if return_details and expand:
+        warnings.warn("NLEIGS: Linearization not converged after %d iterations" % maxdgr)
+    for blk in [basis, Qb, Rb, tb] + [work[key] for key in ("wc", "bw", "z") if key in work]:
+        blk.close()
+    for s in cache.solvers.values():
+        s.lu.close()
+    return lam[conv], X[:, conv], res[conv], details

@@ -530,7 +530,7 @@ def nleigs(nep, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf,), maxdgr
 
     details = {"Lam": Lam[:l, :l], "Res": Res[:l, :l], "sigma": sigma[:min(k, len(sigma))], "xi": xi[:k] if expand else xi,
                "beta": beta[:k] if expand else beta, "nrmD": nrmD[:k] if expand else nrmD, "kconv": kconv, "iterations": min(k, kmax),
-               "factorizations": cache.created, "N": N, "l": l}
+               "factorizations": cache.created, "N": N, "l": l, "res_all": res, "lam_all": lam}
     if return_details and expand:
         warnings.warn("NLEIGS: Linearization not converged after %d iterations" % maxdgr)
     return lam[conv], X[:, conv], res[conv], details

