@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) sum_groups_kernel(size_t count, int ng, c
 }
 }  // namespace nepb
 
-// `batch` nodes are in flight at a time, spread over NEPB_CONTOUR_STREAMS (default 4) groups; each group factorises and
+// `batch` nodes are in flight at a time, spread over NEPB_CONTOUR_STREAMS (default 8) groups; each group factorises and
 // solves its share as one batched launch sequence on its own stream.
 int nepb_contour_create(const nepb_spmf* h, int k, int mg, int batch, nepb_contour** out) {
     NEPB_CHECK_ARG(h && out, "NULL argument");
@@ -199,7 +199,7 @@ int nepb_contour_create(const nepb_spmf* h, int k, int mg, int batch, nepb_conto
     LuSymbolicDev* sd = nullptr;
     int rc = lu_symbolic_get(h, &sd);
     if (rc) return rc;
-    int ng = 4;
+    int ng = 8;
     if (const char* e = getenv("NEPB_CONTOUR_STREAMS")) ng = std::max(1, std::min(16, atoi(e)));
     ng = std::min(ng, batch);
     nepb_contour* c = new nepb_contour();

@@ -90,39 +90,38 @@ __global__ void __launch_bounds__(256) lu_assemble_kernel(int64_t nnz, int p, in
 }
 
 // ---------------------------------------------------------------------------------------------
-// extend-add: item = (parent s, parent column slab [j0, j1))
+// extend-add: item = (parent s, -, first record, number of records) for one column slab [j0, j1) of the parent.  A record
+// describes one child whose contribution block has columns landing in the slab: the column range [xa, xb) (found on the
+// host: rel is strictly increasing) and everything the copy needs, so the kernel makes no dependent look-ups.
+// Children are applied one after the other (fixed summation order); within a child every parent entry is hit once.
+// A warp walks one child column at a time, lanes along its rows: coalesced reads of the contribution block.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts) {
+__global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev d, const int4* __restrict__ items, const EaRec* __restrict__ recs,
+                                                            double2* __restrict__ fronts) {
     const int4 it = items[blockIdx.x];
-    const int s = it.x, j0 = it.y, j1 = it.z;
+    const int s = it.x;
     const int b = blockIdx.y;
     double2* base = fronts + (size_t)b * d.front_total;
     const int ldp = d.ld[s];
     double2* Fp = base + d.front_off[s];
-    for (int ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ++ci) {
-        const int c = d.child_list[ci];
-        const int nfc = d.nf[c], npc = d.np[c], ncb = nfc - npc, ldc = d.ld[c];
-        if (ncb == 0 || d.in_place[c]) continue;  // in-place child: its Schur update already landed in this front
-        const int* rel = d.rel + d.rel_ptr[c];
-        // rel is strictly increasing: the child columns landing in [j0, j1) form a contiguous range
-        int lo = 0, hi = ncb;
-        while (lo < hi) { int m = (lo + hi) >> 1; if (rel[m] < j0) lo = m + 1; else hi = m; }
-        const int xa = lo;
-        hi = ncb;
-        while (lo < hi) { int m = (lo + hi) >> 1; if (rel[m] < j1) lo = m + 1; else hi = m; }
-        const int xb = lo;
-        const double2* Fc = base + d.front_off[c];
-        const int total = (xb - xa) * ncb;
-        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-            const int x = xa + idx / ncb, y = idx % ncb;
-            const double2 v = Fc[(size_t)(npc + y) + (size_t)(npc + x) * ldc];
-            double2* t = Fp + (size_t)rel[y] + (size_t)rel[x] * ldp;
-            double2 o = *t;
-            o.x += v.x;
-            o.y += v.y;
-            *t = o;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int q = 0; q < it.w; ++q) {
+        const EaRec r = recs[it.z + q];
+        const int* __restrict__ rel = d.rel + r.rel_off;
+        const double2* __restrict__ Fc = base + r.child_off + (size_t)r.npc * (r.ldc + 1);  // first entry of the contribution block
+        for (int x = r.xa + wid; x < r.xb; x += 8) {
+            const double2* col = Fc + (size_t)x * r.ldc;
+            double2* pcol = Fp + (size_t)rel[x] * ldp;
+            for (int y = lane; y < r.ncb; y += 32) {
+                const double2 v = col[y];
+                double2* t = pcol + rel[y];
+                double2 o = *t;
+                o.x += v.x;
+                o.y += v.y;
+                *t = o;
+            }
         }
-        __syncthreads();  // children are applied one after the other: fixed summation order
+        __syncthreads();
     }
 }
 
@@ -148,12 +147,43 @@ __device__ __forceinline__ double2 shfl_c(double2 v, int src) {
 }
 
 constexpr int DNP = 32, DCW = 8, DNW = 4;
+constexpr int DLD = 3 * DNP + 1;  // row of the factor block in shared memory: 32 zeros | 32 entries | 32 zeros (+1 pad)
+constexpr size_t DIAG_SMEM = ((size_t)DNP * DLD + 2 * DNP + DNP) * 16 + 16;
+
+// column `lane` of inv(L11) (UP = false) or inv(U11) (UP = true) by right-looking substitution on a register window:
+// y[m] = x[t + m] resp. x[t - m], so y[0] is always the entry being finished and every register index is static.
+// Rows of the factor block are zero-padded on both sides, so the window needs no bounds checks.  W = window length >= np.
+template <int W, bool UP>
+__device__ __forceinline__ void diag_tri_inverse(const double2* __restrict__ sLU, const double2* __restrict__ s_rp, int np, int lane,
+                                                 double2* __restrict__ F, int ld) {
+    double2 y[W];
+#pragma unroll
+    for (int m = 0; m < W; ++m) y[m] = make_double2((UP ? np - 1 - m : m) == lane ? 1.0 : 0.0, 0.0);
+#pragma unroll 1
+    for (int q = 0; q < np; ++q) {
+        const int t = UP ? np - 1 - q : q;
+        double2 xt = y[0];
+        if (UP) xt = cmul(xt, s_rp[t]);
+        if (lane < np && (UP ? t <= lane : t > lane)) F[(size_t)t + (size_t)lane * ld] = xt;
+        const double2* row = sLU + t * DLD + DNP + t;
+#pragma unroll
+        for (int m = 1; m < W; ++m) {
+            const double2 f = UP ? row[-m] : row[m];
+            double2 r = y[m];
+            cfms(r, f, xt);
+            y[m - 1] = r;
+        }
+        y[W - 1] = make_double2(0.0, 0.0);
+    }
+}
+
 __global__ void __launch_bounds__(128) lu_diag_inv_kernel(LuDev d, const int* __restrict__ items, double2* __restrict__ fronts,
                                                           int* __restrict__ piv, LuInfo* __restrict__ info) {
-    __shared__ double2 s_l[2][DNP];
-    __shared__ int s_p[2];
-    __shared__ double2 s_rp[DNP];
-    __shared__ double2 s_LU[DNP][DNP + 1];  // s_LU[c][r] = (L\U)[r][c]
+    extern __shared__ double2 dsm[];
+    double2* sLU = dsm;                      // [c][DLD]: sLU[c*DLD + DNP + r] = (L\U)[r][c]
+    double2* s_l = dsm + DNP * DLD;          // [2][DNP] multipliers of the current step
+    double2* s_rp = s_l + 2 * DNP;           // [DNP] reciprocal pivots
+    int* s_p = (int*)(s_rp + DNP);           // [2] pivot row of the current step
     const int s = items[blockIdx.x];
     const int b = blockIdx.y;
     const int np = d.np[s], ld = d.ld[s];
@@ -166,64 +196,81 @@ __global__ void __launch_bounds__(128) lu_diag_inv_kernel(LuDev d, const int* __
         const int cg = DNW * c + w;
         a[c] = (lane < np && cg < np) ? F[(size_t)lane + (size_t)cg * ld] : make_double2(lane == cg ? 1.0 : 0.0, 0.0);
     }
+    for (int idx = threadIdx.x; idx < np * (2 * DNP + 1); idx += 128) {  // zero padding of the rows that will be read
+        const int r = idx / (2 * DNP + 1), x = idx % (2 * DNP + 1);
+        sLU[r * DLD + (x < DNP ? x : x + DNP)] = make_double2(0.0, 0.0);
+    }
     if (w == 0) s_rp[lane] = make_double2(1.0, 0.0);
     const double amax = __longlong_as_double(info[b].amax_bits);
     const double tiny = 2.220446049250313e-16 * amax;
     double minpiv = INFINITY;
     int nperturbed = 0, flags = 0;
     int pos = (lane < np) ? -1 : lane;  // step at which this row became the pivot row
+    // the owner warp of column j (its window starts at that column, fully updated) picks the pivot row, forms the multipliers
+    // and publishes them; then it rotates its window
+    auto owner_step = [&](int j) {
+        const int par = j & 1;
+        double2 aj = a[0];
+        const double mine = cabs1(aj);
+        const bool cand = pos < 0;
+        const float mf = (mine == mine) ? (float)mine : INFINITY;
+        const unsigned key = cand ? __float_as_uint(mf) + 1u : 0u;  // non-negative floats order like their bit patterns
+        const unsigned best = __reduce_max_sync(0xffffffffu, key);
+        int bi = __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;
+        const unsigned kj = __shfl_sync(0xffffffffu, key, j);
+        if (kj != 0u && __uint_as_float(kj - 1u) >= 0.1f * __uint_as_float(best - 1u)) bi = j;  // prefer the diagonal
+        double2 pvt = shfl_c(aj, bi);
+        const double pa = cabs1(pvt);
+        if (!(pa <= 1.79e308)) {
+            flags |= 2;
+            pvt = make_double2(1.0, 0.0);
+        } else if (pa == 0.0) {
+            flags |= 1;
+            ++nperturbed;
+            pvt = make_double2(tiny > 0.0 ? tiny : 1.0, 0.0);
+        } else if (pa < tiny) {
+            ++nperturbed;
+            const double sc = tiny / pa;
+            pvt = make_double2(pvt.x * sc, pvt.y * sc);
+        }
+        minpiv = fmin(minpiv, pa);
+        const double2 rp = crecip(pvt);
+        double2 l = make_double2(0.0, 0.0);
+        if (lane == bi) {
+            aj = pvt;
+            pos = j;
+        } else if (cand) {
+            l = cmul(aj, rp);
+            aj = l;
+        }
+        sLU[j * DLD + DNP + lane] = aj;  // column j is final: multipliers below the pivot, U entries in the rows chosen earlier
+        s_l[par * DNP + lane] = l;
+        if (lane == 0) {
+            s_p[par] = bi;
+            s_rp[j] = rp;
+        }
+#pragma unroll
+        for (int c = 0; c < DCW - 1; ++c) a[c] = a[c + 1];
+    };
+    __syncthreads();  // padding written before any column lands
+    if (w == 0) owner_step(0);
 #pragma unroll 1
     for (int j = 0; j < np; ++j) {
         const int par = j & 1, owner = j & (DNW - 1);
-        if (w == owner) {  // warp-uniform: the owner of column j picks the pivot row and forms the multipliers
-            double2 aj = a[0];
-            const double mine = cabs1(aj);
-            const bool cand = pos < 0;
-            const float mf = (mine == mine) ? (float)mine : INFINITY;
-            const unsigned key = cand ? __float_as_uint(mf) + 1u : 0u;  // non-negative floats order like their bit patterns
-            const unsigned best = __reduce_max_sync(0xffffffffu, key);
-            int bi = __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;
-            const unsigned kj = __shfl_sync(0xffffffffu, key, j);
-            if (kj != 0u && __uint_as_float(kj - 1u) >= 0.1f * __uint_as_float(best - 1u)) bi = j;  // prefer the diagonal
-            double2 pvt = shfl_c(aj, bi);
-            const double pa = cabs1(pvt);
-            if (!(pa <= 1.79e308)) {
-                flags |= 2;
-                pvt = make_double2(1.0, 0.0);
-            } else if (pa == 0.0) {
-                flags |= 1;
-                ++nperturbed;
-                pvt = make_double2(tiny > 0.0 ? tiny : 1.0, 0.0);
-            } else if (pa < tiny) {
-                ++nperturbed;
-                const double sc = tiny / pa;
-                pvt = make_double2(pvt.x * sc, pvt.y * sc);
-            }
-            minpiv = fmin(minpiv, pa);
-            const double2 rp = crecip(pvt);
-            double2 l = make_double2(0.0, 0.0);
-            if (lane == bi) {
-                aj = pvt;
-                pos = j;
-            } else if (cand) {
-                l = cmul(aj, rp);
-                aj = l;
-            }
-            s_LU[j][lane] = aj;  // column j is final: multipliers below the pivot, U entries in the rows chosen earlier
-            s_l[par][lane] = l;
-            if (lane == 0) {
-                s_p[par] = bi;
-                s_rp[j] = rp;
-            }
-#pragma unroll
-            for (int c = 0; c < DCW - 1; ++c) a[c] = a[c + 1];
-        }
         __syncthreads();
         const int p = s_p[par];
-        const double2 l = s_l[par][lane];  // zero for the pivot row and for rows that became pivot rows earlier
+        const double2 l = s_l[par * DNP + lane];  // zero for the pivot row and for rows that became pivot rows earlier
         if (w != owner && lane == p) pos = j;
         const int first = (j & ~(DNW - 1)) + w + (w > owner ? 0 : DNW);  // first column of this warp beyond j
-        const int rem = (np - first + DNW - 1) / DNW;                    // its columns below np
+        int rem = (np - first + DNW - 1) / DNW;                          // its columns below np
+        if (j + 1 < np && w == ((j + 1) & (DNW - 1))) {
+            // look-ahead: the owner of the next column updates that column first and eliminates it right away, so the
+            // serial chain per step is one column update + the pivot search, not the whole rank-1 update
+            const double2 rj = shfl_c(a[0], p);
+            cfms(a[0], l, rj);
+            owner_step(j + 1);
+            --rem;
+        }
 #pragma unroll
         for (int c = 0; c < DCW; ++c) {
             if (c < rem) {  // warp-uniform
@@ -236,39 +283,20 @@ __global__ void __launch_bounds__(128) lu_diag_inv_kernel(LuDev d, const int* __
     {  // rows into pivot order
         double2 tmp[DCW];
 #pragma unroll
-        for (int c = 0; c < DCW; ++c) tmp[c] = s_LU[DNW * c + w][lane];
+        for (int c = 0; c < DCW; ++c) tmp[c] = (DNW * c + w < np) ? sLU[(DNW * c + w) * DLD + DNP + lane] : make_double2(0.0, 0.0);
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < DCW; ++c) s_LU[DNW * c + w][pos] = tmp[c];
+        for (int c = 0; c < DCW; ++c)
+            if (DNW * c + w < np) sLU[(DNW * c + w) * DLD + DNP + pos] = tmp[c];
         if (w == 0 && lane < np) pv[pos] = lane;
         __syncthreads();
     }
-    if (w < 2) {
-        // w = 0: column `lane` of inv(L11): x = e_lane; for t = 0, 1, ..: x_i -= L[i][t] x_t (i > t)
-        // w = 1: column `lane` of inv(U11): for t = np-1, ..: x_t *= 1/u_tt; x_i -= U[i][t] x_t (i < t)
-        // y[m] = x[t + m] (w = 0) or x[t - m] (w = 1): the window moves with t, so y[0] is always the entry being finished
-        const bool up = (w == 1);
-        double2 y[DNP];
-#pragma unroll
-        for (int m = 0; m < DNP; ++m) y[m] = make_double2((up ? np - 1 - m : m) == lane ? 1.0 : 0.0, 0.0);
-#pragma unroll 1
-        for (int q = 0; q < np; ++q) {
-            const int t = up ? np - 1 - q : q;
-            double2 xt = y[0];
-            if (up) xt = cmul(xt, s_rp[t]);
-            if (lane < np && (up ? t <= lane : t > lane)) F[(size_t)t + (size_t)lane * ld] = xt;
-            const double2* row = &s_LU[t][0];
-#pragma unroll
-            for (int m = 1; m < DNP; ++m) {
-                const int i = up ? t - m : t + m;
-                double2 f = make_double2(0.0, 0.0);
-                if (i >= 0 && i < DNP) f = row[i];  // warp-uniform
-                double2 r = y[m];
-                cfms(r, f, xt);
-                y[m - 1] = r;
-            }
-            y[DNP - 1] = make_double2(0.0, 0.0);
-        }
+    if (np <= 16) {
+        if (w == 0) diag_tri_inverse<16, false>(sLU, s_rp, np, lane, F, ld);
+        else if (w == 1) diag_tri_inverse<16, true>(sLU, s_rp, np, lane, F, ld);
+    } else {
+        if (w == 0) diag_tri_inverse<DNP, false>(sLU, s_rp, np, lane, F, ld);
+        else if (w == 1) diag_tri_inverse<DNP, true>(sLU, s_rp, np, lane, F, ld);
     }
     if (lane == 0) {
         if (flags) atomicOr(&info[b].flags, flags);
@@ -933,6 +961,7 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     sd->lv.resize(S.nlevels);
     std::vector<int32_t> fr_items;
     std::vector<int4> ea_items, pn_items, sc_items, sp_items, fu_items, bp_items;
+    std::vector<EaRec> ea_recs;
     std::vector<int32_t> bw_slot(ns, 0);
     sd->part_slots = 0;
     // chains of in-place fronts: the tail links (2..m) are walked by one CTA per shift in the solves
@@ -982,17 +1011,41 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
             for (int ci = child_ptr[s]; ci < child_ptr[s + 1]; ++ci)
                 if (!S.in_place_child[child_list[ci]] && nf[child_list[ci]] > np[child_list[ci]]) needs_ea = true;
             if (needs_ea) {
-                // slab width: keep roughly <= 16k entries of child data per CTA
+                // slab width: keep roughly <= 4k entries of child data per CTA (short CTAs: the kernel sits on the critical path)
                 int slab = nf[s];
-                if (nf[s] > 96) slab = std::max(16, (int)(16384 / nf[s]));
-                for (int j0 = 0; j0 < nf[s]; j0 += slab) ea_items.push_back(make_int4(s, j0, std::min(nf[s], j0 + slab), 0));
+                if (nf[s] > 64) slab = std::max(8, (int)(4096 / nf[s]));
+                for (int j0 = 0; j0 < nf[s]; j0 += slab) {
+                    const int j1 = std::min(nf[s], j0 + slab);
+                    const int rec0 = (int)ea_recs.size();
+                    for (int ci = child_ptr[s]; ci < child_ptr[s + 1]; ++ci) {
+                        const int c = child_list[ci];
+                        const int ncbc = nf[c] - np[c];
+                        if (ncbc == 0 || S.in_place_child[c]) continue;  // in-place child: its Schur update already landed in this front
+                        const int32_t* rel = S.rel.data() + S.rel_ptr[c];
+                        const int xa = (int)(std::lower_bound(rel, rel + ncbc, j0) - rel);
+                        const int xb = (int)(std::lower_bound(rel, rel + ncbc, j1) - rel);
+                        if (xb <= xa) continue;
+                        EaRec r;
+                        r.child_off = S.front_off[c];
+                        r.rel_off = S.rel_ptr[c];
+                        r.ldc = S.front_ld[c];
+                        r.npc = np[c];
+                        r.ncb = ncbc;
+                        r.xa = xa;
+                        r.xb = xb;
+                        r.pad = 0;
+                        ea_recs.push_back(r);
+                    }
+                    const int cnt = (int)ea_recs.size() - rec0;
+                    if (cnt) ea_items.push_back(make_int4(s, j0, rec0, cnt));
+                }
             }
             for (int t0 = 0; t0 < ncb; t0 += PANEL_T) {
                 pn_items.push_back(make_int4(s, 0, t0, 0));
                 pn_items.push_back(make_int4(s, 1, t0, 0));
             }
             for (int j0 = 0; j0 < ncb; j0 += SCHUR_T)
-                for (int i0 = 0; i0 < ncb; i0 += SCHUR_T) sc_items.push_back(make_int4(s, i0, j0, 0));
+                for (int i0 = 0; i0 < ncb; i0 += SCHUR_T) sc_items.push_back(make_int4(s, i0, j0, 1));
             for (int j0 = 0; j0 < ncb; j0 += SCHUR_T * SCHUR_GROUP)
                 for (int i0 = 0; i0 < ncb; i0 += SCHUR_T)
                     sp_items.push_back(make_int4(s, i0, j0, std::min(SCHUR_GROUP, (ncb - j0 + SCHUR_T - 1) / SCHUR_T)));
@@ -1037,6 +1090,7 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     UP(sd->iperm, S.iperm);
     UP(sd->fr_items, fr_items);
     UP(sd->ea_items, ea_items);
+    UP(sd->ea_recs, ea_recs);
     UP(sd->pn_items, pn_items);
     UP(sd->sc_items, sc_items);
     UP(sd->sp_items, sp_items);
@@ -1080,6 +1134,7 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     sd->smem_schur = (size_t)mnp * (2 * SCHUR_T + 1) * 16;
     sd->smem_schur_pipe = (size_t)mnp * (3 * SCHUR_T + 2) * 16;
     sd->schur_pipe = sd->smem_schur_pipe <= 110 * 1024 && !getenv("NEPB_LU_SCHUR_SIMPLE");
+    cudaFuncSetAttribute(lu_diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
     cudaFuncSetAttribute(lu_schur_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_schur_pipe);
     cudaFuncSetAttribute(lu_panel_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM);
     cudaFuncSetAttribute(lu_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_schur);
@@ -1130,8 +1185,8 @@ static void factor_level_panels(nepb_lu* lu, int l) {
     const int nb = lu->nb;
     double2* F = (double2*)lu->fronts.p;
     const auto& L = sd->lv[l];
-    if (L.ea_count) NEPB_LAUNCH(lu_extend_add_kernel, dim3(L.ea_count, nb), 256, 0, sd->dev, sd->ea_items.p + L.ea_begin, F);
-    NEPB_LAUNCH(lu_diag_inv_kernel, dim3(L.front_count, nb), 128, 0, sd->dev, sd->fr_items.p + L.front_begin, F, lu->piv.p, lu->info.p);
+    if (L.ea_count) NEPB_LAUNCH(lu_extend_add_kernel, dim3(L.ea_count, nb), 256, 0, sd->dev, sd->ea_items.p + L.ea_begin, sd->ea_recs.p, F);
+    NEPB_LAUNCH(lu_diag_inv_kernel, dim3(L.front_count, nb), 128, DIAG_SMEM, sd->dev, sd->fr_items.p + L.front_begin, F, lu->piv.p, lu->info.p);
     if (L.pn_count) NEPB_LAUNCH(lu_panel_inv_kernel, dim3(L.pn_count, nb), 256, PANEL_SMEM, sd->dev, sd->pn_items.p + L.pn_begin, F, lu->piv.p);
 }
 
@@ -1140,7 +1195,11 @@ static void factor_level_schur(nepb_lu* lu, int l) {
     const int nb = lu->nb;
     double2* F = (double2*)lu->fronts.p;
     const auto& L = sd->lv[l];
-    if (L.sc_count && sd->schur_pipe)
+    // few shifts in flight: one tile per CTA (twice the CTAs, half the time per CTA); otherwise two column tiles per CTA share
+    // the L21 tile
+    if (L.sc_count && sd->schur_pipe && (int64_t)nb * L.sp_count < 2 * sm_count())
+        NEPB_LAUNCH(lu_schur_pipe_kernel, dim3(L.sc_count, nb), 256, sd->smem_schur_pipe, sd->dev, sd->sc_items.p + L.sc_begin, F);
+    else if (L.sc_count && sd->schur_pipe)
         NEPB_LAUNCH(lu_schur_pipe_kernel, dim3(L.sp_count, nb), 256, sd->smem_schur_pipe, sd->dev, sd->sp_items.p + L.sp_begin, F);
     else if (L.sc_count)
         NEPB_LAUNCH(lu_schur_kernel, dim3(L.sc_count, nb), 256, sd->smem_schur, sd->dev, sd->sc_items.p + L.sc_begin, F);

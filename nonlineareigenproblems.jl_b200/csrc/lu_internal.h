@@ -29,6 +29,14 @@ struct LuDev {  // passed by value to kernels
     int n;
 };
 
+struct EaRec {  // one child of one extend-add item (32 bytes)
+    int64_t child_off;  // front offset of the child
+    int64_t rel_off;    // its relative indices in the parent
+    int32_t ldc, npc, ncb;
+    int32_t xa, xb;     // child contribution-block columns landing in the item's slab
+    int32_t pad;
+};
+
 struct LuInfo {
     unsigned long long amax_bits;    // max |M_ij| (bits of a non-negative double)
     unsigned long long minpiv_bits;  // min |pivot| / amax
@@ -60,6 +68,7 @@ struct LuSymbolicDev {
     int part_slots = 0;
     DevBuf<int32_t> nf, np, ld, rows, rel, sn_ptr, child_ptr, child_list, perm, iperm, fr_items;
     DevBuf<int4> ea_items, pn_items, sc_items, sp_items, fu_items, bp_items;
+    DevBuf<EaRec> ea_recs;
     size_t smem_diag = 0, smem_panel = 0, smem_schur = 0, smem_schur_pipe = 0;
     bool schur_pipe = false;
 };
