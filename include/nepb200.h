@@ -104,6 +104,10 @@ int nepb_spmf_apply_block(const nepb_spmf* h, int mode, const nepb_block* V, int
 /* the same on column windows: Z[:, zcol0 : zcol0+q) = sum_i A_i (V[:, vcol0 : vcol0+k) C_i) */
 int nepb_spmf_apply_block_ex(const nepb_spmf* h, int mode, const nepb_block* V, int vcol0, int k, int q, const double* C,
                              nepb_block* Z, int zcol0);
+/* row tiles of the multi-column kernel (built lazily, host integer work): tiles of <= 32 consecutive rows whose distinct
+ * columns (<= 192) are staged in shared memory; *distinct_total = sum over tiles = rows of V gathered per product
+ * (vs nnz_union without tiling); all zero when the operator has a row with more than 192 nonzeros (untiled kernels) */
+int nepb_spmf_tiles_info(const nepb_spmf* h, int64_t* ntiles, int64_t* distinct_total, int* max_distinct);
 /* algorithmic HBM bytes of one nepb_spmf_apply_block call (SURVEY.md 8(d) formula) */
 int64_t nepb_spmf_apply_bytes(const nepb_spmf* h, int mode, int k, int q);
 

@@ -104,6 +104,18 @@ struct nepb_spmf {
     // scratch for host-facing calls
     mutable nepb::DevBuf<double> d_tmp_in, d_tmp_out, d_tmp_x, d_coef;
     mutable nepb::DevBuf<double> d_stage;
+    // row tiles of the multi-column product (lazy, spmf.cu): <= R consecutive rows (R = 32 or 16) whose distinct column
+    // indices (<= 6R, sorted) are staged once per tile in shared memory; lidx[e] = position of nonzero e's column in its
+    // tile's list.  tile = two int4: (first row, rows, first entry of cols, distinct columns), (first nonzero, nonzeros, -, -)
+    struct TileSet {
+        int state = 0;  // 0 = not built, 1 = ready, -1 = not applicable (a row exceeds the tile budget) / no memory
+        int64_t ntiles = 0, cols_total = 0;
+        int max_cols = 0, max_nnz = 0;
+        nepb::DevBuf<int4> tiles;
+        nepb::DevBuf<int32_t> cols;
+        nepb::DevBuf<uint16_t> lidx;
+    };
+    mutable TileSet tiling[2];  // [0]: 32-row tiles, [1]: 16-row tiles
     void* lu_symbolic = nullptr;  // owned by lu.cu (lazy)
     nepb::LuOptions lu_opt;
     bool lu_opt_set = false;

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <vector>
 
 #include "common.h"
@@ -178,6 +179,118 @@ __global__ void __launch_bounds__(256) spmm_fused_kernel(int n, int kt, int ldv,
         for (int j = 0; j < CPT; ++j) {
             const int c = gc + j * GC;
             if (c < kt) Z[(size_t)row * ldz + c] = acc[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1t: the same product for 5..32 dense columns with the rows of V a tile of matrix rows needs staged in shared memory.
+// With k columns a gathered row of V is k*16 bytes and every nonzero gathers one: the gathers (not the matrix stream) are
+// what the memory system sees, 21 x 128 B per row of the C4 stencil at k = 8.  Neighbouring rows of a sparse matrix share
+// most of their columns, so the operator is cut once (host, spmf_build_tiles) into tiles of <= R consecutive rows with
+// <= 6R distinct columns.  A CTA
+//   1. issues asynchronous 16-byte copies (cp.async: no registers held, deep memory-level parallelism) of the tile's
+//      distinct V rows into shared memory,
+//   2. streams the tile's slice of the interleaved matrix values once, coalesced, and reduces every nonzero to its
+//      combined coefficient m = sum_i c_i a_i (SCALAR mode; DIAG keeps the p raw values), stored next to the 16-bit
+//      tile-local column index,
+//   3. after one wait runs the row products out of shared memory: 8 lanes per row, and those 8 lanes read 128 contiguous
+//      bytes of a V row per instruction -- one conflict-free shared-memory wavefront per nonzero and 8 columns.
+// Other resident CTAs are in their copy phase meanwhile.  The bound is the shared-memory pipe (one wavefront per clock
+// and SM), not HBM: see DESIGN.md.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src));
+}
+
+template <int VW, bool CA, bool DIAG, int CPT>
+__global__ void __launch_bounds__(256) spmm_tiled_kernel(int kt, unsigned kinv, int ldv, int ldz, int max_cols, int max_nnz,
+                                                         const int4* __restrict__ tiles, const int* __restrict__ tile_cols,
+                                                         const int* __restrict__ rowptr, const uint16_t* __restrict__ lidx,
+                                                         const double* __restrict__ vals, const double2* __restrict__ V,
+                                                         double2* __restrict__ Z, const CoefP cp, const double2* __restrict__ cdiag, int p) {
+    constexpr int GC = 8;                 // lanes per row; lane gc owns the dense columns gc, gc + 8, ..
+    constexpr int MW = DIAG ? VW : 2;     // doubles kept per nonzero: raw term values (DIAG) or the combined coefficient
+    extern __shared__ double2 sV[];                          // [distinct columns][kt]
+    double* sM = (double*)(sV + (size_t)max_cols * kt);      // [tile nonzeros][MW]
+    uint16_t* sL = (uint16_t*)(sM + (size_t)max_nnz * MW);   // [tile nonzeros] tile-local column
+    int* sRp = (int*)(sL + ((max_nnz + 7) & ~7));            // [rows + 1] row pointers relative to the tile
+    const int4 t0 = tiles[2 * blockIdx.x], t1 = tiles[2 * blockIdx.x + 1];
+    const int row0 = t0.x, nrows = t0.y, ncols = t0.w, nz0 = t1.x, nnz = t1.y;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    {  // 1. the tile's rows of V: consecutive threads copy consecutive 16-byte pieces of one row
+        const int total = ncols * kt;
+        const int* cols = tile_cols + t0.z;
+        for (int e = tid; e < total; e += nth) {
+            const int dcol = (int)__umulhi((unsigned)e, kinv);  // e / kt (exact for e < 2^16)
+            const int c = e - dcol * kt;
+            cp_async_16(&sV[e], V + (size_t)cols[dcol] * ldv + c);
+        }
+        asm volatile("cp.async.commit_group;" ::);
+    }
+    // 2. the tile's slice of the matrix stream (contiguous in CSR order)
+    for (int e = tid; e < nnz; e += nth) {
+        double v[VW];
+        load_vals<VW>(vals, (size_t)(nz0 + e), v);
+        if constexpr (DIAG) {
+#pragma unroll
+            for (int t = 0; t < VW; ++t) sM[e * VW + t] = v[t];
+        } else {
+            const double2 m = combine<VW, CA>(v, [&](int i) { return cp.c[i]; });
+            *(double2*)(sM + 2 * e) = m;
+        }
+        sL[e] = lidx[nz0 + e];
+    }
+    if (tid <= nrows) sRp[tid] = rowptr[row0 + tid] - nz0;
+    const int gc = tid % GC;
+    const int r = tid / GC;
+    double2 cd[DIAG ? CPT : 1][DIAG ? (CA ? VW / 2 : VW) : 1];
+    if constexpr (DIAG) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int c = gc + j * GC;
+#pragma unroll
+            for (int i = 0; i < (CA ? VW / 2 : VW); ++i) cd[j][i] = (c < kt) ? cdiag[i + p * c] : make_double2(0.0, 0.0);
+        }
+    }
+    double2 acc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[j] = make_double2(0.0, 0.0);
+    asm volatile("cp.async.wait_group 0;" ::);
+    __syncthreads();
+    int start = 0, end = 0;
+    if (r < nrows) {
+        start = sRp[r];
+        end = sRp[r + 1];
+    }
+    // 3. row products
+#pragma unroll 2
+    for (int idx = start; idx < end; ++idx) {
+        const double2* xr = sV + (int)sL[idx] * kt + gc;
+        if constexpr (!DIAG) {
+            const double2 m = *(const double2*)(sM + 2 * idx);
+#pragma unroll
+            for (int j = 0; j < CPT; ++j)
+                if (gc + j * GC < kt) cfma(acc[j], m, xr[j * GC]);
+        } else {
+            double v[VW];
+#pragma unroll
+            for (int t = 0; t < VW; ++t) v[t] = sM[idx * VW + t];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                if (gc + j * GC < kt) {
+                    const double2 m = combine<VW, CA>(v, [&](int i) { return cd[j][i]; });
+                    cfma(acc[j], m, xr[j * GC]);
+                }
+            }
+        }
+    }
+    if (r < nrows) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int c = gc + j * GC;
+            if (c < kt) Z[(size_t)(row0 + r) * ldz + c] = acc[j];
         }
     }
 }
@@ -466,9 +579,173 @@ static int launch_fused_vw(const nepb_spmf* h, TileCfg cfg, int kt, int ldv, int
     return 0;
 }
 
+// Cut the rows into tiles for spmm_tiled_kernel (host, once per operator and tile height, O(nnz)): greedy over consecutive
+// rows inside fixed chunks of 8192 rows (one chunk per OpenMP task); a tile closes at `tile_rows` rows or when the next row
+// would push its distinct columns beyond 6 * tile_rows.  Pure integer work, deterministic.
+static int spmf_build_tiles(const nepb_spmf* h, int which) {
+    nepb_spmf::TileSet& T = h->tiling[which];
+    if (T.state) return T.state;
+    const int tile_rows = which == 0 ? 32 : 16;
+    const int tile_cols_max = 6 * tile_rows;
+    const int64_t n = h->n;
+    const int32_t* rp = h->h_rowptr;
+    const int32_t* ci = h->h_colind;
+    constexpr int64_t CHUNK = 8192;
+    const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
+    std::vector<std::vector<int4>> ctiles(nchunks);
+    std::vector<std::vector<int32_t>> ccols(nchunks);
+    std::vector<uint16_t> lidx((size_t)h->nnz);
+    int bad = 0;
+#pragma omp parallel
+    {
+        std::vector<int32_t> stamp((size_t)n, -1), local((size_t)n, 0), cur;
+#pragma omp for schedule(dynamic, 1) reduction(| : bad)
+        for (int64_t ch = 0; ch < nchunks; ++ch) {
+            const int64_t r_end = std::min(n, (ch + 1) * CHUNK);
+            int64_t r = ch * CHUNK;
+            while (r < r_end) {
+                cur.clear();
+                const int32_t tile_id = (int32_t)r;  // stamps are first rows of tiles: unique
+                int64_t rr = r;
+                while (rr < r_end && rr - r < tile_rows) {
+                    int added = 0;
+                    for (int32_t e = rp[rr]; e < rp[rr + 1]; ++e)
+                        if (stamp[ci[e]] != tile_id) ++added;
+                    if ((int)cur.size() + added > tile_cols_max) break;
+                    for (int32_t e = rp[rr]; e < rp[rr + 1]; ++e)
+                        if (stamp[ci[e]] != tile_id) {
+                            stamp[ci[e]] = tile_id;
+                            cur.push_back(ci[e]);
+                        }
+                    ++rr;
+                }
+                if (rr == r) {  // a single row with more distinct columns than a tile holds
+                    bad |= 1;
+                    rr = r + 1;
+                    cur.clear();
+                }
+                std::sort(cur.begin(), cur.end());
+                for (size_t t = 0; t < cur.size(); ++t) local[cur[t]] = (int32_t)t;
+                ctiles[ch].push_back(make_int4((int)r, (int)(rr - r), (int)ccols[ch].size(), (int)cur.size()));
+                ctiles[ch].push_back(make_int4(rp[r], rp[rr] - rp[r], 0, 0));
+                ccols[ch].insert(ccols[ch].end(), cur.begin(), cur.end());
+                if (!(bad & 1))
+                    for (int32_t e = rp[r]; e < rp[rr]; ++e) lidx[e] = (uint16_t)local[ci[e]];
+                r = rr;
+            }
+        }
+    }
+    if (bad) {
+        T.state = -1;
+        return -1;
+    }
+    std::vector<int4> tiles;
+    std::vector<int32_t> cols;
+    int maxc = 0, maxz = 0;
+    for (int64_t ch = 0; ch < nchunks; ++ch) {
+        const int off = (int)cols.size();
+        for (size_t t = 0; t < ctiles[ch].size(); t += 2) {
+            int4 a = ctiles[ch][t];
+            a.z += off;
+            tiles.push_back(a);
+            tiles.push_back(ctiles[ch][t + 1]);
+            maxc = std::max(maxc, a.w);
+            maxz = std::max(maxz, ctiles[ch][t + 1].y);
+        }
+        cols.insert(cols.end(), ccols[ch].begin(), ccols[ch].end());
+    }
+    if (cols.size() >= (size_t)std::numeric_limits<int32_t>::max()) {
+        T.state = -1;
+        return -1;
+    }
+    cudaError_t e = T.tiles.alloc(std::max<size_t>(tiles.size(), 1));
+    if (e == cudaSuccess && !tiles.empty()) e = cudaMemcpy(T.tiles.p, tiles.data(), sizeof(int4) * tiles.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = T.cols.alloc(std::max<size_t>(cols.size(), 1));
+    if (e == cudaSuccess && !cols.empty()) e = cudaMemcpy(T.cols.p, cols.data(), sizeof(int32_t) * cols.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = T.lidx.alloc(std::max<size_t>(lidx.size(), 1));
+    if (e == cudaSuccess && !lidx.empty()) e = cudaMemcpy(T.lidx.p, lidx.data(), sizeof(uint16_t) * lidx.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        T.tiles.release();
+        T.cols.release();
+        T.lidx.release();
+        T.state = -1;  // not enough memory for the tile index: the untiled kernels still work
+        return -1;
+    }
+    T.ntiles = (int64_t)tiles.size() / 2;
+    T.cols_total = (int64_t)cols.size();
+    T.max_cols = maxc;
+    T.max_nnz = maxz;
+    T.state = 1;
+    return 1;
+}
+
+static size_t tiled_smem_bytes(const nepb_spmf::TileSet& T, int kt, int mw) {
+    return (size_t)T.max_cols * kt * 16 + (size_t)T.max_nnz * mw * 8 + (size_t)((T.max_nnz + 7) & ~7) * 2 + 34 * 4;
+}
+
+template <int VW, bool CA, bool DIAG>
+static int launch_tiled_vw(const nepb_spmf* h, const nepb_spmf::TileSet& T, int threads, int kt, int ldv, int ldz, const double2* V,
+                           double2* Z, const CoefP& cp, const double2* cdiag) {
+    const unsigned kinv = (unsigned)((0x100000000ULL + (unsigned)kt - 1) / (unsigned)kt);
+    const size_t smem = tiled_smem_bytes(T, kt, DIAG ? VW : 2);
+#define NEPB_TILED(CPT_)                                                                                                              \
+    do {                                                                                                                              \
+        static size_t attr_done = 0;                                                                                                  \
+        if (smem > 48 * 1024 && smem > attr_done) {                                                                                   \
+            NEPB_CUDA(cudaFuncSetAttribute(spmm_tiled_kernel<VW, CA, DIAG, CPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_done = smem;                                                                                                         \
+        }                                                                                                                             \
+        NEPB_LAUNCH((spmm_tiled_kernel<VW, CA, DIAG, CPT_>), (unsigned)T.ntiles, threads, smem, kt, kinv, ldv, ldz, T.max_cols,        \
+                    T.max_nnz, T.tiles.p, T.cols.p, h->d_rowptr.p, T.lidx.p, h->d_vals.p, V, Z, cp, cdiag, h->p);                     \
+    } while (0)
+    if (kt <= 8) NEPB_TILED(1);
+    else if (kt <= 16) NEPB_TILED(2);
+    else if (kt <= 24) NEPB_TILED(3);
+    else NEPB_TILED(4);
+#undef NEPB_TILED
+    return 1;
+}
+
+// tiled path for 5..32 columns (returns 0 when it does not apply: few columns, unsupported value layout, no tiles)
+static int launch_tiled(const nepb_spmf* h, bool diag, int kt, int ldv, int ldz, const double2* V, double2* Z, const CoefP& cp,
+                        const double2* cdiag) {
+    static const bool enabled = !(getenv("NEPB_SPMM_TILED") && atoi(getenv("NEPB_SPMM_TILED")) == 0);
+    if (!enabled || kt < 5 || getenv("NEPB_SPMM_CFG")) return 0;
+    // wide blocks: 16-row tiles keep the staged rows of V small enough for several resident CTAs per SM
+    int which = kt <= 12 ? 0 : 1;
+    if (const char* e = getenv("NEPB_SPMM_TILE_ROWS")) which = atoi(e) == 16 ? 1 : 0;
+    if (spmf_build_tiles(h, which) != 1) return 0;
+    const nepb_spmf::TileSet& T = h->tiling[which];
+    if (tiled_smem_bytes(T, kt, diag ? h->vw : 2) > 200 * 1024) return 0;
+    const int threads = which == 0 ? 256 : 128;
+    const int vw = h->vw;
+    const bool ca = h->is_complex;
+    int rc = 0;
+#define NEPB_VW_TILED(VW_, CA_)                                                                                           \
+    if (!rc && vw == VW_ && ca == CA_)                                                                                    \
+        rc = diag ? launch_tiled_vw<VW_, CA_, true>(h, T, threads, kt, ldv, ldz, V, Z, cp, cdiag)                          \
+                  : launch_tiled_vw<VW_, CA_, false>(h, T, threads, kt, ldv, ldz, V, Z, cp, cdiag);
+    NEPB_VW_TILED(2, false)
+    NEPB_VW_TILED(3, false)
+    NEPB_VW_TILED(4, false)
+    NEPB_VW_TILED(4, true)
+    NEPB_VW_TILED(8, true)
+#undef NEPB_VW_TILED
+    if (rc == 1) {
+        NEPB_LAUNCH_CHECK();
+    }
+    return rc;
+}
+
 // one column tile (<= 32 columns) of the SCALAR / DIAG product
 static int launch_fused(const nepb_spmf* h, bool diag, int kt, int ldv, int ldz, const double2* V, double2* Z,
                         const CoefP& cp, const double2* cdiag) {
+    {
+        const int rc = launch_tiled(h, diag, kt, ldv, ldz, V, Z, cp, cdiag);
+        if (rc == 1) return NEPB_OK;
+        if (rc != 0) return rc;
+    }
     TileCfg cfg = default_cfg(kt), ecfg;
     bool tuned = false;
     if (env_cfg(ecfg) && ecfg.gc * ecfg.cpt >= kt) {
@@ -692,6 +969,15 @@ int nepb_spmf_info(const nepb_spmf* h, int64_t* n, int* p, int64_t* nnz_union, i
     if (p) *p = h->p;
     if (nnz_union) *nnz_union = h->nnz;
     if (val_is_complex) *val_is_complex = h->is_complex;
+    return NEPB_OK;
+}
+
+int nepb_spmf_tiles_info(const nepb_spmf* h, int64_t* ntiles, int64_t* distinct_total, int* max_distinct) {
+    NEPB_CHECK_ARG(h, "handle is NULL");
+    const int st = spmf_build_tiles(h, 0);
+    if (ntiles) *ntiles = st == 1 ? h->tiling[0].ntiles : 0;
+    if (distinct_total) *distinct_total = st == 1 ? h->tiling[0].cols_total : 0;
+    if (max_distinct) *max_distinct = st == 1 ? h->tiling[0].max_cols : 0;
     return NEPB_OK;
 }
 

@@ -246,6 +246,12 @@ class B200SPMF:
         Cblk = np.ascontiguousarray(Cblk, dtype=np.complex128)
         check(lib.nepb_spmf_apply_block(self._h, mode, Vb._h, Zb.k, ptr(Cblk), Zb._h))
 
+    def tiles_info(self):
+        """Row tiles of the multi-column kernel: (tiles, V rows staged per product, largest tile)."""
+        nt, tot, mx = C.c_int64(), C.c_int64(), C.c_int()
+        check(lib.nepb_spmf_tiles_info(self._h, C.byref(nt), C.byref(tot), C.byref(mx)))
+        return nt.value, tot.value, mx.value
+
     def apply_bytes(self, mode, k, q):
         return lib.nepb_spmf_apply_bytes(self._h, mode, k, q)
 

@@ -213,3 +213,40 @@ def test_error_behaviour():
         d.compute_MM(np.eye(2), np.ones((5, 2)))
     with pytest.raises(nepb200.NepbError):
         d.apply(0, np.ones((4, 2)), np.ones(1), 3)  # q != k in SCALAR mode
+
+
+def test_row_tiles_of_the_multicolumn_kernel():
+    """The tiled SpMM (V rows staged in shared memory) depends on host integer work: tiles of <= 32 consecutive rows with
+    <= 192 distinct columns covering every row exactly once.  Checked through its invariants and, end to end, against the
+    oracle on a matrix whose tiles close early (many distinct columns per row), one with empty rows, and one with a row too
+    wide for a tile (which must fall back to the untiled kernels)."""
+    mats, _ = g.stencil_pep(64)
+    dnep = B200SPMF([m.tocsc() for m in mats], [Monomial(i) for i in range(4)])
+    ntiles, distinct, mx = dnep.tiles_info()
+    n = 64 * 64
+    assert ntiles == n // 32 and mx <= 192
+    assert distinct < dnep.nnz_union / 3  # the stencil shares most columns between neighbouring rows
+    rng = np.random.default_rng(11)
+    # ~40 random columns per row: 4-5 rows per tile; rows 100..163 empty
+    n2 = 2000
+    A = sp.random(n2, n2, 0.02, random_state=5, format="lil")
+    A[100:164, :] = 0
+    A = A.tocsc()
+    B = sp.random(n2, n2, 0.004, random_state=6, format="csc")
+    d2 = B200SPMF([A, B], [ONE, IDENTITY])
+    nt2, dist2, mx2 = d2.tiles_info()
+    assert nt2 > n2 // 32 and 0 < mx2 <= 192 and dist2 <= d2.nnz_union
+    for k in (5, 8, 20, 32):
+        V = rng.standard_normal((n2, k)) + 1j * rng.standard_normal((n2, k))
+        lam = 0.7 - 0.2j
+        assert relerr(d2.compute_MM(lam * np.eye(k), V), (A + lam * B) @ V) < RTOL
+        lams = rng.standard_normal(k) + 1j * rng.standard_normal(k)
+        assert relerr(d2.compute_MM(np.diag(lams), V), A @ V + (B @ V) * lams[None, :]) < RTOL
+    # one dense row: no tiling possible
+    C = sp.lil_matrix((400, 400))
+    C[7, :] = 1.0
+    C.setdiag(2.0)
+    d3 = B200SPMF([C.tocsc()], [ONE])
+    assert d3.tiles_info() == (0, 0, 0)
+    V = rng.standard_normal((400, 8)) + 0j
+    assert relerr(d3.compute_MM(np.eye(8), V), C.tocsc() @ V) < RTOL
