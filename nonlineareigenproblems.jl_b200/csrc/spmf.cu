@@ -712,9 +712,13 @@ static int launch_tiled(const nepb_spmf* h, bool diag, int kt, int ldv, int ldz,
                         const double2* cdiag) {
     static const bool enabled = !(getenv("NEPB_SPMM_TILED") && atoi(getenv("NEPB_SPMM_TILED")) == 0);
     if (!enabled || kt < 5 || getenv("NEPB_SPMM_CFG")) return 0;
-    // wide blocks: 16-row tiles keep the staged rows of V small enough for several resident CTAs per SM
-    int which = kt <= 12 ? 0 : 1;
+    // Measured on config C4 (profiles/r1_spmm_tiled.txt): at k = 8 the tiled kernel runs at 48 % of the HBM roofline against
+    // 33 % untiled; from k ~ 16 on the row products are bound by the shared-memory pipe either way (one 128-byte wavefront per
+    // nonzero and 8 columns: 3 per nonzero at k = 20, which alone equals the HBM time) and staging buys nothing, so wide
+    // blocks keep the untiled kernels unless NEPB_SPMM_TILE_ROWS forces 32- or 16-row tiles.
+    int which = 0;
     if (const char* e = getenv("NEPB_SPMM_TILE_ROWS")) which = atoi(e) == 16 ? 1 : 0;
+    else if (kt > 12) return 0;
     if (spmf_build_tiles(h, which) != 1) return 0;
     const nepb_spmf::TileSet& T = h->tiling[which];
     if (tiled_smem_bytes(T, kt, diag ? h->vw : 2) > 200 * 1024) return 0;

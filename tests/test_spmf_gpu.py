@@ -242,6 +242,16 @@ def test_row_tiles_of_the_multicolumn_kernel():
         assert relerr(d2.compute_MM(lam * np.eye(k), V), (A + lam * B) @ V) < RTOL
         lams = rng.standard_normal(k) + 1j * rng.standard_normal(k)
         assert relerr(d2.compute_MM(np.diag(lams), V), A @ V + (B @ V) * lams[None, :]) < RTOL
+    # wide blocks use the untiled kernels by default; NEPB_SPMM_TILE_ROWS forces the tiled kernel (16- or 32-row tiles)
+    import os
+    for rows in ("16", "32"):
+        os.environ["NEPB_SPMM_TILE_ROWS"] = rows
+        try:
+            for k in (8, 20, 32):
+                V = rng.standard_normal((n2, k)) + 1j * rng.standard_normal((n2, k))
+                assert relerr(d2.compute_MM((0.1 + 0.3j) * np.eye(k), V), (A + (0.1 + 0.3j) * B) @ V) < RTOL
+        finally:
+            del os.environ["NEPB_SPMM_TILE_ROWS"]
     # one dense row: no tiling possible
     C = sp.lil_matrix((400, 400))
     C[7, :] = 1.0
