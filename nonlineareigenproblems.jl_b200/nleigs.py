@@ -314,7 +314,7 @@ def nleigs(nep: B200SPMF, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf
     details = {"Lam": Lam[:l, :l], "Res": Res[:l, :l], "sigma": sigma[:min(k, len(sigma))], "xi": xi[:k] if expand else xi,
                "beta": beta[:k] if expand else beta, "nrmD": nrmD[:k] if expand else nrmD, "kconv": kconv, "iterations": min(k, kmax),
                "factorizations": len(cache.solvers), "N": N, "l": l, "H": H[:l + 1, :l], "K": K[:l + 1, :l],
-               "gpu_launches": int(lib.nepb_launch_count() - launches0)}
+               "gpu_launches": int(lib.nepb_launch_count() - launches0), "lam_all": lam, "res_all": res}
     if return_details and expand:
         warnings.warn("NLEIGS: Linearization not converged after %d iterations" % maxdgr)
     for blk in [basis, Qb, Rb, tb] + [work[key] for key in ("wc", "bw", "z") if key in work]:

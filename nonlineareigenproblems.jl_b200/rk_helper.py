@@ -26,6 +26,8 @@ def inpolygon(px, py, polyx, polyy):
     inside = np.zeros(px.shape, dtype=bool)  # crossing parity
     on = np.zeros(px.shape, dtype=bool)  # on a vertex or an edge
     m = len(polyx)
+    px = np.where(finite, px, 0.0)  # non-finite points are rejected at the end; keep the arithmetic quiet
+    py = np.where(finite, py, 0.0)
     for e in range(m):
         ax, ay = polyx[e], polyy[e]
         bx, by = polyx[(e + 1) % m], polyy[(e + 1) % m]
