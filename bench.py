@@ -496,7 +496,7 @@ def main():
         "ms_per_step": t_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64 (complex128 factors / solves, real f64 A_i)", "data": "gun matrices (reference fixture) + synthetic MSWS probe",
         "config": {"workload": "C3 gun SPMF n=9956 p=4 nnz_u=148318, contour_beyn sigma=150^2 radius=500 N=128 k=20",
-                   "parallelism": "quadrature nodes round-robin over %d rank(s), batch %d per GPU, one ncclAllReduce of 6.4 MB" % (dist.world, batch),
+                   "parallelism": "quadrature nodes round-robin over %d rank(s), batch %d per GPU in 8 node groups (streams), forward solve pipelined beside the factorisation, one ncclAllReduce of 6.4 MB" % (dist.world, batch),
                    "l2": "factor storage per batch %.0f MB > 126 MB L2; SpMM roofline inputs 790 MB > L2; no flush needed" % (batch * sym["front_entries"] * 16e-6),
                    "lu": sym},
         "e2e": {"value": GUN_N / (te * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": int(n * GUN_K * 16 + coef.nbytes + Wm.nbytes),
