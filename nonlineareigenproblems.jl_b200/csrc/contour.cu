@@ -218,7 +218,7 @@ int nepb_contour_create(const nepb_spmf* h, int k, int mg, int batch, nepb_conto
         e = cudaStreamCreateWithFlags(&G->st, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&G->done, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&G->side, cudaStreamNonBlocking);
-        for (int i = 0; i < sd->S.nlevels + 2 && e == cudaSuccess; ++i) {
+        for (int i = 0; i < 3 * sd->S.nlevels + 2 && e == cudaSuccess; ++i) {
             cudaEvent_t x = nullptr;
             e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
             if (e == cudaSuccess) G->ev.push_back(x);

@@ -808,8 +808,11 @@ __device__ __forceinline__ void backward_front(const LuDev& d, int s, int b, con
     const int c0 = d.sn_ptr[s];
     const int tid = threadIdx.x;
     if (ncb > SOLVE_BIG && !product_here) {
-        // the products were formed by lu_backward_partial_kernel: subtract the partial sums slot after slot
-        const int nslots = (ncb + SOLVE_CHUNK - 1) / SOLVE_CHUNK;
+        // update rows [xs, ncb) belong to ancestors above the parent: their products were formed one level earlier by
+        // lu_backward_partial_kernel (off the critical path) and are subtracted slot after slot; the rows [0, xs) are the
+        // parent's pivot rows, solved by the launch right before this one -- that short product is done here
+        const int xs = d.xsplit[s];
+        const int nslots = (ncb - xs + SOLVE_CHUNK - 1) / SOLVE_CHUNK;
         const double2* pp = part + ((size_t)b * part_slots + d.bw_slot[s]) * (size_t)max_np * k;
         for (int idx = tid; idx < np * k; idx += blockDim.x) {
             double2 a = Xb[(size_t)c0 * k + idx];
@@ -820,6 +823,7 @@ __device__ __forceinline__ void backward_front(const LuDev& d, int s, int b, con
             }
             sy[idx] = a;
         }
+        bwd_product<CK>(F, ld, np, 0, xs, rows, Xb, k, sy, sT, sX, true);
     } else {
         for (int idx = tid; idx < np * k; idx += blockDim.x) sy[idx] = Xb[(size_t)c0 * k + idx];
         bwd_product<CK>(F, ld, np, 0, ncb, rows, Xb, k, sy, sT, sX, true);
@@ -962,8 +966,21 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     std::vector<int32_t> fr_items;
     std::vector<int4> ea_items, pn_items, sc_items, sp_items, fu_items, bp_items;
     std::vector<EaRec> ea_recs;
-    std::vector<int32_t> bw_slot(ns, 0);
+    std::vector<int32_t> bw_slot(ns, 0), xsplit(ns, 0);
     sd->part_slots = 0;
+    for (int s = 0; s < ns; ++s) {
+        // update rows of s that are pivot columns of its parent come first (rel is increasing): [0, xsplit)
+        const int par = S.sn_parent[s];
+        const int ncb = nf[s] - np[s];
+        if (par < 0 || ncb == 0) continue;
+        const int64_t r0 = S.rel_ptr[s], r1 = S.rel_ptr[s + 1];
+        if (r1 - r0 == ncb) {
+            const int32_t* rel = S.rel.data() + r0;
+            xsplit[s] = (int)(std::lower_bound(rel, rel + ncb, np[par]) - rel);
+        } else {
+            xsplit[s] = std::min(ncb, (int)np[par]);
+        }
+    }
     // chains of in-place fronts: the tail links (2..m) are walked by one CTA per shift in the solves
     std::vector<char> in_tail(ns, 0);
     std::vector<int32_t> chain_fronts, sfr_items;
@@ -985,6 +1002,7 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
         bc_of_level[S.level[chain_fronts[first + cnt - 1]]].push_back(make_int2(first, cnt));
     }
     std::vector<int2> fc_items, bc_items;
+    int max_level_slots = 0;
     for (int l = 0; l < S.nlevels; ++l) {
         auto& L = sd->lv[l];
         L.front_begin = (int)fr_items.size();
@@ -1051,14 +1069,14 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
                     sp_items.push_back(make_int4(s, i0, j0, std::min(SCHUR_GROUP, (ncb - j0 + SCHUR_T - 1) / SCHUR_T)));
             if (!in_tail[s]) sfr_items.push_back(s);
             if (ncb > SOLVE_BIG && !in_tail[s]) {
+                for (int r0 = 0; r0 < ncb; r0 += SOLVE_CHUNK) fu_items.push_back(make_int4(s, r0, std::min(ncb, r0 + SOLVE_CHUNK), 0));
+                // backward partial products over the rows of the ancestors above the parent; levels alternate between two
+                // slot buffers because these items run while the level above still reads its own slots
                 bw_slot[s] = slots;
-                for (int r0 = 0; r0 < ncb; r0 += SOLVE_CHUNK) {
-                    fu_items.push_back(make_int4(s, r0, std::min(ncb, r0 + SOLVE_CHUNK), 0));
-                    bp_items.push_back(make_int4(s, r0, std::min(ncb, r0 + SOLVE_CHUNK), slots++));
-                }
+                for (int r0 = xsplit[s]; r0 < ncb; r0 += SOLVE_CHUNK) bp_items.push_back(make_int4(s, r0, std::min(ncb, r0 + SOLVE_CHUNK), slots++));
             }
         }
-        sd->part_slots = std::max(sd->part_slots, slots);
+        max_level_slots = std::max(max_level_slots, slots);
         L.fu_count = (int)fu_items.size() - L.fu_begin;
         L.sfr_count = (int)sfr_items.size() - L.sfr_begin;
         L.bp_count = (int)bp_items.size() - L.bp_begin;
@@ -1095,8 +1113,19 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     UP(sd->sc_items, sc_items);
     UP(sd->sp_items, sp_items);
     UP(sd->fu_items, fu_items);
+    // odd levels use the second half of the slot buffer
+    sd->part_slots = 2 * std::max(max_level_slots, 1);
+    for (int l = 1; l < S.nlevels; l += 2) {
+        const auto& L = sd->lv[l];
+        for (int i = L.bp_begin; i < L.bp_begin + L.bp_count; ++i) bp_items[i].w += sd->part_slots / 2;
+        for (int i = L.sfr_begin; i < L.sfr_begin + L.sfr_count; ++i) {
+            const int fs = sfr_items[i];
+            if (nf[fs] - np[fs] > SOLVE_BIG) bw_slot[fs] += sd->part_slots / 2;
+        }
+    }
     UP(sd->bp_items, bp_items);
     UP(sd->bw_slot, bw_slot);
+    UP(sd->xsplit, xsplit);
     UP(sd->sfr_items, sfr_items);
     UP(sd->chain_fronts, chain_fronts);
     UP(sd->fc_items, fc_items);
@@ -1116,6 +1145,7 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     d.in_place = sd->in_place.p;
     d.has_ip = sd->has_ip.p;
     d.bw_slot = sd->bw_slot.p;
+    d.xsplit = sd->xsplit.p;
     d.row_ptr = sd->row_ptr.p;
     d.rows = sd->rows.p;
     d.rel_ptr = sd->rel_ptr.p;
@@ -1255,6 +1285,16 @@ static void solve_forward_level(const SolveCtx& c, int l) {
                     c.F, c.piv, c.Xp, c.W, c.k, sd->S.max_np);
 }
 
+// partial products of level l over the solution rows of levels >= l + 2 (everything above the parents)
+template <int CK>
+static void solve_backward_partials(const SolveCtx& c, int l) {
+    LuSymbolicDev* sd = c.sd;
+    const auto& L = sd->lv[l];
+    if (L.bp_count)
+        NEPB_LAUNCH((lu_backward_partial_kernel<CK>), dim3(L.bp_count, c.nb), 128, solve_smem_bytes(L.max_np, c.k), sd->dev,
+                    sd->bp_items.p + L.bp_begin, c.F, (const double2*)c.Xp, c.part, sd->part_slots, L.max_np, c.k);
+}
+
 template <int CK>
 static void solve_backward_level(const SolveCtx& c, int l) {
     LuSymbolicDev* sd = c.sd;
@@ -1263,9 +1303,6 @@ static void solve_backward_level(const SolveCtx& c, int l) {
     if (L.bc_count)
         NEPB_LAUNCH((lu_backward_chain_kernel<CK>), dim3(L.bc_count, c.nb), 256, c.smem, sd->dev, sd->bc_items.p + L.bc_begin, sd->chain_fronts.p,
                     c.F, c.Xp, sd->S.max_np, c.k);
-    if (L.bp_count)
-        NEPB_LAUNCH((lu_backward_partial_kernel<CK>), dim3(L.bp_count, c.nb), 128, sml, sd->dev, sd->bp_items.p + L.bp_begin, c.F,
-                    (const double2*)c.Xp, c.part, sd->part_slots, L.max_np, c.k);
     if (L.sfr_count)
         NEPB_LAUNCH((lu_backward_kernel<CK>), dim3(L.sfr_count, c.nb), 256, sml, sd->dev, sd->sfr_items.p + L.sfr_begin, c.F, c.Xp,
                     (const double2*)c.part, sd->part_slots, L.max_np, c.k);
@@ -1282,6 +1319,16 @@ static void solve_forward_level(const SolveCtx& c, int l) {
         default: solve_forward_level<16>(c, l); break;
     }
 }
+static void solve_backward_partials(const SolveCtx& c, int l) {
+    switch (solve_ck(c.k)) {
+        case 1: solve_backward_partials<1>(c, l); break;
+        case 4: solve_backward_partials<4>(c, l); break;
+        case 8: solve_backward_partials<8>(c, l); break;
+        case 10: solve_backward_partials<10>(c, l); break;
+        default: solve_backward_partials<16>(c, l); break;
+    }
+}
+static bool level_has_partials(const SolveCtx& c, int l) { return c.sd->lv[l].bp_count > 0; }
 static void solve_backward_level(const SolveCtx& c, int l) {
     switch (solve_ck(c.k)) {
         case 1: solve_backward_level<1>(c, l); break;
@@ -1321,7 +1368,10 @@ int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev,
     dim3 pg((unsigned)(((size_t)n * k + 255) / 256), nb);
     NEPB_LAUNCH(lu_permute_in_kernel, pg, 256, 0, n, k, c.sd->perm.p, Bdev, rhs_stride, c.Xp);
     for (int l = 0; l < nlev; ++l) solve_forward_level(c, l);
-    for (int l = nlev - 1; l >= 0; --l) solve_backward_level(c, l);
+    for (int l = nlev - 1; l >= 0; --l) {
+        solve_backward_partials(c, l);
+        solve_backward_level(c, l);
+    }
     NEPB_LAUNCH(lu_permute_out_kernel, pg, 256, 0, n, k, c.sd->iperm.p, c.Xp, Xdev, (size_t)n * k);
     NEPB_LAUNCH_CHECK();
     return NEPB_OK;
@@ -1331,7 +1381,7 @@ int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev,
 // walks the tree in the same bottom-up order as the factorisation, so level l of the forward solve is enqueued on a
 // second stream as soon as the panels of level l are final and runs beside the Schur update / the next levels of the
 // factorisation.  Only the backward substitution remains on the critical path after the root is factorised.
-// `ev` holds at least nlevels + 2 events (no timing).  Works both eagerly and under stream capture (fork / join).
+// `ev` holds at least 3 * nlevels + 2 events (no timing).  Works both eagerly and under stream capture (fork / join).
 int lu_factor_solve_pipelined(nepb_lu* lu, int k, const double2* Bdev, size_t rhs_stride, double2* Xdev, cudaStream_t side,
                               cudaEvent_t* ev) {
     SolveCtx c;
@@ -1358,7 +1408,23 @@ int lu_factor_solve_pipelined(nepb_lu* lu, int k, const double2* Bdev, size_t rh
     }
     NEPB_CUDA(cudaEventRecord(ev[nlev + 1], side));  // join
     NEPB_CUDA(cudaStreamWaitEvent(s0, ev[nlev + 1], 0));
-    for (int l = nlev - 1; l >= 0; --l) solve_backward_level(c, l);
+    // backward, top-down: the partial products of level l need the solution rows of the levels >= l + 2 only, so they run on
+    // the side stream beside the fronts of level l + 1; per level the critical path is one launch
+    cudaEvent_t* evB = ev + nlev + 2;      // evB[l]: fronts of level l solved
+    cudaEvent_t* evP = ev + 2 * nlev + 2;  // evP[l]: partial products of level l formed
+    for (int l = nlev - 1; l >= 0; --l) {
+        const bool hp = level_has_partials(c, l);
+        if (hp) {
+            if (l + 2 < nlev) NEPB_CUDA(cudaStreamWaitEvent(side, evB[l + 2], 0));
+            set_current_stream(side);
+            solve_backward_partials(c, l);
+            set_current_stream(s0);
+            NEPB_CUDA(cudaEventRecord(evP[l], side));
+            NEPB_CUDA(cudaStreamWaitEvent(s0, evP[l], 0));
+        }
+        solve_backward_level(c, l);
+        NEPB_CUDA(cudaEventRecord(evB[l], s0));
+    }
     NEPB_LAUNCH(lu_permute_out_kernel, pg, 256, 0, n, k, c.sd->iperm.p, c.Xp, Xdev, (size_t)n * k);
     NEPB_LAUNCH_CHECK();
     return NEPB_OK;

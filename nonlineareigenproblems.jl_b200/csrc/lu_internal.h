@@ -17,6 +17,7 @@ struct LuDev {  // passed by value to kernels
     const uint8_t* in_place;   // the front's contribution block is its parent's front
     const uint8_t* has_ip;     // the front has such a child
     const int32_t* bw_slot;    // first partial-sum slot of a big front in the backward solve
+    const int32_t* xsplit;     // update rows [0, xsplit) are pivot columns of the parent
     const int64_t* row_ptr;
     const int32_t* rows;
     const int64_t* rel_ptr;
@@ -63,7 +64,7 @@ struct LuSymbolicDev {
     std::vector<LuLevel> lv;
     DevBuf<int64_t> front_off, row_ptr, rel_ptr, w_off, a_pos;
     DevBuf<uint8_t> in_place, has_ip;
-    DevBuf<int32_t> bw_slot, sfr_items, chain_fronts;
+    DevBuf<int32_t> bw_slot, xsplit, sfr_items, chain_fronts;
     DevBuf<int2> fc_items, bc_items;
     int part_slots = 0;
     DevBuf<int32_t> nf, np, ld, rows, rel, sn_ptr, child_ptr, child_list, perm, iperm, fr_items;
@@ -113,7 +114,7 @@ int lu_solve_reserve(nepb_lu* lu, int nb, int k);  // grow scratch outside captu
 // solve for shifts [shift0, shift0+nb): Bdev [b][n][k] (rhs_stride = n*k) or shared (0); Xdev [b][n][k]
 int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev, size_t rhs_stride, double2* Xdev);
 // factorise lu->nb shifts and solve them in one pipelined sequence: forward substitution of level l on `side` beside the
-// factorisation of the levels above it; ev = nlevels + 2 events
+// factorisation of the levels above it; ev = 3 * nlevels + 2 events
 int lu_factor_solve_pipelined(nepb_lu* lu, int k, const double2* Bdev, size_t rhs_stride, double2* Xdev, cudaStream_t side,
                               cudaEvent_t* ev);
 }  // namespace nepb
