@@ -19,6 +19,6 @@ from .solvers import (contour_block_SS, block_ss_quadrature, block_ss_extract, c
                       ResidualErrmeasure, StandardSPMFErrmeasure, DefaultErrmeasure, NoConvergenceException,
                       LostOrthogonalityException)
 from .dense import (dgks, block_gemm, copy_cols, colnorms, solve_block, mlincomb_block, residual_errors,  # noqa: F401
-                    tiar_device, iar_device)
+                    tiar_device, iar_device, iar_chebyshev_device)
 from .nleigs import nleigs, nleigs_backslash, backslash_coefficients, DeviceLinSolverCache  # noqa: F401
 from . import rk_helper  # noqa: F401

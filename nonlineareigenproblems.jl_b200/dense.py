@@ -196,3 +196,102 @@ def iar_device(nep: B200SPMF, maxit=30, linsolvercreator=None, tol=np.finfo(floa
     Q = Q[:, :min(Q.shape[1], conv_eig)]
     V = Vb.download(0, k) if return_basis else None
     return lam, Q, V
+
+
+# ---------------------------------------------------------------------------------------------
+# iar_chebyshev with the basis in HBM (src/method_iar_chebyshev.jl:66-217, compute_y0_cheb for AbstractSPMF :355-367)
+# ---------------------------------------------------------------------------------------------
+def cheb_integration_matrix(m, a, b):
+    """The matrix L of method_iar_chebyshev.jl:130-131: coefficients of the antiderivative in the scaled Chebyshev basis."""
+    L = np.diag(np.concatenate([[2.0], 1.0 / np.arange(2, m + 1)]))
+    if m > 2:
+        L = L + np.diag(-1.0 / np.arange(1, m - 1), -2)
+    return L * (b - a) / 4.0
+
+
+def cheb_divided_difference_blocks(nep: B200SPMF, m, a, b, gamma, sigma):
+    """precompute_data for ComputeY0ChebSPMF_NEP (:270-287): DDf_i = gamma * f_i[sigma I + gamma D, sigma I] from the block
+    matrix function f([[S, I], [0, sigma I]]) (:474-498); D = differentiation matrix in the Chebyshev basis."""
+    Li = np.linalg.inv(cheb_integration_matrix(m, a, b))
+    D = np.vstack([np.zeros((1, m)), Li[:m - 1, :]])
+    S = sigma * np.eye(m) + gamma * D
+    A = np.zeros((2 * m, 2 * m), dtype=np.complex128)
+    A[:m, :m] = S
+    A[:m, m:] = np.eye(m)
+    A[m:, m:] = sigma * np.eye(m)
+    return [gamma * np.asarray(f(A), dtype=np.complex128)[:m, m:] for f in nep.get_fv()]
+
+
+def iar_chebyshev_device(nep: B200SPMF, maxit=30, linsolvercreator=None, tol=np.finfo(float).eps * 10000, neigs=6, errmeasure=None,
+                         sigma=0.0, gamma=1.0, v=None, check_error_every=1, a=None, b=None):
+    """iar_chebyshev for a device SPMF operator with the SPMF formula of compute_y0_cheb,
+        y0 = -M(sigma)^-1 sum_i A_i X (DDf_i T(c)) - Y T(c),
+    i.e. one fused multi-term product with k x 1 coefficient blocks, one device solve and two tall-skinny products per
+    iteration; the n(m+1)-row basis, the DGKS sweeps and the Ritz residuals stay in HBM.  Returns (lam, Q, err, V, H)."""
+    n, m = nep.n, maxit
+    sigma = complex(sigma)
+    src = getattr(nep, "source", None)
+    tauv = getattr(src, "tauv", None)
+    if a is None:  # :81-82: the delay interval for a DEP, [-1, 1] otherwise
+        a = -float(np.max(tauv)) if tauv is not None else -1.0
+    if b is None:
+        b = 0.0 if tauv is not None else 1.0
+    errmeasure = errmeasure or DefaultErrmeasure(nep)
+    H = np.zeros((m + 1, m), dtype=np.complex128)
+    M0inv = (linsolvercreator or B200LinSolverCreator()).create_linsolver(nep, sigma)
+    lu = M0inv.lu
+    L = cheb_integration_matrix(m, a, b)
+    Tc = np.cos(np.arange(m + 1) * np.arccos((a + b) / (a - b)))
+    DDf = cheb_divided_difference_blocks(nep, m, a, b, gamma, sigma)
+    Vb = Block(n * (m + 1), m + 1)
+    xb, yb, tb = Block(n, m), Block(n, m + 1), Block(n, 1)
+    Qb, Rb = Block(n, m), Block(n, m)
+    v = np.random.default_rng(0).standard_normal(n) if v is None else np.asarray(v, dtype=np.complex128)
+    v0 = np.zeros(n * (m + 1), dtype=np.complex128)
+    v0[:n] = v / np.linalg.norm(v)
+    Vb.upload(v0, 0)
+    err = np.ones((m, m))
+    lam = np.zeros(0, dtype=np.complex128)
+    idx = None
+    nq = 0
+    k, conv_eig = 1, 0
+    while k <= m and conv_eig < neigs:
+        check(lib.nepb_iar_expand(Vb._h, k - 1, n, k, xb._h, 0, 0))  # X = reshape(VV[1:n*k, k], n, k)
+        block_gemm(xb, 0, k, L[:k, :k], yb, 1)                       # y[:, 2:k+1] = X * L[1:k, 1:k]
+        Cm = np.ascontiguousarray(np.stack([Df[:k, :k] @ Tc[:k] for Df in DDf]))  # p x k: term i multiplies X by DDf_i T(c)
+        check(lib.nepb_spmf_apply_block_ex(nep._h, _lib.COEF_GENERAL, xb._h, 0, k, 1, ptr(Cm), tb._h, 0))
+        solve_block(lu, tb, 0, 1, yb, 0)                             # y[:, 1] = M0inv * (sum_i A_i X DDf_i T(c))
+        coef = -np.concatenate([[1.0], Tc[1:k + 1]]).astype(np.complex128)
+        block_gemm(yb, 0, k + 1, coef, tb, 0)                        # y0 = -y[:, 1] - y[:, 2:k+1] T(c)[2:k+1]
+        copy_cols(tb, 0, 1, yb, 0)
+        check(lib.nepb_iar_pack(yb._h, 0, k + 1, n, Vb._h, k))
+        h, nrm, _ = dgks(Vb, k, Vb, k, rows=n * (k + 1))
+        H[:k, k - 1] = h
+        H[k, k - 1] = nrm
+        if (k % check_error_every == 0 or k == m) and k > 2:
+            D, Zm = np.linalg.eig(H[:k, :k])
+            block_gemm(Vb, 0, k, Zm, Qb, 0, rows=n)
+            nq = k
+            lam = sigma + gamma / D
+            e = residual_errors(nep, errmeasure, lam, Qb, k, Rb)
+            err[k - 1, :k] = e
+            conv_eig = int(np.count_nonzero(e < tol))
+            idx = np.argsort(err[k - 1, :k], kind="stable")
+            err[k - 1, :k] = err[k - 1, idx]
+        k += 1
+    k -= 1
+    Q = Qb.download(0, nq) if nq else np.zeros((n, 0), complex)
+    if idx is not None:
+        nrof = int(min(len(lam), neigs))
+        lam, Q = lam[idx[:nrof]], Q[:, idx[:nrof]]
+    if conv_eig < neigs and neigs != np.inf:
+        msg = "Number of iterations exceeded. maxit=%d." % maxit
+        if conv_eig < 3:
+            msg += " Check that sigma is not an eigenvalue."
+        raise NoConvergenceException(lam, Q, err[k - 1], msg)
+    lam = lam[:min(len(lam), conv_eig)]
+    Q = Q[:, :min(Q.shape[1], conv_eig)]
+    V = Vb.download(0, k)
+    for blk in (Vb, xb, yb, tb, Qb, Rb):
+        blk.close()
+    return lam, Q, err[:k, :], V, H[:k, :k]

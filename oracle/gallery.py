@@ -63,6 +63,27 @@ def dep0_matrices(n: int = 5):
     return A0, A1, np.array([0.0, 1.0])
 
 
+def dep0_tridiag_matrices(n: int = 100):
+    """basic_random_examples.jl:24-32: sparse tridiagonal DEP from the MSWS stream -> (A0, A1, tauv)."""
+    rng = MSWS_RNG()
+    K = np.concatenate([np.arange(n), np.arange(1, n), np.arange(n - 1)])
+    J = np.concatenate([np.arange(n), np.arange(n - 1), np.arange(1, n)])
+    A0 = sp.csc_matrix((gen_rng_mat(rng, 3 * n - 2, 1).ravel(), (K, J)), shape=(n, n))
+    A1 = sp.csc_matrix((gen_rng_mat(rng, 3 * n - 2, 1).ravel(), (K, J)), shape=(n, n))
+    return A0, A1, np.array([0.0, 1.0])
+
+
+def neuron0_matrices():
+    """gallery_examples.jl:122-139: the 2 x 2 neuron DEP with four delays (trivial stationary solution)."""
+    kappa, beta, a12, a21 = 0.5, -1.0, 1.0, 2.34
+    tauv = np.array([0.0, 0.2, 0.2, 1.5])
+    A0 = -kappa * np.eye(2)
+    A1 = a21 * np.array([[0.0, 0.0], [1.0, 0.0]])
+    A2 = a12 * np.array([[0.0, 1.0], [0.0, 0.0]])
+    A3 = beta * np.eye(2)
+    return [A0, A1, A2, A3], tauv
+
+
 def read_sparse_matrix(filename: str) -> sp.csc_matrix:
     """utils/Serialization.jl:19-31: line1 m, line2 n, then c row indices, c column indices,
     c values (1-based); Julia's sparse(I,J,V,m,n) sums duplicates and keeps explicit zeros."""

@@ -435,6 +435,12 @@ def nep_gallery(name, *params):
     if name == "dep0":
         A0, A1, tauv = g.dep0_matrices(*params)
         return DEP([A0, A1], tauv)
+    if name == "dep0_tridiag":
+        A0, A1, tauv = g.dep0_tridiag_matrices(*params)
+        return DEP([A0, A1], tauv)
+    if name == "neuron0":
+        A, tauv = g.neuron0_matrices()
+        return DEP(A, tauv)
     if name == "nlevp_native_gun":  # NLEVP_native.jl:4-18
         K, M, W1, W2 = g.load_gun_matrices()
         pep = PEP([K, -M])

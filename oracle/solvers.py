@@ -394,3 +394,153 @@ def contour_block_SS(nep, U, V, sigma=0.0, radius=1.0, N=1000, K=3, tol=np.sqrt(
     if return_moments:
         return lam, Vec, Shat, mprime
     return lam, Vec
+
+
+# --------------------------------------------------------------------------------------------
+# iar_chebyshev (src/method_iar_chebyshev.jl)
+# --------------------------------------------------------------------------------------------
+def cheb_integration_matrix(m, a, b):
+    """The hardcoded matrix L of method_iar_chebyshev.jl:130-131 (m x m)."""
+    L = np.diag(np.concatenate([[2.0], 1.0 / np.arange(2, m + 1)]))
+    if m > 2:
+        L = L + np.diag(-1.0 / np.arange(1, m - 1), -2)
+    return L * (b - a) / 4.0
+
+
+def cheb_Tc(m, a, b):
+    """T_i(c), i = 0..m, c = (a+b)/(a-b) (:238, :262, :274)."""
+    cc = (a + b) / (a - b)
+    return np.cos(np.arange(m + 1) * np.arccos(cc))
+
+
+def DD0_mat_fun(f, S, sigma):
+    """Divided-difference matrix function f[S, sigma I] from the block trick of :474-498."""
+    n = S.shape[0]
+    A = np.zeros((2 * n, 2 * n), dtype=np.complex128)
+    A[:n, :n] = S
+    A[:n, n:] = np.eye(n)
+    A[n:, n:] = sigma * np.eye(n)
+    return np.asarray(f(A), dtype=np.complex128)[:n, n:]
+
+
+def cheb_precompute(nep, method, a, b, m, gamma, sigma):
+    """precompute_data (:234-287) for the DEP, PEP and SPMF variants of compute_y0_cheb."""
+    cc, kk = (a + b) / (a - b), 2.0 / (b - a)
+    pre = {"Tc": cheb_Tc(m, a, b)}
+    if method == "DEP":
+        if sigma != 0 or gamma != 1:
+            raise ValueError("This function does not support shift and scale parameters")
+        Ttau = np.zeros((len(nep.tauv), m + 2))
+        II = np.arange(m + 2)
+        for j, tau in enumerate(nep.tauv):
+            t = -kk * tau + cc
+            if abs(t) <= 1:
+                Ttau[j, :] = np.cos(II * np.arccos(t))
+            elif t >= 1:
+                Ttau[j, :] = np.cosh(II * np.arccosh(t))
+            else:
+                Ttau[j, :] = ((-1.0) ** II) * np.cosh(II * np.arccosh(-t))
+        pre["Ttau"] = Ttau
+    elif method == "PEP":
+        if sigma != 0 or gamma != 1:
+            raise ValueError("This function does not support shift and scale parameters")
+        Li = np.linalg.inv(cheb_integration_matrix(m, a, b))
+        pre["D"] = np.vstack([np.zeros((1, m)), Li[:m - 1, :]])
+    elif method == "SPMF":
+        Li = np.linalg.inv(cheb_integration_matrix(m, a, b))
+        D = np.vstack([np.zeros((1, m)), Li[:m - 1, :]])
+        DDs = sigma * np.eye(m) + gamma * D
+        pre["DDf"] = [gamma * DD0_mat_fun(f, DDs, sigma) for f in o.get_fv(nep)]
+    else:
+        raise ValueError("unknown compute_y0 method " + str(method))
+    return pre
+
+
+def compute_y0_cheb(nep, method, X, Y, M0inv, pre):
+    """compute_y0_cheb (:309-367)."""
+    Tc = pre["Tc"]
+    n, N = X.shape
+    if method == "DEP":
+        Av = o.get_Av(nep)
+        y0 = X @ Tc[:N]
+        for j in range(len(nep.tauv)):
+            y0 = y0 - o._dot(Av[j + 1], Y @ pre["Ttau"][j, :N + 1])
+        return M0inv.lin_solve(y0)
+    if method == "PEP":
+        d = len(nep.A) - 1
+        v = Tc[:N].astype(np.complex128)
+        y0 = np.zeros(n, dtype=np.complex128)
+        for j in range(d):
+            y0 = y0 + o._dot(nep.A[j + 1], X @ v)
+            v = pre["D"][:N, :N] @ v
+        y0 = -M0inv.lin_solve(y0)
+        return y0 - Y @ Tc[:N + 1]
+    Av = o.get_Av(nep)
+    y0 = np.zeros((n, N), dtype=np.complex128)
+    for i, A in enumerate(Av):
+        y0 = y0 + o._dot(A, X @ pre["DDf"][i][:N, :N])
+    y0 = y0 @ Tc[:N]
+    y0 = -M0inv.lin_solve(y0)
+    return y0 - Y @ Tc[:N + 1]
+
+
+def iar_chebyshev(nep, maxit=30, linsolvercreator=None, tol=np.finfo(float).eps * 10000, neigs=6, errmeasure=None, sigma=0.0, gamma=1.0,
+                  v=None, check_error_every=1, a=None, b=None, compute_y0_method="auto", orth=orthogonalize_and_normalize_dgks):
+    """method_iar_chebyshev.jl:66-217.  compute_y0_method: "auto" (by type, :84-96), "DEP", "PEP" or "SPMF".  The DEP / PEP
+    formulas need sigma = 0, gamma = 1 (the reference transforms the problem with shift_and_scale first, which is outside the
+    restated path); the SPMF formula carries sigma and gamma itself.  Returns (lam, Q, err, V, H)."""
+    method = compute_y0_method
+    if a is None:  # :81-82: the delay interval for a DEP, [-1, 1] otherwise
+        a = -float(np.max(nep.tauv)) if isinstance(nep, o.DEP) else -1.0
+    if b is None:
+        b = 0.0 if isinstance(nep, o.DEP) else 1.0
+    if method == "auto":
+        method = "DEP" if isinstance(nep, o.DEP) else "PEP" if isinstance(nep, o.PEP) else "SPMF"
+    if method in ("DEP", "PEP") and (sigma != 0 or gamma != 1):
+        raise NotImplementedError("shift_and_scale is not restated: use compute_y0_method='SPMF' with sigma / gamma")
+    n, m = nep.n, maxit
+    sigma = complex(sigma)
+    errmeasure = errmeasure or default_errmeasure(nep)
+    V = np.zeros((n * (m + 1), m + 1), dtype=np.complex128, order="F")
+    H = np.zeros((m + 1, m), dtype=np.complex128)
+    M0inv = (linsolvercreator or FactorizeLinSolverCreator()).create_linsolver(nep, sigma)
+    err = np.ones((m, m))
+    lam = np.zeros(m + 1, dtype=np.complex128)
+    Q = np.zeros((n, m + 1), dtype=np.complex128)
+    v = np.asarray(v, dtype=np.complex128)
+    V[:n, 0] = v / np.linalg.norm(v)
+    L = cheb_integration_matrix(m, a, b)
+    pre = cheb_precompute(nep, method, a, b, m, gamma, sigma)
+    k, conv_eig = 1, 0
+    idx = None
+    while k <= m and conv_eig < neigs:
+        VV = V[:n * (k + 1), :k]
+        vv = V[:n * (k + 1), k]
+        X = VV[:n * k, k - 1].reshape(n, k, order="F")
+        y = np.zeros((n, k + 1), dtype=np.complex128, order="F")
+        y[:, 1:k + 1] = X @ L[:k, :k]
+        y[:, 0] = compute_y0_cheb(nep, method, X, y, M0inv, pre)
+        vv[:] = y.reshape((k + 1) * n, order="F")
+        H[k, k - 1] = orth(VV, vv, H[:k, k - 1])
+        if (k % check_error_every == 0 or k == m) and k > 2:
+            D, Z = np.linalg.eig(H[:k, :k])
+            Q = V[:n, :k] @ Z
+            lam = sigma + gamma / D
+            err[k - 1, :len(lam)] = [errmeasure(lam[s], Q[:, s]) for s in range(len(lam))]
+            conv_eig = int(np.count_nonzero(err[k - 1, :len(lam)] < tol))
+            idx = np.argsort(err[k - 1, :k], kind="stable")
+            err[k - 1, :k] = err[k - 1, idx]
+            if k == m or conv_eig >= neigs:
+                nrof = int(min(len(lam), neigs))
+                lam = lam[idx[:nrof]]
+                Q = Q[:, idx[:nrof]]
+        k += 1
+    k -= 1
+    if conv_eig < neigs and neigs != np.inf:
+        msg = "Number of iterations exceeded. maxit=%d." % maxit
+        if conv_eig < 3:
+            msg += " Check that sigma is not an eigenvalue."
+        raise NoConvergenceException(lam, Q, err[k - 1], msg)
+    lam = lam[:min(len(lam), conv_eig)]
+    Q = Q[:, :min(Q.shape[1], conv_eig)]
+    return lam, Q, err[:k, :], V[:, :k], H[:k, :k]

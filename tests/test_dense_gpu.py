@@ -108,3 +108,40 @@ def test_iar_device_gun_matches_oracle():
     lam_t, Qt, Zt, _ = nepb200.tiar_device(dnep, **kw)
     assert len(lam_t) == len(lam)
     assert np.max(np.abs(np.sort_complex(lam_t) - a) / np.abs(a)) < 1e-6
+
+
+def test_iar_chebyshev_device_matches_oracle():
+    """iar_chebyshev (src/method_iar_chebyshev.jl) with the SPMF formula of compute_y0_cheb on the device against the oracle:
+    the reference's test "DEP format with ComputeY0ChebSPMF_NEP" (test/iar_chebyshev.jl:222-226: dep0_tridiag(1000), sigma = -1,
+    gamma = 2, 5 eigenpairs with residual < 1e-10), "Compute as many eigenpairs as possible" on dep0, and the exception."""
+    import scipy.sparse as sp
+    eps = np.finfo(float).eps
+    A0, A1, tauv = g.dep0_tridiag_matrices(1000)
+    onep = o.nep_gallery("dep0_tridiag", 1000)
+    dnep = nepb200.B200SPMF.from_nep(nepb200.DEP([A0, A1], tauv))
+    kw = dict(sigma=-1, gamma=2, neigs=5, maxit=100, tol=eps * 100, v=np.ones(1000))
+    lo, Qo, erro, Vo, Ho = osol.iar_chebyshev(onep, compute_y0_method="SPMF", **kw)
+    lam, Q, err, V, H = nepb200.iar_chebyshev_device(dnep, **kw)
+    assert len(lam) == len(lo) == 5
+    for x in lam:
+        assert np.min(np.abs(lo - x)) < 1e-9 * max(1.0, abs(x))
+    for l, q in zip(lam, Q.T):
+        assert np.linalg.norm(o.compute_Mlincomb(onep, l, q)) / np.linalg.norm(q) < 1e-10
+    kk = min(H.shape[0], Ho.shape[0], 15)
+    assert np.abs(H[:kk, :kk] - Ho[:kk, :kk]).max() < 1e-8 * np.abs(Ho[:kk, :kk]).max()
+    assert np.linalg.norm(V.conj().T @ V - np.eye(V.shape[1]), 2) < 1e-6
+    # dep0 (dense 5 x 5): as many eigenpairs as 30 iterations give (the reference's literal is 8; the last pair sits within a
+    # factor 3 of tol = 100 eps, so the device count may differ by that pair)
+    A0d, A1d, tv = g.dep0_matrices(5)
+    odep = o.nep_gallery("dep0")
+    ddep = nepb200.B200SPMF.from_nep(nepb200.DEP([A0d, A1d], tv))
+    lam, Q, err, V, H = nepb200.iar_chebyshev_device(ddep, sigma=0, neigs=np.inf, maxit=30, tol=eps * 100, v=np.ones(5))
+    lo, Qo, _, _, _ = osol.iar_chebyshev(odep, sigma=0, neigs=np.inf, maxit=30, tol=eps * 100, v=np.ones(5))
+    assert len(lo) == 8 and 6 <= len(lam) <= 10
+    for l, q in zip(lam, Q.T):
+        assert np.linalg.norm(o.compute_Mlincomb(odep, l, q)) / np.linalg.norm(q) < 5 * np.sqrt(eps)
+    # errors thrown (test/iar_chebyshev.jl:253-257)
+    A0h, A1h, tvh = g.dep0_matrices(100)
+    d100 = nepb200.B200SPMF.from_nep(nepb200.DEP([A0h, A1h], tvh))
+    with pytest.raises(nepb200.NoConvergenceException):
+        nepb200.iar_chebyshev_device(d100, sigma=0, neigs=8, maxit=10, tol=eps * 100, v=np.ones(100))

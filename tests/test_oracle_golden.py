@@ -1,5 +1,6 @@
 """The oracle pinned against the reference's own literal known answers.  CPU only."""
 import numpy as np
+import pytest
 import scipy.sparse as sp
 
 from oracle import gallery as g
@@ -154,3 +155,48 @@ def test_oracle_block_SS_dep0():
     for radius in (1.0, (1.0, 2.0)):
         lam, Vec = s.contour_block_SS(nep, U, V, radius=radius, N=1000, sigma=0.1, K=3)
         assert np.linalg.norm(o.compute_Mlincomb(nep, lam[0], Vec[:, 0])) < np.sqrt(np.finfo(float).eps)
+
+
+def test_oracle_iar_chebyshev_reference_cases():
+    """test/iar_chebyshev.jl and the docstring of src/method_iar_chebyshev.jl:47-63."""
+    from oracle import solvers as s
+    eps = np.finfo(float).eps
+    dep = o.nep_gallery("dep0")
+    n = 5
+
+    def check(nep, lam, Q, count, tol):
+        assert len(lam) == count
+        for l, q in zip(lam, Q.T):
+            assert np.linalg.norm(o.compute_Mlincomb(nep, l, q)) / np.linalg.norm(q) < tol
+
+    # "accuracy eigenpairs" (:87-90) and "Compute as many eigenpairs as possible" (:92-96): exactly 8 with maxit = 30
+    lam, Q, err, V, H = s.iar_chebyshev(dep, sigma=0, neigs=5, maxit=100, tol=eps * 100, v=np.ones(n))
+    check(dep, lam, Q, 5, n * np.sqrt(eps))
+    assert np.linalg.norm(V.conj().T @ V - np.eye(V.shape[1]), 2) < n * np.sqrt(eps)  # "orthogonalization / DGKS" (:103-106)
+    lam, Q, _, _, _ = s.iar_chebyshev(dep, sigma=0, neigs=np.inf, maxit=30, tol=eps * 100, v=np.ones(n))
+    check(dep, lam, Q, 8, n * np.sqrt(eps))
+    # the SPMF formula of compute_y0_cheb reproduces the DEP formula
+    _, _, _, _, H1 = s.iar_chebyshev(dep, sigma=0, neigs=5, maxit=100, tol=eps * 100, v=np.ones(n))
+    _, _, _, _, H2 = s.iar_chebyshev(dep, sigma=0, neigs=5, maxit=100, tol=eps * 100, v=np.ones(n), compute_y0_method="SPMF")
+    assert H1.shape == H2.shape and np.abs(H1 - H2).max() < 1e-10
+    # docstring: dep0(100), tol = 1e-5, neigs = 3 prints these three eigenvalues
+    dep100 = o.nep_gallery("dep0", 100)
+    lam, Q, _, _, _ = s.iar_chebyshev(dep100, v=np.ones(100), tol=1e-5, neigs=3)
+    for ref in (0.050462487848960284, -0.07708779190301127, 0.1503856540695659):
+        assert np.min(np.abs(lam - ref)) < 1e-7
+    # "Errors thrown" (:253-257)
+    with pytest.raises(s.NoConvergenceException):
+        s.iar_chebyshev(dep100, sigma=0, neigs=8, maxit=10, tol=eps * 100, v=np.ones(100))
+    # "Scale Cheb's to different interval w DEP" (:78-83): neuron0, 10 eigenvalues on [-max tau, 0]
+    neu = o.nep_gallery("neuron0")
+    lam, Q, _, _, _ = s.iar_chebyshev(neu, a=-float(np.max(neu.tauv)), b=0, neigs=10, maxit=100, v=np.ones(2))
+    check(neu, lam, Q, 10, 2 * np.sqrt(eps))
+    # "DEP format with ComputeY0ChebSPMF_NEP" (:222-226): dep0_tridiag(1000), sigma = -1, gamma = 2
+    tri = o.nep_gallery("dep0_tridiag", 1000)
+    lam, Q, _, _, _ = s.iar_chebyshev(tri, sigma=-1, gamma=2, neigs=5, maxit=100, tol=eps * 100, compute_y0_method="SPMF", v=np.ones(1000))
+    check(tri, lam, Q, 5, 1e-10)
+    # "PEP" (:126-137): dense degree-3 PEP, n = 100 (matrices from the MSWS stream instead of rand)
+    rng = g.MSWS_RNG(3)
+    pep = o.PEP([(1 - g.gen_rng_mat(rng, 100, 100)) / 2 for _ in range(4)])
+    lam, Q, _, _, _ = s.iar_chebyshev(pep, sigma=0, neigs=5, maxit=100, tol=eps * 100, v=np.ones(100))
+    check(pep, lam, Q, 5, 100 * np.sqrt(eps))
