@@ -179,6 +179,10 @@ def test_oracle_iar_chebyshev_reference_cases():
     _, _, _, _, H1 = s.iar_chebyshev(dep, sigma=0, neigs=5, maxit=100, tol=eps * 100, v=np.ones(n))
     _, _, _, _, H2 = s.iar_chebyshev(dep, sigma=0, neigs=5, maxit=100, tol=eps * 100, v=np.ones(n), compute_y0_method="SPMF")
     assert H1.shape == H2.shape and np.abs(H1 - H2).max() < 1e-10
+    # ... while it is stable: its DDf blocks grow like |D|^j / j!, and at k = 30 on [-1, 0] the SPMF formula has lost all
+    # accuracy (same in the reference: the matrices are identical), whereas the DEP formula still resolves 8 eigenpairs
+    lam_s, _, _, _, Hs = s.iar_chebyshev(dep, sigma=0, neigs=np.inf, maxit=30, tol=eps * 100, v=np.ones(n), compute_y0_method="SPMF")
+    assert len(lam_s) < 8
     # docstring: dep0(100), tol = 1e-5, neigs = 3 prints these three eigenvalues
     dep100 = o.nep_gallery("dep0", 100)
     lam, Q, _, _, _ = s.iar_chebyshev(dep100, v=np.ones(100), tol=1e-5, neigs=3)
