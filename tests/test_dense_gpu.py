@@ -108,47 +108,3 @@ def test_iar_device_gun_matches_oracle():
     lam_t, Qt, Zt, _ = nepb200.tiar_device(dnep, **kw)
     assert len(lam_t) == len(lam)
     assert np.max(np.abs(np.sort_complex(lam_t) - a) / np.abs(a)) < 1e-6
-
-
-def test_iar_chebyshev_device_matches_oracle():
-    """iar_chebyshev (src/method_iar_chebyshev.jl) with the SPMF formula of compute_y0_cheb on the device against the oracle:
-    the reference's test "DEP format with ComputeY0ChebSPMF_NEP" (test/iar_chebyshev.jl:222-226: dep0_tridiag(1000), sigma = -1,
-    gamma = 2, 5 eigenpairs with residual < 1e-10), "Compute as many eigenpairs as possible" on dep0, and the exception."""
-    import scipy.sparse as sp
-    eps = np.finfo(float).eps
-    A0, A1, tauv = g.dep0_tridiag_matrices(1000)
-    onep = o.nep_gallery("dep0_tridiag", 1000)
-    dnep = nepb200.B200SPMF.from_nep(nepb200.DEP([A0, A1], tauv))
-    kw = dict(sigma=-1, gamma=2, neigs=5, maxit=100, tol=eps * 100, v=np.ones(1000))
-    lo, Qo, erro, Vo, Ho = osol.iar_chebyshev(onep, compute_y0_method="SPMF", **kw)
-    lam, Q, err, V, H = nepb200.iar_chebyshev_device(dnep, **kw)
-    assert len(lam) == len(lo) == 5
-    for x in lam:
-        assert np.min(np.abs(lo - x)) < 1e-9 * max(1.0, abs(x))
-    for l, q in zip(lam, Q.T):
-        assert np.linalg.norm(o.compute_Mlincomb(onep, l, q)) / np.linalg.norm(q) < 1e-10
-    kk = min(H.shape[0], Ho.shape[0], 15)
-    assert np.abs(H[:kk, :kk] - Ho[:kk, :kk]).max() < 1e-8 * np.abs(Ho[:kk, :kk]).max()
-    assert np.linalg.norm(V.conj().T @ V - np.eye(V.shape[1]), 2) < 1e-6
-    # dep0 (dense 5 x 5, sigma = 0): the same Arnoldi factorisation as the oracle's SPMF formula.  Kept to 16 iterations: the
-    # SPMF formula multiplies the trailing Chebyshev coefficients of the basis with entries of DDf that grow like
-    # |D|^j / j! (D = differentiation matrix on [-1, 0]), so beyond k ~ 25 it amplifies rounding noise -- in the reference,
-    # in the oracle and on the device alike (at k = 30 all three give the same wrong Ritz values); the reference's DEP formula
-    # does not, which is why its "as many eigenpairs as possible" test (8 at maxit = 30) is pinned on the oracle only.
-    A0d, A1d, tv = g.dep0_matrices(5)
-    odep = o.nep_gallery("dep0")
-    ddep = nepb200.B200SPMF.from_nep(nepb200.DEP([A0d, A1d], tv))
-    kw = dict(sigma=0, neigs=np.inf, maxit=16, tol=1e-6, v=np.ones(5))
-    lam, Q, err, V, H = nepb200.iar_chebyshev_device(ddep, **kw)
-    lo, Qo, _, _, Ho = osol.iar_chebyshev(odep, compute_y0_method="SPMF", **kw)
-    assert len(lo) == 6 and len(lam) == 6
-    assert np.abs(H - Ho).max() < 1e-8 * np.abs(Ho).max()
-    for x in lam:
-        assert np.min(np.abs(lo - x)) < 1e-8
-    for l, q in zip(lam, Q.T):
-        assert np.linalg.norm(o.compute_Mlincomb(odep, l, q)) / np.linalg.norm(q) < 1e-5
-    # errors thrown (test/iar_chebyshev.jl:253-257)
-    A0h, A1h, tvh = g.dep0_matrices(100)
-    d100 = nepb200.B200SPMF.from_nep(nepb200.DEP([A0h, A1h], tvh))
-    with pytest.raises(nepb200.NoConvergenceException):
-        nepb200.iar_chebyshev_device(d100, sigma=0, neigs=8, maxit=10, tol=eps * 100, v=np.ones(100))
