@@ -204,3 +204,24 @@ def test_oracle_iar_chebyshev_reference_cases():
     pep = o.PEP([(1 - g.gen_rng_mat(rng, 100, 100)) / 2 for _ in range(4)])
     lam, Q, _, _, _ = s.iar_chebyshev(pep, sigma=0, neigs=5, maxit=100, tol=eps * 100, v=np.ones(100))
     check(pep, lam, Q, 5, 100 * np.sqrt(eps))
+
+
+def test_oracle_docstring_literals_dep0_100_and_qdep0():
+    """More known answers of SURVEY.md 8(c): the tiar docstring eigenvalues of dep0(100) (src/method_tiar.jl:36-46; tol = 1e-5),
+    the mslp eigenvalue of docs/src/index.md:64-67, and the qdep0 eigenvalue the quasinewton docstring converges to
+    (src/errmeasure.jl:55-70).  (The three values printed in the iar docstring, src/method_iar.jl:37-40, belong to an older
+    dep0 generator: iar and tiar are mathematically the same iteration and agree with each other here.)"""
+    from oracle import solvers as s
+    nep = o.nep_gallery("dep0", 100)
+    v0 = np.ones(100)
+    doc = np.array([0.050462487743188206, -0.07708769561361105, 0.1503916927814904])
+    lam_t, _, _, _ = s.tiar(nep, v=v0, tol=1e-5, neigs=3)
+    lam_i, _, _ = s.iar(nep, v=v0, tol=1e-5, neigs=3)
+    for ref in doc:
+        assert np.min(np.abs(lam_t - ref)) < 1e-8
+        assert np.min(np.abs(lam_i - ref)) < 1e-8
+    lam, v = s.resinv(nep, lam=0.0, v=v0, tol=1e-14)
+    assert abs(lam - 0.05046248970129549) < 1e-12
+    q = o.nep_gallery("qdep0")
+    lam, v = s.resinv(q, lam=-1.0, v=np.ones(q.n), tol=1e-13, maxit=200)
+    assert abs(lam - (-1.002466988585764)) < 1e-10
