@@ -204,7 +204,10 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src));
 }
 
-template <int VW, bool CA, bool DIAG, int CPT>
+// BULK = true (NEPB_SPMM_BULK=1; compiled and inspected, not yet measured -- see DESIGN.md) stages every V row with ONE
+// TMA bulk copy (cp.async.bulk global -> shared, completion counted in bytes on an mbarrier) instead of kt 16-byte LDGSTS
+// copies: the copies then bypass the LSU pipe this kernel is bound by.
+template <int VW, bool CA, bool DIAG, int CPT, bool BULK>
 __global__ void __launch_bounds__(256) spmm_tiled_kernel(int kt, unsigned kinv, int ldv, int ldz, int max_cols, int max_nnz,
                                                          const int4* __restrict__ tiles, const int* __restrict__ tile_cols,
                                                          const int* __restrict__ rowptr, const uint16_t* __restrict__ lidx,
@@ -219,7 +222,23 @@ __global__ void __launch_bounds__(256) spmm_tiled_kernel(int kt, unsigned kinv, 
     const int4 t0 = tiles[2 * blockIdx.x], t1 = tiles[2 * blockIdx.x + 1];
     const int row0 = t0.x, nrows = t0.y, ncols = t0.w, nz0 = t1.x, nnz = t1.y;
     const int tid = threadIdx.x, nth = blockDim.x;
-    {  // 1. the tile's rows of V: consecutive threads copy consecutive 16-byte pieces of one row
+    unsigned bar_s = 0;
+    if constexpr (BULK) {  // 1. the tile's rows of V, one bulk copy per row
+        bar_s = (unsigned)__cvta_generic_to_shared(sRp + 36);  // 8-byte mbarrier behind the row pointers
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::);  // the async proxy must see the initialised barrier
+        }
+        __syncthreads();
+        if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(ncols * kt * 16) : "memory");
+        const int* cols = tile_cols + t0.z;
+        for (int dcol = tid; dcol < ncols; dcol += nth) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sV[dcol * kt]);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(V + (size_t)cols[dcol] * ldv), "r"(kt * 16), "r"(bar_s)
+                         : "memory");
+        }
+    } else {  // 1. the tile's rows of V: consecutive threads copy consecutive 16-byte pieces of one row
         const int total = ncols * kt;
         const int* cols = tile_cols + t0.z;
         for (int e = tid; e < total; e += nth) {
@@ -257,7 +276,16 @@ __global__ void __launch_bounds__(256) spmm_tiled_kernel(int kt, unsigned kinv, 
     double2 acc[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) acc[j] = make_double2(0.0, 0.0);
-    asm volatile("cp.async.wait_group 0;" ::);
+    if constexpr (BULK) {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done)
+                         : "r"(bar_s), "r"(0)
+                         : "memory");
+    } else {
+        asm volatile("cp.async.wait_group 0;" ::);
+    }
     __syncthreads();
     int start = 0, end = 0;
     if (r < nrows) {
@@ -681,7 +709,7 @@ static int spmf_build_tiles(const nepb_spmf* h, int which) {
 }
 
 static size_t tiled_smem_bytes(const nepb_spmf::TileSet& T, int kt, int mw) {
-    return (size_t)T.max_cols * kt * 16 + (size_t)T.max_nnz * mw * 8 + (size_t)((T.max_nnz + 7) & ~7) * 2 + 34 * 4;
+    return (size_t)T.max_cols * kt * 16 + (size_t)T.max_nnz * mw * 8 + (size_t)((T.max_nnz + 7) & ~7) * 2 + 36 * 4 + 16;
 }
 
 template <int VW, bool CA, bool DIAG>
@@ -689,21 +717,29 @@ static int launch_tiled_vw(const nepb_spmf* h, const nepb_spmf::TileSet& T, int 
                            double2* Z, const CoefP& cp, const double2* cdiag) {
     const unsigned kinv = (unsigned)((0x100000000ULL + (unsigned)kt - 1) / (unsigned)kt);
     const size_t smem = tiled_smem_bytes(T, kt, DIAG ? VW : 2);
-#define NEPB_TILED(CPT_)                                                                                                              \
+    const bool bulk = getenv("NEPB_SPMM_BULK") && atoi(getenv("NEPB_SPMM_BULK")) != 0;  // read per call: tests toggle it
+#define NEPB_TILED_B(CPT_, BULK_)                                                                                                     \
     do {                                                                                                                              \
         static size_t attr_done = 0;                                                                                                  \
         if (smem > 48 * 1024 && smem > attr_done) {                                                                                   \
-            NEPB_CUDA(cudaFuncSetAttribute(spmm_tiled_kernel<VW, CA, DIAG, CPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            NEPB_CUDA(cudaFuncSetAttribute(spmm_tiled_kernel<VW, CA, DIAG, CPT_, BULK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)smem));                                                                               \
             attr_done = smem;                                                                                                         \
         }                                                                                                                             \
-        NEPB_LAUNCH((spmm_tiled_kernel<VW, CA, DIAG, CPT_>), (unsigned)T.ntiles, threads, smem, kt, kinv, ldv, ldz, T.max_cols,        \
+        NEPB_LAUNCH((spmm_tiled_kernel<VW, CA, DIAG, CPT_, BULK_>), (unsigned)T.ntiles, threads, smem, kt, kinv, ldv, ldz, T.max_cols, \
                     T.max_nnz, T.tiles.p, T.cols.p, h->d_rowptr.p, T.lidx.p, h->d_vals.p, V, Z, cp, cdiag, h->p);                     \
+    } while (0)
+#define NEPB_TILED(CPT_)                      \
+    do {                                      \
+        if (bulk) NEPB_TILED_B(CPT_, true);   \
+        else NEPB_TILED_B(CPT_, false);       \
     } while (0)
     if (kt <= 8) NEPB_TILED(1);
     else if (kt <= 16) NEPB_TILED(2);
     else if (kt <= 24) NEPB_TILED(3);
     else NEPB_TILED(4);
 #undef NEPB_TILED
+#undef NEPB_TILED_B
     return 1;
 }
 

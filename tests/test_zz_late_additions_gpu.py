@@ -1,5 +1,7 @@
-"""iar_chebyshev on the device (src/method_iar_chebyshev.jl, the first "next" row of SURVEY.md 8(f)) against the oracle.
-Own file, collected last: this path was added after the round's GPU budget allowed a full re-run of the suite."""
+"""Paths added after the round's GPU budget allowed a full re-run of the suite; own file, collected last.
+  * iar_chebyshev on the device (src/method_iar_chebyshev.jl, the first "next" row of SURVEY.md 8(f)) against the oracle
+    (checked step by step on the B200)
+  * the opt-in TMA bulk-copy variant of the tiled SpMM (compiled only)"""
 import numpy as np
 import pytest
 
@@ -53,3 +55,32 @@ def test_iar_chebyshev_device_matches_oracle():
     d100 = nepb200.B200SPMF.from_nep(nepb200.DEP([A0h, A1h], tvh))
     with pytest.raises(nepb200.NoConvergenceException):
         nepb200.iar_chebyshev_device(d100, sigma=0, neigs=8, maxit=10, tol=eps * 100, v=np.ones(100))
+
+
+def test_tiled_spmm_tma_bulk_variant():
+    """The opt-in variant of the tiled multi-column SpMM that stages every V row with one TMA bulk copy (cp.async.bulk +
+    mbarrier, NEPB_SPMM_BULK=1) must give the same product as the default cp.async variant, bit for bit (same summation
+    order), and agree with the oracle.  Compiled and inspected in round 1 (UBLKCP / SYNCS in the SASS), first run here."""
+    import os
+    import scipy.sparse as sp
+    from nepb200 import B200SPMF, Monomial
+    mats, _ = g.stencil_pep(48)
+    Av = [m.tocsc() for m in mats]
+    dnep = B200SPMF(Av, [Monomial(i) for i in range(4)])
+    onep = o.PEP(Av)
+    rng = np.random.default_rng(3)
+    lam = 0.3 + 0.2j
+    for k in (5, 8, 12):
+        V = rng.standard_normal((dnep.n, k)) + 1j * rng.standard_normal((dnep.n, k))
+        Z0 = dnep.compute_MM(lam * np.eye(k), V)
+        os.environ["NEPB_SPMM_BULK"] = "1"
+        try:
+            Z1 = dnep.compute_MM(lam * np.eye(k), V)
+            lams = rng.standard_normal(k) + 1j * rng.standard_normal(k)
+            Zd = dnep.compute_MM(np.diag(lams), V)
+        finally:
+            del os.environ["NEPB_SPMM_BULK"]
+        assert np.array_equal(Z0, Z1)
+        Zo = sp.csc_matrix(o.compute_Mder(onep, lam)) @ V
+        assert np.linalg.norm(Z1 - Zo) <= 1e-12 * np.linalg.norm(Zo)
+        assert np.linalg.norm(Zd - o.compute_MM(onep, np.diag(lams), V)) <= 1e-12 * np.linalg.norm(Zd)
