@@ -277,12 +277,14 @@ __global__ void __launch_bounds__(256) spmm_tiled_kernel(int kt, unsigned kinv, 
 #pragma unroll
     for (int j = 0; j < CPT; ++j) acc[j] = make_double2(0.0, 0.0);
     if constexpr (BULK) {
-        unsigned done = 0;
-        while (!done)
+        unsigned done = 0, spins = 0;
+        while (!done) {
+            if (++spins > (1u << 26)) asm volatile("trap;");  // a lost transaction must fail the launch, never hang the device
             asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                          : "=r"(done)
                          : "r"(bar_s), "r"(0)
                          : "memory");
+        }
     } else {
         asm volatile("cp.async.wait_group 0;" ::);
     }
