@@ -466,11 +466,8 @@ def nleigs(nep, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf,), maxdgr
                     warnings.warn("NLEIGS: Linearization not converged after %d iterations" % maxdgr)
         l = k - N if static else k
         if not static or (static and not expand):
-            grow(kn, l + 1 if l + 1 > V.shape[1] else V.shape[1])
-            if l + 1 > V.shape[1] - 0 and False:
-                pass
-            if V.shape[1] < l + 1:
-                grow(kn, min(kmax + 1, V.shape[1] + blksize))
+            # V holds l + 1 vectors of kn rows after this step; columns are added a block at a time (:180-203)
+            grow(kn, V.shape[1] if V.shape[1] >= l + 1 else min(kmax + 1, max(l + 1, V.shape[1] + blksize)))
             t = np.zeros(l, dtype=np.complex128)
             t[l - 1] = 1
             wc = V[:kn, l - 1].copy()
@@ -487,8 +484,6 @@ def nleigs(nep, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf,), maxdgr
             H[:l, l - 1] = h
             K[:l, l - 1] = h * sigma[k] + t
             K[l, l - 1] = H[l, l - 1] * sigma[k]
-            if V.shape[1] < l + 1:
-                grow(kn, min(kmax + 1, V.shape[1] + blksize))
             V[:kn, l] = w
 
         def check_convergence(all_):
