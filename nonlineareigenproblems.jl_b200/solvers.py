@@ -407,3 +407,110 @@ def contour_block_SS(nep: B200SPMF, U=None, V=None, sigma=0.0, radius=1.0, N=100
     if return_moments:
         return lam, Vec, Shat, mprime
     return lam, Vec
+
+
+# ---------------------------------------------------------------------------------------------
+# infbilanczos (src/method_infbilanczos.jl:33-244)
+# ---------------------------------------------------------------------------------------------
+def _taylor_hankel_blocks(nep, sigma, size):
+    """Coefficient blocks of the bilinear form of infinite bi-Lanczos: C_t[i, j] = f_t^(i+j+1)(sigma) / (i+j+1)!, i, j < size,
+    one size x size column-major block per SPMF term (GENERAL mode of the fused product)."""
+    T = np.stack([f.taylor(sigma, 2 * size + 1) for f in nep.fi])
+    idx = np.arange(size)[:, None] + np.arange(size)[None, :] + 1
+    return np.stack([np.asfortranarray(T[t][idx]).reshape(-1, order="F") for t in range(len(nep.fi))])
+
+
+def left_right_scalar_prod(nep, At, B, ma, mb, sigma):
+    """left_right_scalar_prod (:227-244): sum_j At[:, j]' * (-sum_i M^(i+j-1)(sigma) B[:, i] / (i+j-1)!).  The reference runs
+    the 'nasty double loop' of ma compute_Mlincomb calls (O(m^3 n) over the whole iteration); here it is ONE fused multi-term
+    product Z = sum_t A_t (B C_t) with Hankel blocks of Taylor coefficients, followed by a dense inner product."""
+    size = max(ma, mb)
+    Z = nep.apply(_lib.COEF_GENERAL, B[:, :size], _taylor_hankel_blocks(nep, sigma, size), size)
+    # columns of B beyond mb are zero by construction of the recurrences; columns of Z beyond ma are not used
+    return -np.sum(np.conj(At[:, :ma]) * Z[:, :ma])
+
+
+def infbilanczos(nep, nept, maxit=30, linsolvercreator=None, linsolvertcreator=None, v=None, u=None, tol=1e-12, neigs=5, errmeasure=None,
+                 sigma=0.0, gamma=1, check_error_every=1):
+    """Infinite bi-Lanczos for a device operator `nep` and its transposed problem `nept` (M(conj(lam))^H as its own operator
+    with its own device LU, exactly as the reference takes it).  Host recurrences as in the reference (including its quirks: the
+    left start vector is overwritten by the right one, :55, and gamma is unused); every O(n) product is a fused device SpMM.
+    Returns (lam, Q, TT)."""
+    n = nep.n
+    sigma = complex(sigma)
+    v = np.asarray(v, dtype=np.complex128)
+    u = v.copy()
+    errmeasure = errmeasure or DefaultErrmeasure(nep)
+    M0inv = (linsolvercreator or B200LinSolverCreator()).create_linsolver(nep, sigma)
+    M0Tinv = (linsolvertcreator or B200LinSolverCreator()).create_linsolver(nept, sigma)
+    m = maxit
+
+    def dmul(op, s, X):  # sum_i M^(i)(s) X[:, i-1] / i!  == compute_Mlincomb(op, s, X * Dk, ones, 1)
+        k = X.shape[1]
+        T = np.stack([f.taylor(s, k + 1)[1:] for f in op.fi])  # p x k: block t is the k-vector of Taylor coefficients 1..k
+        return op.apply(_lib.COEF_GENERAL, X, T, 1)[:, 0]
+
+    qt = M0Tinv.lin_solve(u)
+    q = v / np.vdot(qt, dmul(nep, sigma, v.reshape(n, 1)))
+    Z = lambda cols: np.zeros((n, cols), dtype=np.complex128, order="F")  # noqa: E731
+    Q0, Qt0, Q1, Qt1 = Z(m + 1), Z(m + 1), Z(m + 1), Z(m + 1)
+    R1, Rt1, R2, Rt2 = Z(m + 1), Z(m + 1), Z(m + 1), Z(m + 1)
+    R1[:, 0], Rt1[:, 0] = q, qt
+    Q_basis = Z(m + 1)
+    alpha = np.zeros(m + 1, dtype=np.complex128)
+    beta = np.zeros(m + 1, dtype=np.complex128)
+    gam = np.zeros(m + 1, dtype=np.complex128)
+    lam, Q, err = np.zeros(0, dtype=np.complex128), Z(0), np.zeros(0)
+    for k in range(1, m + 1):
+        omega = np.conj(left_right_scalar_prod(nep, Rt1, R1, k, k, sigma))
+        beta[k - 1] = np.sqrt(abs(omega))
+        gam[k - 1] = np.conj(omega) / beta[k - 1]
+        Q1[:, :k] = R1[:, :k] / beta[k - 1]
+        Qt1[:, :k] = Rt1[:, :k] / np.conj(gam[k - 1])
+        Q_basis[:, k - 1] = Q1[:, 0]
+        z2 = -M0inv.lin_solve(dmul(nep, sigma, Q1[:, :k]))
+        zt2 = -M0Tinv.lin_solve(dmul(nept, np.conj(sigma), Qt1[:, :k]))
+        R2[:, 0] = z2
+        R2[:, 1:k + 1] = Q1[:, :k]
+        Rt2[:, 0] = zt2
+        Rt2[:, 1:k + 1] = Qt1[:, :k]
+        if k > 1:
+            R2[:, :k - 1] -= gam[k - 1] * Q0[:, :k - 1]
+            Rt2[:, :k - 1] -= np.conj(beta[k - 1]) * Qt0[:, :k - 1]
+        alpha[k] = left_right_scalar_prod(nep, Qt1, R2, k, k + 1, sigma)
+        R2[:, :k] -= alpha[k] * Q1[:, :k]
+        Rt2[:, :k] -= np.conj(alpha[k]) * Qt1[:, :k]
+        R1, R2 = R2, R1
+        R2[:] = 0
+        Rt1, Rt2 = Rt2, Rt1
+        Rt2[:] = 0
+        Q0, Q1 = Q1, Q0
+        Q1[:] = 0
+        Qt0, Qt1 = Qt1, Qt0
+        Qt1[:] = 0
+        if k % check_error_every == 0 or k == m:
+            omega = left_right_scalar_prod(nep, Rt1, R1, k + 1, k + 1, sigma)
+            beta[k] = np.sqrt(abs(omega))
+            gam[k] = np.conj(omega) / beta[k]
+            TT = np.zeros((k + 1, k + 1), dtype=np.complex128)  # spdiagm(-1 => beta, 0 => alpha, 1 => gamma), k entries each
+            i = np.arange(k)
+            TT[i, i] = alpha[1:k + 1]
+            TT[i + 1, i] = beta[1:k + 1]
+            TT[i, i + 1] = gam[1:k + 1]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                D, Zv = np.linalg.eig(TT)
+                lam = sigma + 1.0 / D
+            Q = Q_basis[:, :k + 1] @ Zv
+            err = np.array([errmeasure.estimate_error(lam[s], Q[:, s]) if np.isfinite(lam[s]) else np.inf for s in range(len(lam))])
+            conv_eig = int(np.count_nonzero(err < tol))
+            idx = np.argsort(err[:k], kind="stable")
+            err = err[idx]
+            if conv_eig >= neigs or k == m:
+                nrof = int(min(len(lam), neigs, conv_eig))
+                lam = lam[idx[:nrof]]
+                Q = Q[:, idx[:nrof]]
+                if nrof:
+                    Q = Q / np.linalg.norm(Q, axis=0)[None, :]
+                if conv_eig >= neigs or neigs == np.inf:
+                    return lam, Q, TT
+    raise NoConvergenceException(lam, Q, err, "Number of iterations exceeded. maxit=%d." % maxit)

@@ -16,6 +16,8 @@ The Beyn probe matrix is an argument: the reference draws it with Julia's randn 
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as sla
@@ -544,3 +546,103 @@ def iar_chebyshev(nep, maxit=30, linsolvercreator=None, tol=np.finfo(float).eps 
     lam = lam[:min(len(lam), conv_eig)]
     Q = Q[:, :min(Q.shape[1], conv_eig)]
     return lam, Q, err[:k, :], V[:, :k], H[:k, :k]
+
+
+# --------------------------------------------------------------------------------------------
+# infbilanczos (src/method_infbilanczos.jl)
+# --------------------------------------------------------------------------------------------
+def left_right_scalar_prod(nep, nept, At, B, ma, mb, sigma):
+    """method_infbilanczos.jl:227-244: sum_j At[:, j]' * (-sum_i M^(j+i-1)(sigma) B[:, i] / (j+i-1)!), the bilinear form of the
+    infinite bi-Lanczos method (the double loop the reference calls 'nasty': O(m^3 n))."""
+    c = 0.0
+    for j in range(1, ma + 1):
+        dd = 1.0 / np.array([math.factorial(t) for t in range(j, j + mb)], dtype=np.float64)
+        XX = B[:, :mb] * dd[None, :]
+        z = -o.compute_Mlincomb(nep, sigma, XX, np.ones(mb), j)
+        c = c + np.vdot(At[:, j - 1], z)
+    return c
+
+
+def infbilanczos(nep, nept, maxit=30, linsolvercreator=None, linsolvertcreator=None, v=None, u=None, tol=1e-12, neigs=5, errmeasure=None,
+                 sigma=0.0, gamma=1, check_error_every=1):
+    """method_infbilanczos.jl:33-225.  `nept` is the transposed problem M(conj(lam))^H given as its own NEP (the reference takes
+    it, and a second linear solver for it, as arguments).  As in the reference, the left starting vector is overwritten by the
+    right one (`u=Vector{T}(v)`, :55) and gamma is unused.  Returns (lam, Q, TT)."""
+    n = nep.n
+    sigma = complex(sigma)
+    v = np.asarray(v, dtype=np.complex128)
+    u = v.copy()
+    errmeasure = errmeasure or default_errmeasure(nep)
+    M0inv = (linsolvercreator or FactorizeLinSolverCreator()).create_linsolver(nep, sigma)
+    M0Tinv = (linsolvertcreator or FactorizeLinSolverCreator()).create_linsolver(nept, sigma)
+    m = maxit
+    qt = M0Tinv.lin_solve(u)
+    q = v / np.vdot(qt, o.compute_Mlincomb(nep, sigma, v.reshape(n, 1), np.ones(1), 1))
+    Z = lambda cols: np.zeros((n, cols), dtype=np.complex128)  # noqa: E731
+    Q0, Qt0, Q1, Qt1 = Z(m), Z(m), Z(m), Z(m)
+    R1, Rt1, R2, Rt2 = Z(m + 1), Z(m + 1), Z(m + 1), Z(m + 1)
+    R1[:, 0], Rt1[:, 0] = q, qt
+    Z2, Zt2 = Z(m), Z(m)
+    Q_basis = Z(m + 1)
+    alpha = np.zeros(m + 1, dtype=np.complex128)
+    beta = np.zeros(m + 1, dtype=np.complex128)
+    gam = np.zeros(m + 1, dtype=np.complex128)
+    lam = np.zeros(0, dtype=np.complex128)
+    Q = Z(0)
+    err = np.zeros(0)
+    TT = np.zeros((0, 0), dtype=np.complex128)
+    for k in range(1, m + 1):
+        omega = np.conj(left_right_scalar_prod(nep, nept, Rt1, R1, k, k, sigma))
+        beta[k - 1] = np.sqrt(abs(omega))
+        gam[k - 1] = np.conj(omega) / beta[k - 1]
+        Q1[:, :k] = R1[:, :k] / beta[k - 1]
+        Qt1[:, :k] = Rt1[:, :k] / np.conj(gam[k - 1])
+        Q_basis[:, k - 1] = Q1[:, 0]
+        Dk = 1.0 / np.array([math.factorial(t) for t in range(1, k + 1)], dtype=np.float64)
+        Z2[:, k - 1] = -M0inv.lin_solve(o.compute_Mlincomb(nep, sigma, Q1[:, :k] * Dk[None, :], np.ones(k), 1))
+        Zt2[:, k - 1] = -M0Tinv.lin_solve(o.compute_Mlincomb(nept, np.conj(sigma), Qt1[:, :k] * Dk[None, :], np.ones(k), 1))
+        R2[:, 0] = Z2[:, k - 1]
+        R2[:, 1:k + 1] = Q1[:, :k]
+        if k > 1:
+            R2[:, :k - 1] -= gam[k - 1] * Q0[:, :k - 1]
+        Rt2[:, 0] = Zt2[:, k - 1]
+        Rt2[:, 1:k + 1] = Qt1[:, :k]
+        if k > 1:
+            Rt2[:, :k - 1] -= np.conj(beta[k - 1]) * Qt0[:, :k - 1]
+        alpha[k] = left_right_scalar_prod(nep, nept, Qt1, R2, k, k + 1, sigma)
+        R2[:, :k] -= alpha[k] * Q1[:, :k]
+        Rt2[:, :k] -= np.conj(alpha[k]) * Qt1[:, :k]
+        R1, R2 = R2, R1
+        R2[:] = 0
+        Rt1, Rt2 = Rt2, Rt1
+        Rt2[:] = 0
+        Q0, Q1 = Q1, Q0
+        Q1[:] = 0
+        Qt0, Qt1 = Qt1, Qt0
+        Qt1[:] = 0
+        if k % check_error_every == 0 or k == m:
+            omega = left_right_scalar_prod(nep, nept, Rt1, R1, k + 1, k + 1, sigma)
+            beta[k] = np.sqrt(abs(omega))
+            gam[k] = np.conj(omega) / beta[k]
+            a0, b0, g0 = alpha[1:k + 1], beta[1:k + 1], gam[1:k + 1]
+            TT = np.zeros((k + 1, k + 1), dtype=np.complex128)  # spdiagm(-1 => b0, 0 => a0, 1 => g0): k entries on each diagonal
+            idxk = np.arange(k)
+            TT[idxk, idxk] = a0[:k]
+            TT[idxk + 1, idxk] = b0[:k]
+            TT[idxk, idxk + 1] = g0[:k]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                D, Zv = np.linalg.eig(TT)
+                lam = sigma + 1.0 / D
+            Q = Q_basis[:, :k + 1] @ Zv
+            err = np.array([errmeasure(lam[s], Q[:, s]) if np.isfinite(lam[s]) else np.inf for s in range(len(lam))], dtype=float)
+            conv_eig = int(np.count_nonzero(err < tol))
+            idx = np.argsort(err[:k], kind="stable")
+            err = err[idx]
+            if conv_eig >= neigs or k == m:
+                nrof = int(min(len(lam), neigs, conv_eig))
+                lam = lam[idx[:nrof]]
+                Q = Q[:, idx[:nrof]]
+                Q = Q / np.linalg.norm(Q, axis=0)[None, :] if nrof else Q
+                if conv_eig >= neigs or neigs == np.inf:
+                    return lam, Q, TT
+    raise NoConvergenceException(lam, Q, err, "Number of iterations exceeded. maxit=%d." % maxit)

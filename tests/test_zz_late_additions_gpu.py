@@ -1,6 +1,7 @@
 """Paths added after the round's GPU budget allowed a full re-run of the suite; own file, collected last.
   * iar_chebyshev on the device (src/method_iar_chebyshev.jl, the first "next" row of SURVEY.md 8(f)) against the oracle
     (checked step by step on the B200)
+  * infbilanczos on the device (host recurrences checked on the CPU against the reference's literal, tests/test_infbilanczos.py)
   * the opt-in TMA bulk-copy variant of the tiled SpMM (compiled only)"""
 import os
 
@@ -57,6 +58,38 @@ def test_iar_chebyshev_device_matches_oracle():
     d100 = nepb200.B200SPMF.from_nep(nepb200.DEP([A0h, A1h], tvh))
     with pytest.raises(nepb200.NoConvergenceException):
         nepb200.iar_chebyshev_device(d100, sigma=0, neigs=8, maxit=10, tol=eps * 100, v=np.ones(100))
+
+
+def test_infbilanczos_device_matches_reference_literal():
+    """infbilanczos (src/method_infbilanczos.jl) with both operators and both factorisations on the device: the tridiagonal
+    matrix of test/infbilanczos.jl:19-24 (literal, 1e-10), three eigenpairs with residual < 1e-7, the oracle's eigenvalues.
+    The host recurrences are checked on the CPU with a stand-in operator (tests/test_infbilanczos.py); this adds the ABI calls:
+    GENERAL-mode fused products with square Hankel coefficient blocks and with k x 1 blocks, two device LUs."""
+    import scipy.sparse as sp
+    from nepb200 import B200SPMF, Monomial, ONE, Exp
+    tstar = np.array([[-1.665117675679600, 5.780562035399026, 0, 0],
+                      [5.780562035399026, 11.562308485001218, -18.839546184493731, 0],
+                      [0, 18.839546184493734, -15.213756300995186, 9.788512505128466],
+                      [0, 0, 9.788512505128464, -0.120825360586847]])
+    A0, A1 = g.load_qdep0_matrices()
+    n = A0.shape[0]
+    mI = -sp.identity(n, format="csc")
+    fi = [Monomial(2), ONE, Exp(-1.0)]
+    dnep = B200SPMF([mI, A0, A1], fi)
+    dnept = B200SPMF([mI, sp.csc_matrix(A0.T), sp.csc_matrix(A1.T)], fi)
+    onep = o.nep_gallery("qdep0")
+    onept = o.SPMF_NEP([sp.csc_matrix(A.T) for A in onep.A], onep.fi)
+    kw = dict(maxit=40, neigs=3, sigma=0, v=np.ones(n), u=np.ones(n), check_error_every=3, tol=1e-7)
+    lam, V, T = nepb200.infbilanczos(dnep, dnept, errmeasure=nepb200.ResidualErrmeasure(dnep), **kw)
+    lo, Vo, To = osol.infbilanczos(onep, onept, errmeasure=o.residual_errmeasure(onep), **kw)
+    n0 = min(4, len(lam))
+    assert len(lam) == len(lo) == 3
+    assert np.linalg.norm(tstar[:n0, :n0] - T[:n0, :n0], 2) < 1e-10
+    assert np.abs(T[:10, :10] - To[:10, :10]).max() < 1e-8 * np.abs(To).max()
+    for x in lam:
+        assert np.min(np.abs(lo - x)) < 1e-8
+    for l, q in zip(lam, V.T):
+        assert np.linalg.norm(o.compute_Mlincomb(onep, l, q)) < 1e-7
 
 
 @pytest.mark.skipif(not os.environ.get("NEPB_RUN_UNVALIDATED"), reason="kernel variant compiled but never run on a device yet: "
