@@ -328,3 +328,78 @@ class B200SPMF:
 
     def compute_resnorm(self, lam, v):
         return float(np.linalg.norm(self.compute_Mlincomb(lam, v)))
+
+
+# ---------------------------------------------------------------------------------------------
+# projection W^H M(lam) V (Proj_SPMF_NEP, NEPTypes.jl:652-800; create_proj_NEP :600-640)
+# ---------------------------------------------------------------------------------------------
+class B200ProjSPMF:
+    """Proj_SPMF_NEP for a device operator: N(lam) = sum_i f_i(lam) B_i with B_i = W^H A_i V.
+    All A_i V come from ONE fused pass over the operator (GENERAL mode with selector blocks: output columns i*k..(i+1)*k-1
+    are A_i V), instead of p sparse products that each re-read their own index arrays (:733-736); the k x k matrices B_i
+    and the compute functions of the projected problem live on the host, as in the reference (it builds a small dense
+    SPMF_NEP and delegates to it, :793-800)."""
+
+    def __init__(self, nep: B200SPMF, maxsize=None):
+        self.orgnep = nep
+        self.fi = nep.get_fv()
+        self.maxsize = maxsize
+        self.B = [np.zeros((0, 0), dtype=np.complex128) for _ in self.fi]
+
+    def _terms_times(self, V):
+        """[A_1 V, ..., A_p V] as an n x (p k) array from one fused product."""
+        V = np.asarray(V, dtype=np.complex128)
+        if V.ndim == 1:
+            V = V.reshape(-1, 1)
+        k, p = V.shape[1], len(self.fi)
+        blocks = np.zeros((p, k, p * k), dtype=np.complex128)
+        for t in range(p):
+            blocks[t, np.arange(k), t * k + np.arange(k)] = 1.0  # C_t selects term t into its own column window
+        flat = np.stack([np.asfortranarray(blocks[t]).reshape(-1, order="F") for t in range(p)])
+        return self.orgnep.apply(_lib.COEF_GENERAL, V, flat, p * k), k
+
+    def set_projectmatrices(self, W, V):
+        W = np.asarray(W, dtype=np.complex128)
+        Z, k = self._terms_times(V)
+        if self.maxsize is not None and k > self.maxsize:
+            raise ValueError("projection larger than the preallocated size")  # the @assert of :729
+        WT = W.conj().T
+        self.B = [WT @ Z[:, t * k:(t + 1) * k] for t in range(len(self.fi))]
+        return self
+
+    def expand_projectmatrices(self, Wnew, Vnew):
+        """Only the last row and column of every B_i are new (:774-791): two fused passes with 1 and k+1 columns."""
+        Wnew, Vnew = np.asarray(Wnew, dtype=np.complex128), np.asarray(Vnew, dtype=np.complex128)
+        k = Vnew.shape[1] - 1
+        Zv, _ = self._terms_times(Vnew[:, -1])        # A_i v
+        Zr, kk = self._terms_times(Vnew[:, :k + 1])   # A_i [V v] for the new row
+        WT = Wnew[:, :k].conj().T
+        w = Wnew[:, -1].conj()
+        out = []
+        for t, Bold in enumerate(self.B):
+            Bn = np.zeros((k + 1, k + 1), dtype=np.complex128)
+            Bn[:k, :k] = Bold[:k, :k]
+            Bn[:k, k] = WT @ Zv[:, t]
+            Bn[k, :] = w @ Zr[:, t * kk:(t + 1) * kk]
+            out.append(Bn)
+        self.B = out
+        return self
+
+    # the projected problem is a k x k dense SPMF evaluated on the host (:793-800)
+    def compute_Mder(self, lam, der=0):
+        return sum(f.derivative(lam, der) * B for f, B in zip(self.fi, self.B))
+
+    def compute_MM(self, S, V):
+        S = np.atleast_2d(np.asarray(S, dtype=np.complex128))
+        return sum(B @ np.asarray(V, dtype=np.complex128) @ np.asarray(f(S), dtype=np.complex128) for f, B in zip(self.fi, self.B))
+
+    def compute_Mlincomb(self, lam, V, a=None):
+        V = np.asarray(V, dtype=np.complex128)
+        Vm = V.reshape(V.shape[0], -1)
+        k = Vm.shape[1]
+        a = np.ones(k, dtype=np.complex128) if a is None else np.asarray(a, dtype=np.complex128)
+        return sum(B @ (Vm @ (a * np.array([f.derivative(lam, j) for j in range(k)]))) for f, B in zip(self.fi, self.B))
+
+
+def create_proj_NEP(nep: B200SPMF, maxsize=None):
+    return B200ProjSPMF(nep, maxsize)

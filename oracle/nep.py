@@ -182,6 +182,49 @@ class DerSPMF:
         self.fD = np.stack([np.asarray(f(SS))[:, 0] for f in fv], axis=1)
 
 
+class Proj_SPMF_NEP:
+    """NEPTypes.jl:652-800: N(lam) = W^H M(lam) V for an AbstractSPMF, kept as the small dense SPMF sum_i f_i(lam) (W^H A_i V).
+    The compute functions of the projected problem are those of `nep_proj` (delegation, :793-800)."""
+
+    def __init__(self, nep, maxsize=None):
+        self.orgnep = nep
+        self.orgnep_Av = get_Av(nep)
+        self.orgnep_fv = get_fv(nep)
+        self.maxsize = maxsize
+        self.B = [np.zeros((0, 0), dtype=np.complex128) for _ in self.orgnep_Av]
+        self.nep_proj = None
+
+    def set_projectmatrices(self, W, V):
+        """:723-740."""
+        W, V = np.asarray(W), np.asarray(V)
+        if self.maxsize is not None:
+            assert V.shape[1] <= self.maxsize
+        WT = W.conj().T
+        self.B = [np.asarray(WT @ _dot(A, V), dtype=np.complex128) for A in self.orgnep_Av]
+        self.nep_proj = SPMF_NEP(self.B, self.orgnep_fv)
+
+    def expand_projectmatrices(self, Wnew, Vnew):
+        """:774-791: only the new last row and column of every W^H A_i V are computed."""
+        Wnew, Vnew = np.asarray(Wnew), np.asarray(Vnew)
+        k = Vnew.shape[1] - 1
+        w, v = Wnew[:, -1], Vnew[:, -1]
+        WT = Wnew[:, :k].conj().T
+        out = []
+        for A, Bold in zip(self.orgnep_Av, self.B):
+            Bn = np.zeros((k + 1, k + 1), dtype=np.complex128)
+            Bn[:k, :k] = Bold[:k, :k]
+            Bn[:k, k] = WT @ _dot(A, v)
+            Bn[k, :] = w.conj() @ _dot(A, Vnew[:, :k + 1])
+            out.append(Bn)
+        self.B = out
+        self.nep_proj = SPMF_NEP(self.B, self.orgnep_fv)
+
+
+def create_proj_NEP(nep, maxsize=None):
+    """NEPTypes.jl:600-640 for the SPMF case."""
+    return Proj_SPMF_NEP(nep, maxsize)
+
+
 def size(nep, d=None):
     return (nep.n, nep.n) if d is None else nep.n
 
@@ -435,6 +478,10 @@ def nep_gallery(name, *params):
     if name == "dep0":
         A0, A1, tauv = g.dep0_matrices(*params)
         return DEP([A0, A1], tauv)
+    if name == "pep0":  # basic_random_examples.jl:36-44
+        n = params[0] if params else 200
+        rng = g.MSWS_RNG()
+        return PEP([g.gen_rng_mat(rng, n, n) for _ in range(3)])
     if name == "dep0_tridiag":
         A0, A1, tauv = g.dep0_tridiag_matrices(*params)
         return DEP([A0, A1], tauv)

@@ -1,0 +1,48 @@
+"""NumPy stand-ins with the contract of the device operator (`apply` in GENERAL mode), its solver creator and its residual
+error measure: they let the CPU tests run the product's HOST recurrences (infbilanczos, projection) against the reference's
+literals; the ABI calls behind the real objects are covered by the GPU tests.  Test infrastructure only."""
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as sla
+
+from nepb200 import _lib
+
+
+class HostOperator:
+    """NumPy stand-in for B200SPMF with the same `apply` contract (GENERAL mode only)."""
+
+    def __init__(self, A, fi):
+        self.A, self.fi, self.p, self.n = A, fi, len(A), A[0].shape[0]
+
+    def get_fv(self):
+        return self.fi
+
+    def get_Av(self):
+        return self.A
+
+    def apply(self, mode, V, blocks, q):
+        assert mode == _lib.COEF_GENERAL
+        V = np.asarray(V, dtype=np.complex128)
+        k = V.shape[1]
+        blocks = np.asarray(blocks, dtype=np.complex128).reshape(self.p, -1)
+        return sum(self.A[t] @ (V @ blocks[t].reshape(k, q, order="F")) for t in range(self.p))
+
+
+class HostSolverCreator:
+    def create_linsolver(self, op, lam):
+        M = sum(complex(f(complex(lam))) * A for f, A in zip(op.fi, op.A))
+        lu = sla.splu(sp.csc_matrix(M, dtype=np.complex128))
+
+        class S:
+            def lin_solve(self, b, tol=0):
+                return lu.solve(np.asarray(b, dtype=np.complex128))
+        return S()
+
+
+class HostResidual:
+    def __init__(self, op):
+        self.op = op
+
+    def estimate_error(self, lam, v):
+        M = sum(complex(f(complex(lam))) * A for f, A in zip(self.op.fi, self.op.A))
+        return float(np.linalg.norm(M @ v) / np.linalg.norm(v))

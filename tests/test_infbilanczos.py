@@ -46,38 +46,7 @@ def test_oracle_infbilanczos_reference_literals():
     assert len(lam) == 3 and np.linalg.norm(o.compute_Mlincomb(dep, lam[0], V[:, 0])) < 1e-12
 
 
-class _HostOperator:
-    """NumPy stand-in for B200SPMF with the same `apply` contract (GENERAL mode only)."""
-
-    def __init__(self, A, fi):
-        self.A, self.fi, self.p, self.n = A, fi, len(A), A[0].shape[0]
-
-    def apply(self, mode, V, blocks, q):
-        assert mode == _lib.COEF_GENERAL
-        V = np.asarray(V, dtype=np.complex128)
-        k = V.shape[1]
-        blocks = np.asarray(blocks, dtype=np.complex128).reshape(self.p, -1)
-        return sum(self.A[t] @ (V @ blocks[t].reshape(k, q, order="F")) for t in range(self.p))
-
-
-class _HostSolverCreator:
-    def create_linsolver(self, op, lam):
-        M = sum(complex(f(complex(lam))) * A for f, A in zip(op.fi, op.A))
-        lu = sla.splu(sp.csc_matrix(M, dtype=np.complex128))
-
-        class S:
-            def lin_solve(self, b, tol=0):
-                return lu.solve(np.asarray(b, dtype=np.complex128))
-        return S()
-
-
-class _HostResidual:
-    def __init__(self, op):
-        self.op = op
-
-    def estimate_error(self, lam, v):
-        M = sum(complex(f(complex(lam))) * A for f, A in zip(self.op.fi, self.op.A))
-        return float(np.linalg.norm(M @ v) / np.linalg.norm(v))
+from host_standin import HostOperator as _HostOperator, HostSolverCreator as _HostSolverCreator, HostResidual as _HostResidual  # noqa: E402
 
 
 def test_product_infbilanczos_host_recurrences_match_reference_literal():

@@ -2,6 +2,7 @@
   * iar_chebyshev on the device (src/method_iar_chebyshev.jl, the first "next" row of SURVEY.md 8(f)) against the oracle
     (checked step by step on the B200)
   * infbilanczos on the device (host recurrences checked on the CPU against the reference's literal, tests/test_infbilanczos.py)
+  * Proj_SPMF_NEP on the device operator (host logic checked in tests/test_projection.py)
   * the opt-in TMA bulk-copy variant of the tiled SpMM (compiled only)"""
 import os
 
@@ -90,6 +91,29 @@ def test_infbilanczos_device_matches_reference_literal():
         assert np.min(np.abs(lo - x)) < 1e-8
     for l, q in zip(lam, V.T):
         assert np.linalg.norm(o.compute_Mlincomb(onep, l, q)) < 1e-7
+
+
+def test_projection_device_matches_oracle():
+    """Proj_SPMF_NEP on the device operator: W^H A_i V for all four gun terms from one fused pass,
+    set / expand, against the oracle restatement (host logic verified on the CPU in tests/test_projection.py)."""
+    from nepb200 import B200SPMF, ONE, IDENTITY, PowShift
+    K, M, W1, W2 = g.load_gun_matrices()
+    dnep = B200SPMF([K, -M, W1, W2], [ONE, IDENTITY, PowShift(0.5, 0.0, 1j), PowShift(0.5, 108.8774 ** 2, 1j)])
+    onep = o.nep_gallery("nlevp_native_gun")
+    rng = np.random.default_rng(8)
+    n, k = dnep.n, 6
+    W = rng.standard_normal((n, k)) + 1j * rng.standard_normal((n, k))
+    V = rng.standard_normal((n, k)) + 1j * rng.standard_normal((n, k))
+    po, pp = o.create_proj_NEP(onep), nepb200.create_proj_NEP(dnep)
+    po.set_projectmatrices(W[:, :k - 1], V[:, :k - 1])
+    pp.set_projectmatrices(W[:, :k - 1], V[:, :k - 1])
+    po.expand_projectmatrices(W, V)
+    pp.expand_projectmatrices(W, V)
+    for Bo, Bp in zip(po.B, pp.B):
+        assert np.linalg.norm(Bo - Bp) <= 1e-12 * max(np.linalg.norm(Bo), 1e-300)
+    lam = 250.0 ** 2 + 3j
+    No = W.conj().T @ (o.compute_Mder(onep, lam) @ V)
+    assert np.linalg.norm(pp.compute_Mder(lam) - No) <= 1e-12 * np.linalg.norm(No)
 
 
 @pytest.mark.skipif(not os.environ.get("NEPB_RUN_UNVALIDATED"), reason="kernel variant compiled but never run on a device yet: "
