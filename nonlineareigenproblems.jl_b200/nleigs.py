@@ -134,8 +134,8 @@ def _device_backslash(nep, cache, basis, l, wcb, bwb, zb, tb, sigma, k, beta, N,
     solve_block(solver.lu, tb, 0, 1, bwb, 0, alpha=1.0 / beta[0])
     block_gemm(bwb, 0, m, CW, wcb, 0)
     check(lib.nepb_iar_pack(wcb._h, 0, m, n, basis.b._h, l))
-    if not add_to_cache:
-        solver.lu.close()
+    if not add_to_cache and cache.solvers.get(complex(shift)) is not solver:
+        solver.lu.close()  # a one-off factorisation (linsolvercache.jl:21-23); never a cached one
 
 
 def nleigs(nep: B200SPMF, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf,), maxdgr=100, minit=20, maxit=200, tol=1e-10,
@@ -193,7 +193,7 @@ def nleigs(nep: B200SPMF, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf
     cache = DeviceLinSolverCache(nep, umfpack_refinements)
     first = cache.get(sigma[0], reusefact == 2)
     v = first.lin_solve(v / np.linalg.norm(v))
-    if reusefact != 2:
+    if cache.solvers.get(complex(sigma[0])) is not first:
         first.lu.close()
     cols = kmax + 1
     basis = _Basis(n, cols)
