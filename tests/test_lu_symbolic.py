@@ -61,3 +61,31 @@ def test_grid_stencil_pattern():
     P = S[np.ix_(perm, perm)]
     pref, ccref = _etree_counts_dense(P)
     assert np.array_equal(parent, pref) and np.array_equal(cc, ccref)
+
+
+def test_fast_and_legacy_symbolic_algorithms_agree(monkeypatch):
+    """Column counts (Gilbert-Ng-Peyton skeleton counting) and front row structures (supernodal merge of the children's update
+    rows) replace the O(nnz(L)) row-subtree traversals; NEPB_LU_CHECK=1 makes the library compute both variants and fail unless
+    the column counts and every front's row list are identical.  Also the legacy variant alone (NEPB_LU_LEGACY=1) must give
+    the same public results."""
+    from nepb200 import synthetic
+    rng = np.random.default_rng(1)
+    pats = [sp.random(n, n, d, random_state=int(rng.integers(1 << 30)), format="csc") + sp.identity(n, format="csc")
+            for n, d in ((1, 1.0), (2, 1.0), (9, 0.3), (60, 0.06), (300, 0.01), (2500, 0.0015), (3000, 0.0002))]
+    K, M, W1, W2 = g.load_gun_matrices()
+    pats.append((abs(K) + abs(M) + abs(W1) + abs(W2)).tocsc())
+    indptr, indices, _ = synthetic.stencil_pattern(120)
+    pats.append(sp.csr_matrix((np.ones(len(indices)), indices, indptr), shape=(120 * 120, 120 * 120)).tocsc())
+    for A in pats:
+        for ordering in (0, 1):
+            for relax, mx in ((0, 0), (4, 8), (1, 1)):
+                monkeypatch.delenv("NEPB_LU_LEGACY", raising=False)
+                monkeypatch.setenv("NEPB_LU_CHECK", "1")
+                perm, parent, cc, st = nepb200.analyse_pattern(A, ordering=ordering, relax_leaf=relax, max_np=mx, fronts=True)
+                monkeypatch.delenv("NEPB_LU_CHECK")
+                monkeypatch.setenv("NEPB_LU_LEGACY", "1")
+                perm2, parent2, cc2, st2 = nepb200.analyse_pattern(A, ordering=ordering, relax_leaf=relax, max_np=mx, fronts=True)
+                assert np.array_equal(perm, perm2) and np.array_equal(parent, parent2) and np.array_equal(cc, cc2)
+                for key in ("nnz_factor", "front_entries", "nfronts", "nlevels", "max_front", "flops", "solve_rows"):
+                    assert st[key] == st2[key]
+                assert np.array_equal(st["np"], st2["np"]) and np.array_equal(st["nf"], st2["nf"]) and np.array_equal(st["level"], st2["level"])
