@@ -132,10 +132,20 @@ int nepb_lu_symbolic_get(const nepb_spmf* h, int32_t* perm, int32_t* parent, int
 int nepb_lu_analyse_pattern(int64_t n, const int64_t* colptr, const int64_t* rowval, int index_base, int ordering,
                             int relax_leaf, int max_np, int32_t* perm, int32_t* parent, int32_t* colcount, double* stats,
                             int32_t* sn_ptr, int32_t* sn_rows, int32_t* sn_level);
+/* Static pivoting, host only (lu_matching.cpp): the row matching that maximises the product of the diagonal magnitudes of
+ * |A| (CSC, absval[nnz] >= 0) and the scalings that make matched entries 1 and all others <= 1 in modulus (Duff & Koster
+ * 2001).  row_of_col[n] (0-based) is the row matched to each column, dr[n] / dc[n] the row / column scalings.  This is what
+ * stands in for UMFPACK's numerical pivoting (src/LinSolvers.jl:116) when a factorisation on the plain pattern meets zero or
+ * tiny pivots: nepb_lu_create then permutes and scales with the matching of the offending shift, repeats the symbolic
+ * analysis on the row-permuted pattern and factorises again (NEPB_LU_MATCHING = 0 never / 1 on demand / 2 always).
+ * Returns NEPB_E_SINGULAR for a structurally singular pattern. */
+int nepb_lu_matching(int64_t n, const int64_t* colptr, const int64_t* rowval, int index_base, const double* absval,
+                     int32_t* row_of_col, double* dr, double* dc);
 /* factorise nshift matrices at once: coef is nshift x p complex, row s = (f_1(sigma_s) .. f_p(sigma_s)) */
 int nepb_lu_create(const nepb_spmf* h, int nshift, const double* coef, nepb_lu** out);
 int nepb_lu_destroy(nepb_lu* lu);
-/* flags: bit0 = an exactly zero pivot was replaced (matrix singular to working precision), bit1 = non-finite pivot;
+/* flags: bit0 = an exactly zero pivot was replaced (matrix singular to working precision), bit1 = non-finite pivot,
+ * bit3 (8) = this factorisation uses the static-pivoting row matching / scaling;
  * nperturbed = pivots below eps*max|M_ij| that were lifted to that threshold; min_pivot_ratio = min|pivot|/max|M_ij| */
 int nepb_lu_status(const nepb_lu* lu, int shift, int* flags, int* nperturbed, double* min_pivot_ratio);
 /* lin_solve (src/LinSolvers.jl:135-137): X = M(sigma_shift)^-1 B, B and X host column-major n x nrhs (may alias).
@@ -148,6 +158,11 @@ int nepb_lu_solve(nepb_lu* lu, int shift, int nrhs, const double* B, int64_t ldb
  * (NULL = 1); used by iar / tiar / resinv loops that keep their vectors in HBM (y[:,1] = -lin_solve(..), method_iar.jl:103) */
 int nepb_lu_solve_block(nepb_lu* lu, int shift, const nepb_block* B, int bcol0, int nrhs, nepb_block* X, int xcol0,
                         const double* alpha);
+/* the same with iterative refinement against the fused SpMM residual (umfpack_refinements of LinSolverCreators.jl:66 on the
+ * device-resident path) and the final backward error (berr_out optional).  Like nepb_lu_solve it returns NEPB_E_SINGULAR when
+ * the backward error stays above 1e-9 after refinement, or after any solve with a factorisation whose pivots were replaced. */
+int nepb_lu_solve_block_ex(nepb_lu* lu, int shift, const nepb_block* B, int bcol0, int nrhs, nepb_block* X, int xcol0,
+                           const double* alpha, int refine_steps, double* berr_out);
 
 /* ---- a11: dense tall-skinny blocks of iar / tiar (src/method_iar.jl:100-116, src/method_tiar.jl:119,128,187-189) ---
  * orthogonalize_and_normalize!(V[:, 0:k), w, h, DGKS()) with w = W[:, wcol] (V and W may be the same block), over the
@@ -176,7 +191,9 @@ typedef struct nepb_contour nepb_contour;
 int nepb_contour_create(const nepb_spmf* h, int k, int mg, int batch, nepb_contour** out);
 int nepb_contour_destroy(nepb_contour* c);
 /* reduce != 0: sum the moments over all ranks of the communicator (one ncclAllReduce, in place in HBM).
- * node_flags[nnodes] (optional): bit0 zero pivot, bit1 non-finite pivot, bit2 perturbed pivots. */
+ * node_flags[nnodes] (optional): bit0 zero pivot, bit1 non-finite pivot, bit2 perturbed pivots, bit3 (8) the static-pivoting
+ * row matching is in use (the integration is repeated once on a matched analysis when a node on the plain pattern shows
+ * any of the other bits), bit4 (16) a pivot below 1e-8 max|M_ij| (the node is close to an eigenvalue). */
 int nepb_contour_integrate(nepb_contour* c, int nnodes, const double* coef, const double* weights, const double* Vh,
                            int64_t ldv, int reduce, double* S /* n x k x mg, column-major */, int* node_flags);
 /* the same in three steps, so that a benchmark can time the device part alone */

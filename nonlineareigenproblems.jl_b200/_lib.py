@@ -83,6 +83,7 @@ SIGNATURES = {
     "nepb_lu_symbolic_info": (c_int, [vp, P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_int), P(c_dbl)]),
     "nepb_lu_symbolic_get": (c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "nepb_lu_analyse_pattern": (c_int, [c_i64, vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp]),
+    "nepb_lu_matching": (c_int, [c_i64, vp, vp, c_int, vp, vp, vp, vp]),
     "nepb_lu_create": (c_int, [vp, c_int, vp, P(vp)]),
     "nepb_lu_destroy": (c_int, [vp]),
     "nepb_lu_status": (c_int, [vp, c_int, P(c_int), P(c_int), P(c_dbl)]),
@@ -100,6 +101,7 @@ SIGNATURES = {
     "nepb_comm_allreduce_sum_dev": (c_int, [vp, c_i64]),
     "nepb_spmf_apply_block_ex": (c_int, [vp, c_int, vp, c_int, c_int, c_int, vp, vp, c_int]),
     "nepb_lu_solve_block": (c_int, [vp, c_int, vp, c_int, c_int, vp, c_int, vp]),
+    "nepb_lu_solve_block_ex": (c_int, [vp, c_int, vp, c_int, c_int, vp, c_int, vp, c_int, P(c_dbl)]),
     "nepb_orth_dgks": (c_int, [vp, c_int, vp, c_int, c_i64, vp, P(c_dbl), P(c_int)]),
     "nepb_block_gemm": (c_int, [vp, c_int, c_int, vp, c_i64, c_int, vp, c_int, c_i64]),
     "nepb_block_copy_cols": (c_int, [vp, c_int, c_int, vp, c_int, vp, c_i64]),

@@ -109,14 +109,17 @@ struct nepb_spmf {
     // tile's list.  tile = two int4: (first row, rows, first entry of cols, distinct columns), (first nonzero, nonzeros, -, -)
     struct TileSet {
         int state = 0;  // 0 = not built, 1 = ready, -1 = not applicable (a row exceeds the tile budget) / no memory
-        int64_t ntiles = 0, cols_total = 0;
+        int64_t ntiles = 0, cols_total = 0, runs_total = 0;
         int max_cols = 0, max_nnz = 0;
         nepb::DevBuf<int4> tiles;
         nepb::DevBuf<int32_t> cols;
         nepb::DevBuf<uint16_t> lidx;
+        nepb::DevBuf<int2> runs;  // runs of consecutive columns of every tile: (first column, position in the tile | length << 16)
     };
     mutable TileSet tiling[2];  // [0]: 32-row tiles, [1]: 16-row tiles
     void* lu_symbolic = nullptr;  // owned by lu.cu (lazy)
+    std::vector<void*> lu_matched;   // analyses of row-permuted patterns (static pivoting), newest last; owned by lu.cu
+    bool lu_prefer_matched = false;  // a factorisation on the plain pattern met zero / tiny pivots
     nepb::LuOptions lu_opt;
     bool lu_opt_set = false;
     std::vector<int32_t> lu_user_perm;

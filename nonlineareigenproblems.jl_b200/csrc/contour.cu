@@ -190,26 +190,17 @@ __global__ void __launch_bounds__(256) sum_groups_kernel(size_t count, int ng, c
 }
 }  // namespace nepb
 
-// `batch` nodes are in flight at a time, spread over NEPB_CONTOUR_STREAMS (default 8) groups; each group factorises and
-// solves its share as one batched launch sequence on its own stream.
-int nepb_contour_create(const nepb_spmf* h, int k, int mg, int batch, nepb_contour** out) {
-    NEPB_CHECK_ARG(h && out, "NULL argument");
-    NEPB_CHECK_ARG(k >= 1 && k <= 256 && mg >= 1 && mg <= 64 && batch >= 1 && batch <= 4096, "bad sizes (k=%d mg=%d batch=%d)", k, mg, batch);
-    *out = nullptr;
-    LuSymbolicDev* sd = nullptr;
-    int rc = lu_symbolic_get(h, &sd);
-    if (rc) return rc;
+// (re)build the node groups of a contour handle on the symbolic analysis `sd`
+static int contour_alloc_groups(nepb_contour* c, LuSymbolicDev* sd) {
+    const nepb_spmf* h = c->op;
+    for (auto* g : c->groups) delete g;
+    c->groups.clear();
     int ng = 8;
     if (const char* e = getenv("NEPB_CONTOUR_STREAMS")) ng = std::max(1, std::min(16, atoi(e)));
-    ng = std::min(ng, batch);
-    nepb_contour* c = new nepb_contour();
-    c->op = h;
-    c->batch = batch;
-    c->k = k;
-    c->mg = mg;
+    ng = std::min(ng, c->batch);
+    const int batch = c->batch, k = c->k, mg = c->mg;
     const size_t nk = (size_t)h->n * k;
-    cudaError_t e = c->vh.alloc(2 * nk);
-    if (e == cudaSuccess) e = c->s.alloc(2 * nk * mg);
+    cudaError_t e = cudaSuccess;
     for (int g = 0; g < ng && e == cudaSuccess; ++g) {
         ContourGroup* G = new ContourGroup();
         c->groups.push_back(G);
@@ -242,8 +233,37 @@ int nepb_contour_create(const nepb_spmf* h, int k, int mg, int batch, nepb_conto
     }
     if (e != cudaSuccess) {
         set_error("contour workspace (batch %d, %.1f MB of fronts per node) does not fit: %s", batch, sd->S.front_total * 16e-6, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? NEPB_E_NOMEM : NEPB_E_CUDA;
+    }
+    return NEPB_OK;
+}
+
+// `batch` nodes are in flight at a time, spread over NEPB_CONTOUR_STREAMS (default 8) groups; each group factorises and
+// solves its share as one batched launch sequence on its own stream.
+int nepb_contour_create(const nepb_spmf* h, int k, int mg, int batch, nepb_contour** out) {
+    NEPB_CHECK_ARG(h && out, "NULL argument");
+    NEPB_CHECK_ARG(k >= 1 && k <= 256 && mg >= 1 && mg <= 64 && batch >= 1 && batch <= 4096, "bad sizes (k=%d mg=%d batch=%d)", k, mg, batch);
+    *out = nullptr;
+    LuSymbolicDev* sd = nullptr;
+    int rc = lu_symbolic_get(h, &sd);
+    if (rc) return rc;
+    nepb_contour* c = new nepb_contour();
+    c->op = h;
+    c->batch = batch;
+    c->k = k;
+    c->mg = mg;
+    const size_t nk = (size_t)h->n * k;
+    cudaError_t e = c->vh.alloc(2 * nk);
+    if (e == cudaSuccess) e = c->s.alloc(2 * nk * mg);
+    if (e != cudaSuccess) {
+        set_error("contour moments do not fit: %s", cudaGetErrorString(e));
         delete c;
         return e == cudaErrorMemoryAllocation ? NEPB_E_NOMEM : NEPB_E_CUDA;
+    }
+    rc = contour_alloc_groups(c, sd);
+    if (rc) {
+        delete c;
+        return rc;
     }
     *out = c;
     return NEPB_OK;
@@ -342,7 +362,8 @@ static int contour_integrate_groups(nepb_contour* c, int nnodes, const double* c
             cudaError_t e = cudaStreamSynchronize(G->st);
             if (e != cudaSuccess) { set_error("CUDA error in the contour pipeline: %s", cudaGetErrorString(e)); rc = NEPB_E_CUDA; break; }
             for (int bidx = 0; bidx < cnt; ++bidx)
-                c->node_flags[i0 + first[g] + bidx] = G->h_info[bidx].flags | (G->h_info[bidx].nperturbed ? 4 : 0);
+                c->node_flags[i0 + first[g] + bidx] = G->h_info[bidx].flags | (G->h_info[bidx].nperturbed ? 4 : 0) |
+                                                        (lu_info_suspicious(G->h_info[bidx]) ? 16 : 0);
         }
     }
     reset_current_stream();
@@ -366,6 +387,26 @@ int nepb_contour_integrate_dev(nepb_contour* c, int nnodes, const double* coef, 
     int rc = contour_integrate_groups(c, nnodes, coef, weights);
     reset_current_stream();
     if (rc) return rc;
+    // static-pivoting fallback, as in nepb_lu_create: a node whose factorisation on the plain pattern met zero / tiny pivots
+    // triggers one row matching (at that node), a rebuild of the groups on the matched analysis and a second pass
+    static const int matching = getenv("NEPB_LU_MATCHING") ? atoi(getenv("NEPB_LU_MATCHING")) : 1;
+    if (matching > 0 && !c->groups.empty() && !c->groups[0]->lu->sym->matched()) {
+        int bad = -1;
+        for (int i = 0; i < nnodes && bad < 0; ++i)
+            if (c->node_flags[i] & (1 | 2 | 4 | 16)) bad = i;
+        if (bad >= 0) {
+            LuSymbolicDev* md = nullptr;
+            rc = lu_symbolic_make_matched(c->op, coef + (size_t)2 * bad * c->op->p, &md);
+            if (rc) return rc;
+            rc = contour_alloc_groups(c, md);
+            if (rc) return rc;
+            rc = contour_integrate_groups(c, nnodes, coef, weights);
+            reset_current_stream();
+            if (rc) return rc;
+        }
+    }
+    if (c->groups[0]->lu->sym->matched())
+        for (int i = 0; i < nnodes; ++i) c->node_flags[i] |= 8;
     if (reduce) {
         rc = nepb_comm_allreduce_sum_dev(c->s.p, (int64_t)(2 * (size_t)c->op->n * c->k * c->mg));
         if (rc) return rc;

@@ -66,12 +66,13 @@ __device__ __forceinline__ double cabs1(double2 a) { return fabs(a.x) + fabs(a.y
 // assembly: fronts[b][a_pos[e]] = sum_i coef[b][i] * vals[e][i]   (fused compute_Mder + scatter)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) lu_assemble_kernel(int64_t nnz, int p, int ca, const int64_t* __restrict__ a_pos,
-                                                          const double* __restrict__ vals, const double2* __restrict__ coef,
-                                                          double2* __restrict__ fronts, int64_t front_total, LuInfo* __restrict__ info) {
+                                                          const double* __restrict__ a_scale, const double* __restrict__ vals,
+                                                          const double2* __restrict__ coef, double2* __restrict__ fronts,
+                                                          int64_t front_total, LuInfo* __restrict__ info) {
     const int b = blockIdx.y;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const double2* c = coef + (size_t)b * p;
-    double a = 0.0;
+    double a = 0.0, a0 = 0.0;
     if (e < nnz) {
         const int vw = ca ? 2 * p : p;
         const double* v = vals + (size_t)e * vw;
@@ -80,13 +81,26 @@ __global__ void __launch_bounds__(256) lu_assemble_kernel(int64_t nnz, int p, in
             const double2 x = ca ? make_double2(v[2 * i], v[2 * i + 1]) : make_double2(v[i], 0.0);
             cfma2(m, c[i], x);
         }
+        a0 = cabs1(m);
+        if (a_scale) {  // static pivoting: D_r M D_c (lu_matching.cpp)
+            const double sc = a_scale[e];
+            m.x *= sc;
+            m.y *= sc;
+        }
         fronts[(size_t)b * front_total + a_pos[e]] = m;
         a = cabs1(m);
     }
     // max |entry| of M(sigma_b): scale for the tiny-pivot test
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, off));
-    if ((threadIdx.x & 31) == 0 && a > 0.0) atomicMax((unsigned long long*)&info[b].amax_bits, (unsigned long long)__double_as_longlong(a));
+    for (int off = 16; off > 0; off >>= 1) {
+        a = fmax(a, __shfl_xor_sync(0xffffffffu, a, off));
+        a0 = fmax(a0, __shfl_xor_sync(0xffffffffu, a0, off));
+    }
+    if ((threadIdx.x & 31) == 0 && a0 > 0.0 && a_scale) atomicMax((unsigned long long*)&info[b].amax_plain_bits, (unsigned long long)__double_as_longlong(a0));
+    if ((threadIdx.x & 31) == 0 && a > 0.0) {
+        atomicMax((unsigned long long*)&info[b].amax_bits, (unsigned long long)__double_as_longlong(a));
+        if (!a_scale) atomicMax((unsigned long long*)&info[b].amax_plain_bits, (unsigned long long)__double_as_longlong(a));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -543,22 +557,35 @@ __global__ void __launch_bounds__(256, 2) lu_schur_pipe_kernel(LuDev d, const in
 // solves.  Xp: permuted right-hand sides / solutions, [b][n][k] row-major; W: per-front work rows [b][w_total][k].
 // rhs_stride = 0 when all shifts share one right-hand side block (contour integration).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lu_permute_in_kernel(int n, int k, const int* __restrict__ perm, const double2* __restrict__ Bm,
-                                                            size_t rhs_stride, double2* __restrict__ Xp) {
+__global__ void __launch_bounds__(256) lu_permute_in_kernel(int n, int k, const int* __restrict__ rperm, const double* __restrict__ dr,
+                                                            const double2* __restrict__ Bm, size_t rhs_stride, double2* __restrict__ Xp) {
     const int b = blockIdx.y;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)n * k) return;
     const int i = (int)(idx / k), c = (int)(idx % k);
-    Xp[(size_t)b * n * k + idx] = Bm[b * rhs_stride + (size_t)perm[i] * k + c];
+    const int r = rperm[i];  // operator row that became row i of the factorised matrix
+    double2 v = Bm[b * rhs_stride + (size_t)r * k + c];
+    if (dr) {
+        const double sc = dr[r];
+        v.x *= sc;
+        v.y *= sc;
+    }
+    Xp[(size_t)b * n * k + idx] = v;
 }
 
-__global__ void __launch_bounds__(256) lu_permute_out_kernel(int n, int k, const int* __restrict__ iperm, const double2* __restrict__ Xp,
-                                                             double2* __restrict__ X, size_t x_stride) {
+__global__ void __launch_bounds__(256) lu_permute_out_kernel(int n, int k, const int* __restrict__ iperm, const double* __restrict__ dc,
+                                                             const double2* __restrict__ Xp, double2* __restrict__ X, size_t x_stride) {
     const int b = blockIdx.y;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)n * k) return;
     const int i = (int)(idx / k), c = (int)(idx % k);
-    X[b * x_stride + idx] = Xp[(size_t)b * n * k + (size_t)iperm[i] * k + c];
+    double2 v = Xp[(size_t)b * n * k + (size_t)iperm[i] * k + c];
+    if (dc) {
+        const double sc = dc[i];
+        v.x *= sc;
+        v.y *= sc;
+    }
+    X[b * x_stride + idx] = v;
 }
 
 constexpr int SOLVE_BIG = 192;    // fronts with more update rows than this get several CTAs in the solves
@@ -926,14 +953,9 @@ static cudaError_t upload(DevBuf<T>& buf, const std::vector<T>& v) {
 
 static LuOptions g_default_opt;
 
-int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
-    static std::mutex mtx;
-    std::lock_guard<std::mutex> lock(mtx);
+// rowmap / dr / dc: optional static-pivoting data from max_product_matching (row i of the operator -> row rowmap[i])
+static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const double* dr, const double* dc, LuSymbolicDev** out) {
     nepb_spmf* hm = const_cast<nepb_spmf*>(h);
-    if (hm->lu_symbolic) {
-        *out = (LuSymbolicDev*)hm->lu_symbolic;
-        return NEPB_OK;
-    }
     NEPB_CHECK_ARG(h->n < (int64_t)1 << 31, "n too large");
     LuSymbolicDev* sd = new LuSymbolicDev();
     LuOptions opt = hm->lu_opt_set ? hm->lu_opt : g_default_opt;
@@ -941,7 +963,7 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     if (const char* e = getenv("NEPB_LU_RELAX")) opt.relax_leaf = std::max(1, atoi(e));
     if (const char* e = getenv("NEPB_LU_ORDERING")) opt.ordering = atoi(e);
     opt.max_np = std::max(1, std::min(32, opt.max_np));  // the pivot-block kernels hold a 32 x 32 block in one warp's lanes
-    int rc = lu_symbolic_analyse((int)h->n, h->h_rowptr, h->h_colind, hm->lu_user_perm.empty() ? nullptr : hm->lu_user_perm.data(), opt, sd->S);
+    int rc = lu_symbolic_analyse((int)h->n, h->h_rowptr, h->h_colind, hm->lu_user_perm.empty() || rowmap ? nullptr : hm->lu_user_perm.data(), opt, sd->S, rowmap);
     if (rc) {
         delete sd;
         return rc;
@@ -1106,6 +1128,24 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     UP(sd->a_pos, S.a_pos);
     UP(sd->perm, S.perm);
     UP(sd->iperm, S.iperm);
+    {
+        // right-hand side gather: row i of the factorised matrix is operator row rperm[i]
+        std::vector<int32_t> rperm(S.perm), inv;
+        if (rowmap) {
+            inv.resize(S.n);
+            for (int i = 0; i < S.n; ++i) inv[rowmap[i]] = i;
+            for (int i = 0; i < S.n; ++i) rperm[i] = inv[S.perm[i]];
+        }
+        UP(sd->rperm, rperm);
+        if (dr && dc) {
+            std::vector<double> vr(dr, dr + S.n), vc(dc, dc + S.n), sc(S.nnz);
+            for (int i = 0; i < S.n; ++i)
+                for (int e = h->h_rowptr[i]; e < h->h_rowptr[i + 1]; ++e) sc[e] = dr[i] * dc[h->h_colind[e]];
+            UP(sd->dr, vr);
+            UP(sd->dc, vc);
+            UP(sd->a_scale, sc);
+        }
+    }
     UP(sd->fr_items, fr_items);
     UP(sd->ea_items, ea_items);
     UP(sd->ea_recs, ea_recs);
@@ -1177,17 +1217,81 @@ int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
     cudaFuncSetAttribute(lu_backward_partial_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     NEPB_SOLVE_ATTR(1) NEPB_SOLVE_ATTR(4) NEPB_SOLVE_ATTR(8) NEPB_SOLVE_ATTR(10) NEPB_SOLVE_ATTR(16)
 #undef NEPB_SOLVE_ATTR
-    hm->lu_symbolic = sd;
     *out = sd;
+    return NEPB_OK;
+}
+
+static std::mutex g_sym_mtx;
+
+int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out) {
+    std::lock_guard<std::mutex> lock(g_sym_mtx);
+    nepb_spmf* hm = const_cast<nepb_spmf*>(h);
+    if (hm->lu_prefer_matched && !hm->lu_matched.empty()) {
+        *out = (LuSymbolicDev*)hm->lu_matched.back();
+        return NEPB_OK;
+    }
+    if (!hm->lu_symbolic) {
+        LuSymbolicDev* sd = nullptr;
+        int rc = lu_symbolic_build(h, nullptr, nullptr, nullptr, &sd);
+        if (rc) return rc;
+        hm->lu_symbolic = sd;
+    }
+    *out = (LuSymbolicDev*)hm->lu_symbolic;
     return NEPB_OK;
 }
 
 void lu_symbolic_release(void* p) { delete (LuSymbolicDev*)p; }
 
+__global__ void __launch_bounds__(256) lu_absval_kernel(int64_t nnz, int p, int ca, const double* __restrict__ vals,
+                                                        const double2* __restrict__ coef, double* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const int vw = ca ? 2 * p : p;
+    const double* v = vals + (size_t)e * vw;
+    double2 m = make_double2(0.0, 0.0);
+    for (int i = 0; i < p; ++i) {
+        const double2 x = ca ? make_double2(v[2 * i], v[2 * i + 1]) : make_double2(v[i], 0.0);
+        cfma2(m, coef[i], x);
+    }
+    out[e] = hypot(m.x, m.y);
+}
+
+// Static pivoting for an operator whose diagonal does not carry the weight at this shift: maximum-product matching and
+// I-matrix scaling of M(sigma) = sum_i coef_i A_i (lu_matching.cpp), then a fresh symbolic analysis of the row-permuted
+// pattern.  The result becomes the operator's preferred analysis (later factorisations start from it); earlier analyses
+// stay alive because existing factorisations point to them.
+int lu_symbolic_make_matched(const nepb_spmf* h, const double* coef, LuSymbolicDev** out) {
+    nepb_spmf* hm = const_cast<nepb_spmf*>(h);
+    DevBuf<double> d_abs, d_coef;
+    NEPB_CUDA(d_abs.alloc((size_t)h->nnz));
+    NEPB_CUDA(d_coef.alloc((size_t)2 * h->p));
+    NEPB_CUDA(cudaMemcpyAsync(d_coef.p, coef, sizeof(double) * 2 * h->p, cudaMemcpyHostToDevice, stream()));
+    NEPB_LAUNCH(lu_absval_kernel, (unsigned)((h->nnz + 255) / 256), 256, 0, h->nnz, h->p, h->is_complex, h->d_vals.p, (const double2*)d_coef.p, d_abs.p);
+    NEPB_LAUNCH_CHECK();
+    std::vector<double> absval((size_t)h->nnz), dr, dc;
+    NEPB_CUDA(cudaMemcpyAsync(absval.data(), d_abs.p, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, stream()));
+    NEPB_CUDA(cudaStreamSynchronize(stream()));
+    std::vector<int32_t> rowmap;
+    const int matched = max_product_matching((int)h->n, h->h_rowptr, h->h_colind, absval.data(), rowmap, dr, dc);
+    if (matched < (int)h->n) {
+        set_error("M(sigma) is structurally singular: only %d of %lld rows can be matched to a nonzero", matched, (long long)h->n);
+        return NEPB_E_SINGULAR;
+    }
+    LuSymbolicDev* sd = nullptr;
+    int rc = lu_symbolic_build(h, rowmap.data(), dr.data(), dc.data(), &sd);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g_sym_mtx);
+    hm->lu_matched.push_back(sd);
+    hm->lu_prefer_matched = true;
+    *out = sd;
+    return NEPB_OK;
+}
+
 __global__ void lu_info_init_kernel(int nb, LuInfo* __restrict__ info) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     info[b].amax_bits = 0;
+    info[b].amax_plain_bits = 0;
     info[b].minpiv_bits = 0x7ff0000000000000ULL;  // +inf
     info[b].flags = 0;
     info[b].nperturbed = 0;
@@ -1203,7 +1307,7 @@ static int factor_prologue(nepb_lu* lu) {
     NEPB_CUDA(cudaMemsetAsync(lu->fronts.p, 0, sizeof(double) * 2 * (size_t)nb * S.front_total, stream()));
     NEPB_LAUNCH(lu_info_init_kernel, (nb + 127) / 128, 128, 0, nb, lu->info.p);
     dim3 grid((unsigned)((h->nnz + 255) / 256), nb);
-    NEPB_LAUNCH(lu_assemble_kernel, grid, 256, 0, h->nnz, h->p, h->is_complex, sd->a_pos.p, h->d_vals.p, (const double2*)lu->coef.p,
+    NEPB_LAUNCH(lu_assemble_kernel, grid, 256, 0, h->nnz, h->p, h->is_complex, sd->a_pos.p, sd->a_scale.p, h->d_vals.p, (const double2*)lu->coef.p,
                 (double2*)lu->fronts.p, S.front_total, lu->info.p);
     return NEPB_OK;
 }
@@ -1366,13 +1470,13 @@ int lu_solve_device(nepb_lu* lu, int shift0, int nb, int k, const double2* Bdev,
     if (rc) return rc;
     const int n = c.sd->S.n, nlev = c.sd->S.nlevels;
     dim3 pg((unsigned)(((size_t)n * k + 255) / 256), nb);
-    NEPB_LAUNCH(lu_permute_in_kernel, pg, 256, 0, n, k, c.sd->perm.p, Bdev, rhs_stride, c.Xp);
+    NEPB_LAUNCH(lu_permute_in_kernel, pg, 256, 0, n, k, c.sd->rperm.p, c.sd->dr.p, Bdev, rhs_stride, c.Xp);
     for (int l = 0; l < nlev; ++l) solve_forward_level(c, l);
     for (int l = nlev - 1; l >= 0; --l) {
         solve_backward_partials(c, l);
         solve_backward_level(c, l);
     }
-    NEPB_LAUNCH(lu_permute_out_kernel, pg, 256, 0, n, k, c.sd->iperm.p, c.Xp, Xdev, (size_t)n * k);
+    NEPB_LAUNCH(lu_permute_out_kernel, pg, 256, 0, n, k, c.sd->iperm.p, c.sd->dc.p, c.Xp, Xdev, (size_t)n * k);
     NEPB_LAUNCH_CHECK();
     return NEPB_OK;
 }
@@ -1393,7 +1497,7 @@ int lu_factor_solve_pipelined(nepb_lu* lu, int k, const double2* Bdev, size_t rh
     NEPB_CUDA(cudaEventRecord(ev[0], s0));  // fork: the side stream starts after everything already queued on s0
     NEPB_CUDA(cudaStreamWaitEvent(side, ev[0], 0));
     set_current_stream(side);
-    NEPB_LAUNCH(lu_permute_in_kernel, pg, 256, 0, n, k, c.sd->perm.p, Bdev, rhs_stride, c.Xp);
+    NEPB_LAUNCH(lu_permute_in_kernel, pg, 256, 0, n, k, c.sd->rperm.p, c.sd->dr.p, Bdev, rhs_stride, c.Xp);
     set_current_stream(s0);
     rc = factor_prologue(lu);
     if (rc) return rc;
@@ -1425,7 +1529,7 @@ int lu_factor_solve_pipelined(nepb_lu* lu, int k, const double2* Bdev, size_t rh
         solve_backward_level(c, l);
         NEPB_CUDA(cudaEventRecord(evB[l], s0));
     }
-    NEPB_LAUNCH(lu_permute_out_kernel, pg, 256, 0, n, k, c.sd->iperm.p, c.Xp, Xdev, (size_t)n * k);
+    NEPB_LAUNCH(lu_permute_out_kernel, pg, 256, 0, n, k, c.sd->iperm.p, c.sd->dc.p, c.Xp, Xdev, (size_t)n * k);
     NEPB_LAUNCH_CHECK();
     return NEPB_OK;
 }
@@ -1510,6 +1614,33 @@ int lu_create(const nepb_spmf* h, int nshift, const double* coef, nepb_lu** out)
     }
     rc = lu_refactor(lu, nshift, coef);
     if (!rc) rc = lu_fetch_info(lu);
+    // Static-pivoting fallback (NEPB_LU_MATCHING: 0 = never, 1 = when the plain factorisation met a zero or tiny pivot
+    // [default], 2 = always): permute / scale with the maximum-product matching of the first offending shift and factorise again
+    static const int matching = getenv("NEPB_LU_MATCHING") ? atoi(getenv("NEPB_LU_MATCHING")) : 1;
+    if (!rc && matching > 0) {
+        int bad = -1;
+        for (int b = 0; b < nshift && bad < 0; ++b)
+            if (lu_info_suspicious(lu->h_info[b])) bad = b;
+        if (matching >= 2 && bad < 0 && !sd->matched()) bad = 0;
+        if (bad >= 0 && sd->matched() && !(lu->h_info[bad].flags & 3) && lu->h_info[bad].nperturbed == 0)
+            bad = -1;  // small pivots under an existing matching: genuinely close to singular, the solves verify themselves
+        if (bad >= 0) {
+            LuSymbolicDev* md = nullptr;
+            rc = lu_symbolic_make_matched(h, coef + (size_t)2 * bad * h->p, &md);
+            if (!rc) {
+                lu->sym = md;
+                for (auto& kv : lu->solve_graphs) cudaGraphExecDestroy(kv.second.exec);
+                lu->solve_graphs.clear();
+                e = lu->fronts.alloc((size_t)2 * nshift * md->S.front_total);
+                if (e != cudaSuccess) {
+                    set_error("allocating %d factorisations (%.1f MB each) failed: %s", nshift, md->S.front_total * 16e-6, cudaGetErrorString(e));
+                    rc = e == cudaErrorMemoryAllocation ? NEPB_E_NOMEM : NEPB_E_CUDA;
+                }
+            }
+            if (!rc) rc = lu_refactor(lu, nshift, coef);
+            if (!rc) rc = lu_fetch_info(lu);
+        }
+    }
     if (rc) {
         delete lu;
         return rc;
@@ -1612,6 +1743,30 @@ int nepb_lu_analyse_pattern(int64_t n, const int64_t* colptr, const int64_t* row
     return NEPB_OK;
 }
 
+int nepb_lu_matching(int64_t n, const int64_t* colptr, const int64_t* rowval, int index_base, const double* absval,
+                     int32_t* row_of_col, double* dr, double* dc) {
+    NEPB_CHECK_ARG(n >= 1 && n < ((int64_t)1 << 31) && colptr && rowval && absval && row_of_col, "bad arguments");
+    const int64_t nnz = colptr[n] - index_base;
+    NEPB_CHECK_ARG(nnz >= 0 && nnz < ((int64_t)1 << 31), "pattern too large");
+    std::vector<int32_t> cp(n + 1), ri((size_t)nnz), match;
+    for (int64_t j = 0; j <= n; ++j) cp[j] = (int32_t)(colptr[j] - index_base);
+    for (int64_t e = 0; e < nnz; ++e) {
+        ri[e] = (int32_t)(rowval[e] - index_base);
+        NEPB_CHECK_ARG(ri[e] >= 0 && ri[e] < n, "row index out of range");
+    }
+    // the matching routine is orientation-agnostic: handing it the CSC arrays matches columns (outer) to rows (inner)
+    std::vector<double> douter, dinner;
+    const int matched = max_product_matching((int)n, cp.data(), ri.data(), absval, match, douter, dinner);
+    if (matched < n) {
+        set_error("structurally singular: only %d of %lld columns can be matched to a nonzero", matched, (long long)n);
+        return NEPB_E_SINGULAR;
+    }
+    memcpy(row_of_col, match.data(), sizeof(int32_t) * n);
+    if (dc) memcpy(dc, douter.data(), sizeof(double) * n);
+    if (dr) memcpy(dr, dinner.data(), sizeof(double) * n);
+    return NEPB_OK;
+}
+
 int nepb_lu_create(const nepb_spmf* h, int nshift, const double* coef, nepb_lu** out) {
     NEPB_CHECK_ARG(h && coef && out, "NULL argument");
     NEPB_CHECK_ARG(nshift >= 1 && nshift <= 65535, "nshift must be in 1..65535");
@@ -1626,7 +1781,7 @@ int nepb_lu_destroy(nepb_lu* lu) {
 int nepb_lu_status(const nepb_lu* lu, int shift, int* flags, int* nperturbed, double* min_pivot_ratio) {
     NEPB_CHECK_ARG(lu && shift >= 0 && shift < lu->nb, "bad arguments");
     const LuInfo& I = lu->h_info[shift];
-    if (flags) *flags = I.flags;
+    if (flags) *flags = I.flags | (lu->sym->matched() ? 8 : 0);
     if (nperturbed) *nperturbed = I.nperturbed;
     if (min_pivot_ratio) {
         double r;
@@ -1635,6 +1790,75 @@ int nepb_lu_status(const nepb_lu* lu, int shift, int* flags, int* nperturbed, do
     }
     return NEPB_OK;
 }
+
+}  // extern "C"
+
+namespace nepb {
+// Iterative refinement of lu->sol against lu->rhs (k columns, both staged on the device) with the fused SpMM residual --
+// UMFPACK's control[8] in the reference (LinSolvers.jl:117-120).  Stops once the normwise backward error
+// max_c |r_c|_inf / (|M|_max |x_c|_inf + |b_c|_inf) is at rounding level or no longer halves.  A factorisation that had to
+// replace zero / tiny pivots is always checked, and a solve whose backward error stays above 1e-9 is an error
+// (LinearAlgebra.SingularException in the reference), never a silent result.
+int lu_refine_staged(nepb_lu* lu, int shift, int k, int refine_steps, bool want_berr, double* berr_out) {
+    const nepb_spmf* h = lu->op;
+    const int64_t n = h->n;
+    const LuInfo& I = lu->h_info[shift];
+    const bool suspicious = lu_info_suspicious(I);
+    *berr_out = 0.0;
+    if (refine_steps <= 0 && !want_berr && !suspicious) return NEPB_OK;
+    NEPB_CUDA(lu->res.reserve((size_t)2 * n * k));
+    NEPB_CUDA(lu->cor.reserve((size_t)2 * n * k));
+    NEPB_CUDA(lu->colmax.reserve(3 * 256));
+    const double* coef = lu->h_coef.data() + (size_t)2 * shift * h->p;
+    const size_t cnt = (size_t)n * k;
+    const unsigned gb = (unsigned)((cnt + 255) / 256);
+    double amax;
+    memcpy(&amax, &I.amax_plain_bits, 8);  // |M|_max of the operator itself (amax_bits is the scaled one under static pivoting)
+    double prev = INFINITY, berr = 0.0;
+    int rc;
+    for (int it = 0;; ++it) {
+        rc = spmf_apply_device(h, NEPB_COEF_SCALAR, k, k, (const double2*)lu->sol.p, coef, (double2*)lu->res.p);
+        if (rc) return rc;
+        NEPB_LAUNCH(residual_kernel, gb, 256, 0, cnt, (const double2*)lu->rhs.p, (double2*)lu->res.p);
+        NEPB_CUDA(cudaMemsetAsync(lu->colmax.p, 0, sizeof(unsigned long long) * 3 * 256, stream()));
+        NEPB_LAUNCH(colmax_kernel, gb, 256, 0, (int)n, k, (const double2*)lu->res.p, lu->colmax.p);
+        NEPB_LAUNCH(colmax_kernel, gb, 256, 0, (int)n, k, (const double2*)lu->sol.p, lu->colmax.p + 256);
+        NEPB_LAUNCH(colmax_kernel, gb, 256, 0, (int)n, k, (const double2*)lu->rhs.p, lu->colmax.p + 512);
+        NEPB_LAUNCH_CHECK();
+        unsigned long long hm[3 * 256];
+        NEPB_CUDA(cudaMemcpyAsync(hm, lu->colmax.p, sizeof(hm), cudaMemcpyDeviceToHost, stream()));
+        NEPB_CUDA(cudaStreamSynchronize(stream()));
+        berr = 0.0;
+        for (int c = 0; c < k; ++c) {
+            double r, x, bb;
+            memcpy(&r, &hm[c], 8);
+            memcpy(&x, &hm[256 + c], 8);
+            memcpy(&bb, &hm[512 + c], 8);
+            const double den = amax * x + bb;
+            berr = std::max(berr, den > 0 ? r / den : (r > 0 ? INFINITY : 0.0));
+        }
+        if (it >= refine_steps || berr <= 1.2e-16 || berr >= 0.5 * prev) break;
+        prev = berr;
+        rc = lu_solve_device(lu, shift, 1, k, (const double2*)lu->res.p, 0, (double2*)lu->cor.p);
+        if (rc) return rc;
+        NEPB_LAUNCH(axpy_kernel, gb, 256, 0, cnt, (const double2*)lu->cor.p, (double2*)lu->sol.p);
+    }
+    *berr_out = berr;
+    if (!(berr == berr) || berr == INFINITY) {
+        set_error("solution of shift %d is not finite (singular matrix?)", shift);
+        return NEPB_E_SINGULAR;
+    }
+    if ((refine_steps > 0 || suspicious) && berr > 1e-9) {
+        set_error("solve with M(sigma_%d) is inaccurate: backward error %.2e after refinement (%d pivots replaced%s); the matrix is "
+                  "singular to working precision or the static pivoting failed", shift, berr, I.nperturbed,
+                  lu->sym->matched() ? ", row matching in use" : "");
+        return NEPB_E_SINGULAR;
+    }
+    return NEPB_OK;
+}
+}  // namespace nepb
+
+extern "C" {
 
 // Solve M(sigma_shift) X = B on the host interface (lin_solve, LinSolvers.jl:135-137,157-159): B, X are n x nrhs column-major.
 // refine_steps > 0: iterative refinement with the fused SpMM residual (UMFPACK's control[8] in the reference); it stops
@@ -1647,8 +1871,9 @@ int nepb_lu_solve(nepb_lu* lu, int shift, int nrhs, const double* B, int64_t ldb
     const nepb_spmf* h = lu->op;
     const int64_t n = h->n;
     NEPB_CHECK_ARG(nrhs >= 1 && ldb >= n && ldx >= n, "bad right-hand side shape");
-    if (lu->h_info[shift].flags & 2) {
-        set_error("non-finite pivot in the factorisation of shift %d", shift);
+    if (lu->h_info[shift].flags & 3) {
+        set_error("%s pivot in the factorisation of shift %d: the matrix is singular to working precision",
+                  (lu->h_info[shift].flags & 2) ? "non-finite" : "zero", shift);
         return NEPB_E_SINGULAR;
     }
     const int KC = 64;  // right-hand sides per pass
@@ -1661,49 +1886,10 @@ int nepb_lu_solve(nepb_lu* lu, int shift, int nrhs, const double* B, int64_t ldb
         if (rc) return rc;
         rc = lu_solve_staged(lu, shift, k);
         if (rc) return rc;
-        if (refine_steps > 0 || berr_out) {
-            NEPB_CUDA(lu->res.reserve((size_t)2 * n * k));
-            NEPB_CUDA(lu->cor.reserve((size_t)2 * n * k));
-            NEPB_CUDA(lu->colmax.reserve(3 * 256));
-            const double* coef = lu->h_coef.data() + (size_t)2 * shift * h->p;
-            const size_t cnt = (size_t)n * k;
-            const unsigned gb = (unsigned)((cnt + 255) / 256);
-            double amax;
-            memcpy(&amax, &lu->h_info[shift].amax_bits, 8);
-            double prev = INFINITY, berr = 0.0;
-            for (int it = 0;; ++it) {
-                rc = spmf_apply_device(h, NEPB_COEF_SCALAR, k, k, (const double2*)lu->sol.p, coef, (double2*)lu->res.p);
-                if (rc) return rc;
-                NEPB_LAUNCH(residual_kernel, gb, 256, 0, cnt, (const double2*)lu->rhs.p, (double2*)lu->res.p);
-                NEPB_CUDA(cudaMemsetAsync(lu->colmax.p, 0, sizeof(unsigned long long) * 3 * 256, stream()));
-                NEPB_LAUNCH(colmax_kernel, gb, 256, 0, (int)n, k, (const double2*)lu->res.p, lu->colmax.p);
-                NEPB_LAUNCH(colmax_kernel, gb, 256, 0, (int)n, k, (const double2*)lu->sol.p, lu->colmax.p + 256);
-                NEPB_LAUNCH(colmax_kernel, gb, 256, 0, (int)n, k, (const double2*)lu->rhs.p, lu->colmax.p + 512);
-                NEPB_LAUNCH_CHECK();
-                unsigned long long hm[3 * 256];
-                NEPB_CUDA(cudaMemcpyAsync(hm, lu->colmax.p, sizeof(hm), cudaMemcpyDeviceToHost, stream()));
-                NEPB_CUDA(cudaStreamSynchronize(stream()));
-                berr = 0.0;
-                for (int c = 0; c < k; ++c) {
-                    double r, x, bb;
-                    memcpy(&r, &hm[c], 8);
-                    memcpy(&x, &hm[256 + c], 8);
-                    memcpy(&bb, &hm[512 + c], 8);
-                    const double den = amax * x + bb;
-                    berr = std::max(berr, den > 0 ? r / den : (r > 0 ? INFINITY : 0.0));
-                }
-                if (it >= refine_steps || berr <= 1.2e-16 || berr >= 0.5 * prev) break;
-                prev = berr;
-                rc = lu_solve_device(lu, shift, 1, k, (const double2*)lu->res.p, 0, (double2*)lu->cor.p);
-                if (rc) return rc;
-                NEPB_LAUNCH(axpy_kernel, gb, 256, 0, cnt, (const double2*)lu->cor.p, (double2*)lu->sol.p);
-            }
-            if (!(berr == berr)) {
-                set_error("solution of shift %d is not finite (singular matrix?)", shift);
-                return NEPB_E_SINGULAR;
-            }
-            worst = std::max(worst, berr);
-        }
+        double berr = 0.0;
+        rc = lu_refine_staged(lu, shift, k, refine_steps, berr_out != nullptr, &berr);
+        if (rc) return rc;
+        worst = std::max(worst, berr);
         rc = download_colmajor(n, k, lu->sol.p, k, 0, lu->stage, X + 2 * (size_t)c0 * ldx, ldx);
         if (rc) return rc;
     }
@@ -1712,14 +1898,16 @@ int nepb_lu_solve(nepb_lu* lu, int shift, int nrhs, const double* B, int64_t ldb
 }
 
 // Device-resident lin_solve: X[:, xcol0 : xcol0+nrhs) = alpha * M(sigma_shift)^-1 B[:, bcol0 : bcol0+nrhs); nothing crosses PCIe.
-int nepb_lu_solve_block(nepb_lu* lu, int shift, const nepb_block* B, int bcol0, int nrhs, nepb_block* X, int xcol0, const double* alpha) {
+int nepb_lu_solve_block_ex(nepb_lu* lu, int shift, const nepb_block* B, int bcol0, int nrhs, nepb_block* X, int xcol0, const double* alpha,
+                           int refine_steps, double* berr_out) {
     NEPB_CHECK_ARG(lu && B && X, "NULL argument");
     NEPB_CHECK_ARG(shift >= 0 && shift < lu->nb, "shift index out of range");
     const int64_t n = lu->op->n;
     NEPB_CHECK_ARG(B->n == n && X->n == n, "block row count differs from the operator size");
     NEPB_CHECK_ARG(nrhs >= 1 && nrhs <= 64 && bcol0 >= 0 && bcol0 + nrhs <= B->k && xcol0 >= 0 && xcol0 + nrhs <= X->k, "bad column windows");
-    if (lu->h_info[shift].flags & 2) {
-        set_error("non-finite pivot in the factorisation of shift %d", shift);
+    if (lu->h_info[shift].flags & 3) {
+        set_error("%s pivot in the factorisation of shift %d: the matrix is singular to working precision",
+                  (lu->h_info[shift].flags & 2) ? "non-finite" : "zero", shift);
         return NEPB_E_SINGULAR;
     }
     NEPB_CUDA(lu->rhs.reserve((size_t)2 * n * nrhs));
@@ -1728,10 +1916,18 @@ int nepb_lu_solve_block(nepb_lu* lu, int shift, const nepb_block* B, int bcol0, 
     NEPB_LAUNCH(cols_gather_kernel, gb, 256, 0, n, nrhs, (const double2*)B->d.p + bcol0, B->k, (double2*)lu->rhs.p);
     int rc = lu_solve_staged(lu, shift, nrhs);
     if (rc) return rc;
+    double berr = 0.0;
+    rc = lu_refine_staged(lu, shift, nrhs, refine_steps, berr_out != nullptr, &berr);
+    if (rc) return rc;
+    if (berr_out) *berr_out = berr;
     const double2 a = alpha ? make_double2(alpha[0], alpha[1]) : make_double2(1.0, 0.0);
     NEPB_LAUNCH(cols_scatter_kernel, gb, 256, 0, n, nrhs, (const double2*)lu->sol.p, (double2*)X->d.p + xcol0, X->k, a);
     NEPB_LAUNCH_CHECK();
     return NEPB_OK;
+}
+
+int nepb_lu_solve_block(nepb_lu* lu, int shift, const nepb_block* B, int bcol0, int nrhs, nepb_block* X, int xcol0, const double* alpha) {
+    return nepb_lu_solve_block_ex(lu, shift, B, bcol0, nrhs, X, xcol0, alpha, 0, nullptr);
 }
 
 }  // extern "C"

@@ -1,5 +1,7 @@
 // Internal layouts shared by lu.cu and contour.cu.
 #pragma once
+#include <string.h>
+
 #include <map>
 #include <utility>
 #include <vector>
@@ -39,11 +41,21 @@ struct EaRec {  // one child of one extend-add item (32 bytes)
 };
 
 struct LuInfo {
-    unsigned long long amax_bits;    // max |M_ij| (bits of a non-negative double)
+    unsigned long long amax_bits;    // max |M_ij| of the matrix that is factorised (bits of a non-negative double)
+    unsigned long long amax_plain_bits;  // max |M_ij| of the operator itself (differs under static-pivoting scaling)
     unsigned long long minpiv_bits;  // min |pivot| / amax
     int flags;                       // 1: exactly zero pivot met (perturbed), 2: non-finite pivot
     int nperturbed;
 };
+
+// zero / non-finite / lifted pivots, or a pivot below 1e-8 max|M_ij|: with pivoting restricted to the pivot block this is how
+// an unsafe elimination order shows (huge multipliers follow); it triggers the static-pivoting fallback on the plain pattern
+// and a backward-error check of every solve
+inline bool lu_info_suspicious(const LuInfo& I) {
+    double r;
+    memcpy(&r, &I.minpiv_bits, 8);
+    return (I.flags & 3) || I.nperturbed > 0 || !(r >= 1e-8);
+}
 
 struct LuLevel {
     int front_begin = 0, front_count = 0, max_np = 1;
@@ -67,7 +79,9 @@ struct LuSymbolicDev {
     DevBuf<int32_t> bw_slot, xsplit, sfr_items, chain_fronts;
     DevBuf<int2> fc_items, bc_items;
     int part_slots = 0;
-    DevBuf<int32_t> nf, np, ld, rows, rel, sn_ptr, child_ptr, child_list, perm, iperm, fr_items;
+    DevBuf<int32_t> nf, np, ld, rows, rel, sn_ptr, child_ptr, child_list, perm, iperm, rperm, fr_items;
+    DevBuf<double> dr, dc, a_scale;  // static pivoting (empty = none): row / column scalings, per-nonzero product
+    bool matched() const { return a_scale.p != nullptr; }
     DevBuf<int4> ea_items, pn_items, sc_items, sp_items, fu_items, bp_items;
     DevBuf<EaRec> ea_recs;
     size_t smem_diag = 0, smem_panel = 0, smem_schur = 0, smem_schur_pipe = 0;
@@ -75,6 +89,7 @@ struct LuSymbolicDev {
 };
 
 int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out);
+int lu_symbolic_make_matched(const nepb_spmf* h, const double* coef, LuSymbolicDev** out);
 
 }  // namespace nepb
 

@@ -306,18 +306,22 @@ struct PhaseTimer {  // NEPB_LU_TIMING=1: wall time of every phase of the analys
 }  // namespace
 
 int lu_symbolic_analyse(int n, const int32_t* rowptr, const int32_t* colind, const int32_t* user_perm,
-                        const LuOptions& opt, LuSymbolic& S) {
+                        const LuOptions& opt, LuSymbolic& S, const int32_t* rowmap) {
     PhaseTimer timer;
     S = LuSymbolic();
     S.n = n;
     S.nnz = rowptr[n];
+    // rowmap (optional, from max_product_matching): row i of the operator is row rowmap[i] of the matrix that is factorised, so
+    // that its diagonal is the matching; everything below works on that row-permuted pattern
+    if (rowmap) S.rowmap.assign(rowmap, rowmap + n);
     // ---- adjacency of A + A^T without the diagonal ---------------------------------------------------
     std::vector<int64_t> xadj(n + 1, 0);
     std::vector<int32_t> adj;
     {
         std::vector<int32_t> cnt(n, 0);
-        for (int i = 0; i < n; ++i)
-            for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+        for (int i0 = 0; i0 < n; ++i0)
+            for (int e = rowptr[i0]; e < rowptr[i0 + 1]; ++e) {
+                const int i = rowmap ? rowmap[i0] : i0;
                 const int j = colind[e];
                 if (j != i) {
                     cnt[i]++;
@@ -327,8 +331,9 @@ int lu_symbolic_analyse(int n, const int32_t* rowptr, const int32_t* colind, con
         for (int i = 0; i < n; ++i) xadj[i + 1] = xadj[i] + cnt[i];
         adj.resize(xadj[n]);
         std::vector<int64_t> fill(xadj.begin(), xadj.end() - 1);
-        for (int i = 0; i < n; ++i)
-            for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+        for (int i0 = 0; i0 < n; ++i0)
+            for (int e = rowptr[i0]; e < rowptr[i0 + 1]; ++e) {
+                const int i = rowmap ? rowmap[i0] : i0;
                 const int j = colind[e];
                 if (j != i) {
                     adj[fill[i]++] = j;
@@ -738,7 +743,7 @@ int lu_symbolic_analyse(int n, const int32_t* rowptr, const int32_t* colind, con
     int bad2 = 0;
 #pragma omp parallel for schedule(static) reduction(| : bad2)
     for (int i = 0; i < n; ++i) {
-        const int pi = S.iperm[i];
+        const int pi = S.iperm[rowmap ? rowmap[i] : i];
         for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
             const int pj = S.iperm[colind[e]];
             const int s = S.col_sn[std::min(pi, pj)];

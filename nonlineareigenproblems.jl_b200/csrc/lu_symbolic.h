@@ -10,6 +10,7 @@ struct LuSymbolic {
     int64_t nnz = 0;
     // ordering: perm[new] = old, iperm[old] = new (fill-reducing ordering composed with the etree postorder)
     std::vector<int32_t> perm, iperm;
+    std::vector<int32_t> rowmap;  // empty, or row i of the operator = row rowmap[i] of the factorised matrix (static pivoting)
     std::vector<int32_t> parent;  // column elimination tree of the permuted pattern of A + A^T (-1 = root)
     std::vector<int32_t> colcount;  // |struct(L_j)| including the diagonal
     // supernodes = fronts
@@ -44,7 +45,11 @@ struct LuOptions {
 
 // csr rowptr/colind of the n x n union pattern (0-based, int32); user_perm optional (perm[new] = old)
 int lu_symbolic_analyse(int n, const int32_t* rowptr, const int32_t* colind, const int32_t* user_perm,
-                        const LuOptions& opt, LuSymbolic& S);
+                        const LuOptions& opt, LuSymbolic& S, const int32_t* rowmap = nullptr);
+
+// maximum-product matching of rows to columns with I-matrix scalings (lu_matching.cpp); returns the matched rows (n = success)
+int max_product_matching(int n, const int32_t* rowptr, const int32_t* colind, const double* absval,
+                         std::vector<int32_t>& row_to_col, std::vector<double>& dr, std::vector<double>& dc);
 
 // approximate-minimum-degree ordering of the symmetric graph (adjacency without diagonal); out[new] = old
 void amd_order(int n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj, std::vector<int32_t>& out);

@@ -325,6 +325,164 @@ __global__ void __launch_bounds__(256) spmm_tiled_kernel(int kt, unsigned kinv, 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K1b (round 2, the default for 5..32 dense columns): the tiled product with EVERY operand of a tile brought in by the TMA
+// unit, so that the LSU / shared-memory pipe -- the measured limiter of spmm_tiled_kernel (profiles/r1_ncu_spmm_tiled.txt:
+// l1tex 72 %, DRAM 36 %) -- only serves the row products:
+//   * the tile's distinct columns are kept as RUNS of consecutive columns (host, spmf_build_tiles); V is row-major, so a run
+//     of c consecutive rows of V is one contiguous piece of c*kt*16 bytes = ONE cp.async.bulk.  Neighbouring rows of a
+//     discretisation share most of their columns: the C4 stencil has 5 runs of ~36 rows per 32-row tile instead of 180
+//     separate row copies (a pattern without locality degenerates to one copy per row, still correct);
+//   * the tile's slice of the interleaved values (contiguous in CSR order) and of the 16-bit tile-local column indices are
+//     two more bulk copies (start addresses rounded down to 16 bytes, the slack skipped when reading);
+//   * all copies complete on one mbarrier (transaction bytes); nothing is held in registers while the data is in flight, and
+//     the other resident CTAs of the SM (4-7 of them) are in their product phase meanwhile -- the resident CTAs ARE the
+//     pipeline stages.
+// After the wait the raw values are combined once per nonzero (SCALAR) and the row products run as in spmm_tiled_kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(unsigned dst_s, const void* src, unsigned bytes, unsigned bar_s) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(src),
+                 "r"(bytes), "r"(bar_s)
+                 : "memory");
+}
+
+struct TmaSmem {  // byte offsets inside the dynamic shared memory of spmm_tma_kernel (host and device agree through this)
+    unsigned sV, sA, sM, sL, sRp, bar, total;
+};
+__host__ __device__ inline TmaSmem tma_smem_layout(int max_cols, int max_nnz, int kt, int vw, bool diag, int rows) {
+    TmaSmem L;
+    unsigned o = 0;
+    L.sV = o;
+    o += (unsigned)max_cols * kt * 16;
+    L.sA = o;
+    o += ((unsigned)max_nnz * vw * 8 + 16 + 15) & ~15u;  // + slack for the rounded-down start
+    L.sM = o;
+    if (!diag) o += (unsigned)max_nnz * 16;
+    L.sL = o;
+    o += ((unsigned)max_nnz * 2 + 16 + 15) & ~15u;
+    L.sRp = o;
+    o += ((unsigned)(rows + 1) * 4 + 15) & ~15u;
+    L.bar = o;
+    o += 16;
+    L.total = o;
+    return L;
+}
+
+template <int VW, bool CA, bool DIAG, int CPT>
+__global__ void __launch_bounds__(256) spmm_tma_kernel(int kt, int ldv, int ldz, int max_cols, int max_nnz, int tile_rows,
+                                                       const int4* __restrict__ tiles, const int2* __restrict__ runs,
+                                                       const int* __restrict__ tile_cols, const int* __restrict__ rowptr,
+                                                       const uint16_t* __restrict__ lidx,
+                                                       const double* __restrict__ vals, const double2* __restrict__ V,
+                                                       double2* __restrict__ Z, const CoefP cp, const double2* __restrict__ cdiag, int p) {
+    constexpr int GC = 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const TmaSmem L = tma_smem_layout(max_cols, max_nnz, kt, VW, DIAG, tile_rows);
+    double2* sV = (double2*)(smem_raw + L.sV);
+    int* sRp = (int*)(smem_raw + L.sRp);
+    const int4 t0 = tiles[2 * blockIdx.x], t1 = tiles[2 * blockIdx.x + 1];
+    const int row0 = t0.x, nrows = t0.y, ncols = t0.w, nz0 = t1.x, nnz = t1.y, run0 = t1.z, nruns = t1.w;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(smem_raw + L.bar);
+    // slices of the matrix stream, start rounded down to 16 bytes
+    const size_t a_byte = (size_t)nz0 * VW * 8, l_byte = (size_t)nz0 * 2;
+    const unsigned a_skip = (unsigned)(a_byte & 15), l_skip = (unsigned)(l_byte & 15);
+    const unsigned a_len = ((unsigned)nnz * VW * 8 + a_skip + 15) & ~15u, l_len = ((unsigned)nnz * 2 + l_skip + 15) & ~15u;
+    const double* sA = (const double*)(smem_raw + L.sA + a_skip);
+    const uint16_t* sL = (const uint16_t*)(smem_raw + L.sL + l_skip);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned total = (unsigned)ncols * kt * 16 + a_len + l_len;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(total) : "memory");
+        bulk_g2s((unsigned)__cvta_generic_to_shared(smem_raw + L.sA), (const unsigned char*)vals + (a_byte - a_skip), a_len, bar_s);
+        bulk_g2s((unsigned)__cvta_generic_to_shared(smem_raw + L.sL), (const unsigned char*)lidx + (l_byte - l_skip), l_len, bar_s);
+    }
+    if (ldv == kt) {
+        for (int r = tid; r < nruns; r += nth) {  // one bulk copy per run of consecutive V rows
+            const int2 rn = runs[run0 + r];
+            const int dst_row = rn.y & 0xffff, len = rn.y >> 16;
+            bulk_g2s((unsigned)__cvta_generic_to_shared(sV + (size_t)dst_row * kt), V + (size_t)rn.x * ldv, (unsigned)len * kt * 16, bar_s);
+        }
+    } else {  // a column window of a wider block: rows are not adjacent in memory, one copy per row
+        const int* cols = tile_cols + t0.z;
+        for (int dcol = tid; dcol < ncols; dcol += nth)
+            bulk_g2s((unsigned)__cvta_generic_to_shared(sV + (size_t)dcol * kt), V + (size_t)cols[dcol] * ldv, (unsigned)kt * 16, bar_s);
+    }
+    if (tid <= nrows) sRp[tid] = rowptr[row0 + tid] - nz0;
+    const int gc = tid % GC;
+    const int r = tid / GC;
+    double2 cd[DIAG ? CPT : 1][DIAG ? (CA ? VW / 2 : VW) : 1];
+    if constexpr (DIAG) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int c = gc + j * GC;
+#pragma unroll
+            for (int i = 0; i < (CA ? VW / 2 : VW); ++i) cd[j][i] = (c < kt) ? cdiag[i + p * c] : make_double2(0.0, 0.0);
+        }
+    }
+    {
+        unsigned done = 0, spins = 0;
+        while (!done) {
+            if (++spins > (1u << 26)) asm volatile("trap;");  // a lost transaction must fail the launch, never hang the device
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done)
+                         : "r"(bar_s), "r"(0)
+                         : "memory");
+        }
+    }
+    double2* sM = (double2*)(smem_raw + L.sM);
+    if constexpr (!DIAG) {  // combined coefficient of every nonzero, once
+        for (int e = tid; e < nnz; e += nth) {
+            double v[VW];
+#pragma unroll
+            for (int t = 0; t < VW; ++t) v[t] = sA[e * VW + t];
+            sM[e] = combine<VW, CA>(v, [&](int i) { return cp.c[i]; });
+        }
+    }
+    __syncthreads();
+    int start = 0, end = 0;
+    if (r < nrows) {
+        start = sRp[r];
+        end = sRp[r + 1];
+    }
+    double2 acc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[j] = make_double2(0.0, 0.0);
+#pragma unroll 2
+    for (int idx = start; idx < end; ++idx) {
+        const double2* xr = sV + (int)sL[idx] * kt + gc;
+        if constexpr (!DIAG) {
+            const double2 m = sM[idx];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j)
+                if (gc + j * GC < kt) cfma(acc[j], m, xr[j * GC]);
+        } else {
+            double v[VW];
+#pragma unroll
+            for (int t = 0; t < VW; ++t) v[t] = sA[idx * VW + t];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                if (gc + j * GC < kt) {
+                    const double2 m = combine<VW, CA>(v, [&](int i) { return cd[j][i]; });
+                    cfma(acc[j], m, xr[j * GC]);
+                }
+            }
+        }
+    }
+    if (r < nrows) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int c = gc + j * GC;
+            if (c < kt) Z[(size_t)(row0 + r) * ldz + c] = acc[j];
+        }
+    }
+}
+
 // runtime-p fallback (any p <= MAXP, real or complex values); same row ownership with GC=4, GN=2
 template <bool DIAG>
 __global__ void __launch_bounds__(256) spmm_fused_generic_kernel(int n, int kt, int ldv, int ldz, const int* __restrict__ rowptr,
@@ -624,6 +782,7 @@ static int spmf_build_tiles(const nepb_spmf* h, int which) {
     const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
     std::vector<std::vector<int4>> ctiles(nchunks);
     std::vector<std::vector<int32_t>> ccols(nchunks);
+    std::vector<std::vector<int2>> cruns(nchunks);  // runs of consecutive columns: (first column, position in the tile | length << 16)
     std::vector<uint16_t> lidx((size_t)h->nnz);
     int bad = 0;
 #pragma omp parallel
@@ -656,8 +815,15 @@ static int spmf_build_tiles(const nepb_spmf* h, int which) {
                 }
                 std::sort(cur.begin(), cur.end());
                 for (size_t t = 0; t < cur.size(); ++t) local[cur[t]] = (int32_t)t;
+                const int run_first = (int)cruns[ch].size();
+                for (size_t t = 0; t < cur.size();) {
+                    size_t u = t + 1;
+                    while (u < cur.size() && cur[u] == cur[u - 1] + 1) ++u;
+                    cruns[ch].push_back(make_int2(cur[t], (int)t | ((int)(u - t) << 16)));
+                    t = u;
+                }
                 ctiles[ch].push_back(make_int4((int)r, (int)(rr - r), (int)ccols[ch].size(), (int)cur.size()));
-                ctiles[ch].push_back(make_int4(rp[r], rp[rr] - rp[r], 0, 0));
+                ctiles[ch].push_back(make_int4(rp[r], rp[rr] - rp[r], run_first, (int)cruns[ch].size() - run_first));
                 ccols[ch].insert(ccols[ch].end(), cur.begin(), cur.end());
                 if (!(bad & 1))
                     for (int32_t e = rp[r]; e < rp[rr]; ++e) lidx[e] = (uint16_t)local[ci[e]];
@@ -671,14 +837,19 @@ static int spmf_build_tiles(const nepb_spmf* h, int which) {
     }
     std::vector<int4> tiles;
     std::vector<int32_t> cols;
+    std::vector<int2> runs;
     int maxc = 0, maxz = 0;
     for (int64_t ch = 0; ch < nchunks; ++ch) {
         const int off = (int)cols.size();
+        const int roff = (int)runs.size();
+        runs.insert(runs.end(), cruns[ch].begin(), cruns[ch].end());
         for (size_t t = 0; t < ctiles[ch].size(); t += 2) {
             int4 a = ctiles[ch][t];
             a.z += off;
             tiles.push_back(a);
-            tiles.push_back(ctiles[ch][t + 1]);
+            int4 b = ctiles[ch][t + 1];
+            b.z += roff;
+            tiles.push_back(b);
             maxc = std::max(maxc, a.w);
             maxz = std::max(maxz, ctiles[ch][t + 1].y);
         }
@@ -692,17 +863,21 @@ static int spmf_build_tiles(const nepb_spmf* h, int which) {
     if (e == cudaSuccess && !tiles.empty()) e = cudaMemcpy(T.tiles.p, tiles.data(), sizeof(int4) * tiles.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = T.cols.alloc(std::max<size_t>(cols.size(), 1));
     if (e == cudaSuccess && !cols.empty()) e = cudaMemcpy(T.cols.p, cols.data(), sizeof(int32_t) * cols.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = T.lidx.alloc(std::max<size_t>(lidx.size(), 1));
+    if (e == cudaSuccess) e = T.lidx.alloc(lidx.size() + 16);  // + slack: bulk copies round the slice end up to 16 bytes
     if (e == cudaSuccess && !lidx.empty()) e = cudaMemcpy(T.lidx.p, lidx.data(), sizeof(uint16_t) * lidx.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = T.runs.alloc(std::max<size_t>(runs.size(), 1));
+    if (e == cudaSuccess && !runs.empty()) e = cudaMemcpy(T.runs.p, runs.data(), sizeof(int2) * runs.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         cudaGetLastError();
         T.tiles.release();
         T.cols.release();
         T.lidx.release();
+        T.runs.release();
         T.state = -1;  // not enough memory for the tile index: the untiled kernels still work
         return -1;
     }
     T.ntiles = (int64_t)tiles.size() / 2;
+    T.runs_total = (int64_t)runs.size();
     T.cols_total = (int64_t)cols.size();
     T.max_cols = maxc;
     T.max_nnz = maxz;
@@ -745,6 +920,62 @@ static int launch_tiled_vw(const nepb_spmf* h, const nepb_spmf::TileSet& T, int 
     return 1;
 }
 
+template <int VW, bool CA, bool DIAG>
+static int launch_tma_vw(const nepb_spmf* h, const nepb_spmf::TileSet& T, int tile_rows, int kt, int ldv, int ldz, const double2* V,
+                         double2* Z, const CoefP& cp, const double2* cdiag) {
+    const TmaSmem L = tma_smem_layout(T.max_cols, T.max_nnz, kt, VW, DIAG, tile_rows);
+    const int threads = 8 * tile_rows;
+#define NEPB_TMA(CPT_)                                                                                                                  \
+    do {                                                                                                                                \
+        static size_t attr_done[16] = {0};                                                                                              \
+        int dev = 0;                                                                                                                    \
+        cudaGetDevice(&dev);                                                                                                            \
+        if (L.total > 48 * 1024 && L.total > attr_done[dev & 15]) {                                                                     \
+            NEPB_CUDA(cudaFuncSetAttribute(spmm_tma_kernel<VW, CA, DIAG, CPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
+            attr_done[dev & 15] = L.total;                                                                                              \
+        }                                                                                                                               \
+        NEPB_LAUNCH((spmm_tma_kernel<VW, CA, DIAG, CPT_>), (unsigned)T.ntiles, threads, L.total, kt, ldv, ldz, T.max_cols, T.max_nnz,   \
+                    tile_rows, T.tiles.p, T.runs.p, T.cols.p, h->d_rowptr.p, T.lidx.p, h->d_vals.p, V, Z, cp, cdiag, h->p);                       \
+    } while (0)
+    if (kt <= 8) NEPB_TMA(1);
+    else if (kt <= 16) NEPB_TMA(2);
+    else if (kt <= 24) NEPB_TMA(3);
+    else NEPB_TMA(4);
+#undef NEPB_TMA
+    return 1;
+}
+
+// the TMA-staged tiled product (default for 5..32 columns when the operands allow bulk copies); 0 = does not apply
+static int launch_tma(const nepb_spmf* h, bool diag, int kt, int ldv, int ldz, const double2* V, double2* Z, const CoefP& cp,
+                      const double2* cdiag) {
+    static const bool enabled = !(getenv("NEPB_SPMM_TMA") && atoi(getenv("NEPB_SPMM_TMA")) == 0);
+    if (!enabled || kt < 5 || getenv("NEPB_SPMM_CFG") || getenv("NEPB_SPMM_BULK")) return 0;
+    if (((uintptr_t)V & 15) != 0) return 0;  // bulk copies need 16-byte aligned sources (rows are ldv*16 bytes apart)
+    int which = kt > 12 ? 1 : 0;
+    if (const char* e = getenv("NEPB_SPMM_TILE_ROWS")) which = atoi(e) == 16 ? 1 : 0;
+    if (spmf_build_tiles(h, which) != 1) return 0;
+    const nepb_spmf::TileSet& T = h->tiling[which];
+    const int tile_rows = which == 0 ? 32 : 16;
+    if (tma_smem_layout(T.max_cols, T.max_nnz, kt, h->vw, diag, tile_rows).total > 200 * 1024) return 0;
+    const int vw = h->vw;
+    const bool ca = h->is_complex;
+    int rc = 0;
+#define NEPB_VW_TMA(VW_, CA_)                                                                                  \
+    if (!rc && vw == VW_ && ca == CA_)                                                                          \
+        rc = diag ? launch_tma_vw<VW_, CA_, true>(h, T, tile_rows, kt, ldv, ldz, V, Z, cp, cdiag)                \
+                  : launch_tma_vw<VW_, CA_, false>(h, T, tile_rows, kt, ldv, ldz, V, Z, cp, cdiag);
+    NEPB_VW_TMA(2, false)
+    NEPB_VW_TMA(3, false)
+    NEPB_VW_TMA(4, false)
+    NEPB_VW_TMA(4, true)
+    NEPB_VW_TMA(8, true)
+#undef NEPB_VW_TMA
+    if (rc == 1) {
+        NEPB_LAUNCH_CHECK();
+    }
+    return rc;
+}
+
 // tiled path for 5..32 columns (returns 0 when it does not apply: few columns, unsupported value layout, no tiles)
 static int launch_tiled(const nepb_spmf* h, bool diag, int kt, int ldv, int ldz, const double2* V, double2* Z, const CoefP& cp,
                         const double2* cdiag) {
@@ -784,7 +1015,10 @@ static int launch_tiled(const nepb_spmf* h, bool diag, int kt, int ldv, int ldz,
 static int launch_fused(const nepb_spmf* h, bool diag, int kt, int ldv, int ldz, const double2* V, double2* Z,
                         const CoefP& cp, const double2* cdiag) {
     {
-        const int rc = launch_tiled(h, diag, kt, ldv, ldz, V, Z, cp, cdiag);
+        int rc = launch_tma(h, diag, kt, ldv, ldz, V, Z, cp, cdiag);
+        if (rc == 1) return NEPB_OK;
+        if (rc != 0) return rc;
+        rc = launch_tiled(h, diag, kt, ldv, ldz, V, Z, cp, cdiag);
         if (rc == 1) return NEPB_OK;
         if (rc != 0) return rc;
     }
@@ -980,7 +1214,7 @@ int nepb_spmf_create(int64_t n, int p, const int64_t* const* colptr, const int64
     h->h_csr_of_csc = (int32_t*)dup(u.csr_of_csc.data(), sizeof(int32_t) * u.nnz);
 #define NEPB_UP(buf, src, count, T)                                                                       \
     do {                                                                                                  \
-        cudaError_t e_ = buf.alloc(count);                                                                \
+        cudaError_t e_ = buf.alloc((count) + 16 / sizeof(T)); /* slack: bulk copies round slice ends up to 16 bytes */ \
         if (e_ == cudaSuccess) e_ = cudaMemcpy(buf.p, src, sizeof(T) * (count), cudaMemcpyHostToDevice);  \
         if (e_ != cudaSuccess) {                                                                          \
             set_error("CUDA error while uploading the operator: %s", cudaGetErrorString(e_));             \
@@ -1000,6 +1234,7 @@ int nepb_spmf_create(int64_t n, int p, const int64_t* const* colptr, const int64
 int nepb_spmf_destroy(nepb_spmf* h) {
     if (h) {
         if (h->lu_symbolic) lu_symbolic_release(h->lu_symbolic);
+        for (void* m : h->lu_matched) lu_symbolic_release(m);
         delete h;
     }
     return NEPB_OK;

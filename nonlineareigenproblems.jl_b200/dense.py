@@ -45,9 +45,21 @@ def colnorms(A: Block, c0: int, nc: int, rows: int = 0):
     return out
 
 
-def solve_block(lu, Bb: Block, bcol0: int, nrhs: int, Xb: Block, xcol0: int, alpha=1.0, shift=0):
-    a = np.array([complex(alpha)], dtype=np.complex128)
-    check(lib.nepb_lu_solve_block(lu._h, shift, Bb._h, bcol0, nrhs, Xb._h, xcol0, ptr(a)))
+def solve_block(solver, Bb: Block, bcol0: int, nrhs: int, Xb: Block, xcol0: int, alpha=1.0, shift=0):
+    """X[:, xcol0:xcol0+nrhs] = alpha * lin_solve(solver, B[:, bcol0:bcol0+nrhs]) with the operands in HBM.
+
+    `solver` is whatever the linsolvercreator returned (the reference's extension point, LinSolvers.jl:100,124-137): a device
+    factorisation (B200FactorizeLinSolver, or a bare B200LU) solves in place with the solver's `umfpack_refinements` steps of
+    iterative refinement; any other LinSolver goes through its own `lin_solve` with host arrays."""
+    lu = getattr(solver, "lu", solver)
+    if hasattr(lu, "_h") and hasattr(lu, "nshift"):
+        a = np.array([complex(alpha)], dtype=np.complex128)
+        refine = int(getattr(solver, "refinements", 0))
+        check(lib.nepb_lu_solve_block_ex(lu._h, shift, Bb._h, bcol0, nrhs, Xb._h, xcol0, ptr(a), refine, None))
+        return
+    B = Bb.download(bcol0, nrhs)
+    X = np.asarray(solver.lin_solve(B if nrhs > 1 else B[:, 0]), dtype=np.complex128).reshape(Bb.n, nrhs, order="F")
+    Xb.upload(alpha * X, xcol0)
 
 
 def mlincomb_block(nep: B200SPMF, lam, Vb: Block, vcol0: int, k: int, a, Zb: Block, zcol0: int):
@@ -87,7 +99,6 @@ def tiar_device(nep: B200SPMF, maxit=30, linsolvercreator=None, tol=np.finfo(flo
     alpha = np.asarray(gamma, dtype=np.complex128) ** np.arange(m + 1)
     alpha[0] = 0
     M0inv = (linsolvercreator or B200LinSolverCreator()).create_linsolver(nep, sigma)
-    lu = M0inv.lu
     Zb, yb, tb = Block(n, m + 1), Block(n, m + 1), Block(n, 1)
     Qb, Rb = Block(n, m), Block(n, m)
     v = np.random.default_rng(0).standard_normal(n) if v is None else np.asarray(v, dtype=np.complex128)
@@ -103,7 +114,7 @@ def tiar_device(nep: B200SPMF, maxit=30, linsolvercreator=None, tol=np.finfo(flo
         Cm = a[:k, k - 1, :k].T / np.arange(1, k + 1)[None, :]
         block_gemm(Zb, 0, k, Cm, yb, 1)
         mlincomb_block(nep, sigma, yb, 0, k + 1, alpha[:k + 1], tb, 0)
-        solve_block(lu, tb, 0, 1, Zb, k, alpha=-1.0)  # Z[:, k] = -lin_solve(M0inv, y1)
+        solve_block(M0inv, tb, 0, 1, Zb, k, alpha=-1.0)  # Z[:, k] = -lin_solve(M0inv, y1)
         h0, t[k], _ = dgks(Zb, k, Zb, k)
         t[:k] = h0
         g = np.zeros((k + 1, k + 1), dtype=np.complex128)
@@ -154,7 +165,6 @@ def iar_device(nep: B200SPMF, maxit=30, linsolvercreator=None, tol=np.finfo(floa
     alpha = np.asarray(gamma, dtype=np.complex128) ** np.arange(m + 1)
     alpha[0] = 0
     M0inv = (linsolvercreator or B200LinSolverCreator()).create_linsolver(nep, sigma)
-    lu = M0inv.lu
     Vb = Block(n * (m + 1), m + 1)
     yb, tb = Block(n, m + 1), Block(n, 1)
     Qb, Rb = Block(n, m), Block(n, m)
@@ -169,7 +179,7 @@ def iar_device(nep: B200SPMF, maxit=30, linsolvercreator=None, tol=np.finfo(floa
     while k <= m and conv_eig < neigs:
         check(lib.nepb_iar_expand(Vb._h, k - 1, n, k, yb._h, 1, 1))  # y[:, 1:k+1] = reshape(VV[1:n*k, k], n, k) ./ (1:k)'
         mlincomb_block(nep, sigma, yb, 0, k + 1, alpha[:k + 1], tb, 0)
-        solve_block(lu, tb, 0, 1, yb, 0, alpha=-1.0)
+        solve_block(M0inv, tb, 0, 1, yb, 0, alpha=-1.0)
         check(lib.nepb_iar_pack(yb._h, 0, k + 1, n, Vb._h, k))  # vv = vec(y[:, 1:k+1])
         h, nrm, _ = dgks(Vb, k, Vb, k, rows=n * (k + 1))
         H[:k, k - 1] = h
@@ -239,7 +249,6 @@ def iar_chebyshev_device(nep: B200SPMF, maxit=30, linsolvercreator=None, tol=np.
     errmeasure = errmeasure or DefaultErrmeasure(nep)
     H = np.zeros((m + 1, m), dtype=np.complex128)
     M0inv = (linsolvercreator or B200LinSolverCreator()).create_linsolver(nep, sigma)
-    lu = M0inv.lu
     L = cheb_integration_matrix(m, a, b)
     Tc = np.cos(np.arange(m + 1) * np.arccos((a + b) / (a - b)))
     DDf = cheb_divided_difference_blocks(nep, m, a, b, gamma, sigma)
@@ -260,7 +269,7 @@ def iar_chebyshev_device(nep: B200SPMF, maxit=30, linsolvercreator=None, tol=np.
         block_gemm(xb, 0, k, L[:k, :k], yb, 1)                       # y[:, 2:k+1] = X * L[1:k, 1:k]
         Cm = np.ascontiguousarray(np.stack([Df[:k, :k] @ Tc[:k] for Df in DDf]))  # p x k: term i multiplies X by DDf_i T(c)
         check(lib.nepb_spmf_apply_block_ex(nep._h, _lib.COEF_GENERAL, xb._h, 0, k, 1, ptr(Cm), tb._h, 0))
-        solve_block(lu, tb, 0, 1, yb, 0)                             # y[:, 1] = M0inv * (sum_i A_i X DDf_i T(c))
+        solve_block(M0inv, tb, 0, 1, yb, 0)                             # y[:, 1] = M0inv * (sum_i A_i X DDf_i T(c))
         coef = -np.concatenate([[1.0], Tc[1:k + 1]]).astype(np.complex128)
         block_gemm(yb, 0, k + 1, coef, tb, 0)                        # y0 = -y[:, 1] - y[:, 2:k+1] T(c)[2:k+1]
         copy_cols(tb, 0, 1, yb, 0)

@@ -104,6 +104,18 @@ def analyse_pattern(A, ordering=0, relax_leaf=0, max_np=0, fronts=False):
     return perm, parent, cc, info
 
 
+def matching(A):
+    """Maximum-product row matching and I-matrix scalings of a scipy sparse matrix (host only): row_of_col, dr, dc with
+    |dr_i a_ij dc_j| <= 1 and = 1 on the matching (the static-pivoting preprocessing of the device LU)."""
+    A = A.tocsc()
+    n = A.shape[0]
+    cp, rv = A.indptr.astype(np.int64), A.indices.astype(np.int64)
+    av = np.ascontiguousarray(np.abs(A.data), dtype=np.float64)
+    roc, dr, dc = np.empty(n, np.int32), np.empty(n), np.empty(n)
+    check(lib.nepb_lu_matching(n, ptr(cp), ptr(rv), 0, ptr(av), ptr(roc), ptr(dr), ptr(dc)))
+    return roc, dr, dc
+
+
 # ---------------------------------------------------------------------------------------------
 # LinSolver objects
 # ---------------------------------------------------------------------------------------------
@@ -119,8 +131,15 @@ class B200FactorizeLinSolver(LinSolver):
         self.lu = B200LU(nep, [lam])
         self.refinements = umfpack_refinements
         st = self.lu.status(0)
+        # UMFPACK throws SingularException for an exactly singular matrix (`lu` inside `factorize`, LinSolvers.jl:116).  Here:
+        # a non-finite pivot, or a zero pivot that survived the static-pivoting fallback (bit 3 = row matching in use).  Pivots
+        # that were only lifted (nperturbed > 0) are not fatal by themselves: every solve with such factors is verified through
+        # its backward error in the library and fails loudly there (nepb_lu_solve / nepb_lu_solve_block_ex).
         if st["flags"] & 2:
             raise _lib.SingularException(_lib.NEPB_E_SINGULAR, "non-finite pivot while factorising M(%s)" % (lam,))
+        if st["flags"] & 1:
+            raise _lib.SingularException(_lib.NEPB_E_SINGULAR, "M(%s) is singular to working precision (zero pivot%s)"
+                                         % (lam, " after row matching" if st["flags"] & 8 else ""))
         self.status = st
 
     def lin_solve(self, b, tol=0):

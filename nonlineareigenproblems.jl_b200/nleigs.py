@@ -78,7 +78,7 @@ def nleigs_backslash(nep: B200SPMF, cache: DeviceLinSolverCache, wc, sigma, k, b
     Cm = -np.ascontiguousarray(np.asarray(sgdd, dtype=np.complex128)[:, 1:N + 1])  # p x N: block i = N-vector
     check(lib.nepb_spmf_apply_block_ex(nep._h, _lib.COEF_GENERAL, zb._h, 1, N, 1, ptr(Cm), t._h, 0))
     solver = cache.get(shift, add_to_cache)
-    solve_block(solver.lu, t, 0, 1, bwb, 0, alpha=1.0 / beta[0])  # Bw_0 is unused from here on: it receives w0
+    solve_block(solver, t, 0, 1, bwb, 0, alpha=1.0 / beta[0])  # Bw_0 is unused from here on: it receives w0
     block_gemm(bwb, 0, m, CW, wcb, 0)
     w = wcb.download()
     for b in (wcb, bwb, zb, t):
@@ -120,6 +120,13 @@ class _Basis:
         self.b.close()
 
 
+def _release(solver):
+    """Free the device factors of a solver that owns some (user-supplied LinSolvers may not)."""
+    lu = getattr(solver, "lu", None)
+    if lu is not None and hasattr(lu, "close"):
+        lu.close()
+
+
 def _device_backslash(nep, cache, basis, l, wcb, bwb, zb, tb, sigma, k, beta, N, xi, sgdd, add_to_cache):
     """backslash (:399-518) for continuation vector V[:, l-1]; the result is packed into column l of the basis.
     Same products as nleigs_backslash, operands resident in HBM."""
@@ -131,11 +138,11 @@ def _device_backslash(nep, cache, basis, l, wcb, bwb, zb, tb, sigma, k, beta, N,
     Cm = -np.ascontiguousarray(np.asarray(sgdd, dtype=np.complex128)[:, 1:N + 1])
     check(lib.nepb_spmf_apply_block_ex(nep._h, _lib.COEF_GENERAL, zb._h, 1, N, 1, ptr(Cm), tb._h, 0))
     solver = cache.get(shift, add_to_cache)
-    solve_block(solver.lu, tb, 0, 1, bwb, 0, alpha=1.0 / beta[0])
+    solve_block(solver, tb, 0, 1, bwb, 0, alpha=1.0 / beta[0])
     block_gemm(bwb, 0, m, CW, wcb, 0)
     check(lib.nepb_iar_pack(wcb._h, 0, m, n, basis.b._h, l))
     if not add_to_cache and cache.solvers.get(complex(shift)) is not solver:
-        solver.lu.close()  # a one-off factorisation (linsolvercache.jl:21-23); never a cached one
+        _release(solver)  # a one-off factorisation (linsolvercache.jl:21-23); never a cached one
 
 
 def nleigs(nep: B200SPMF, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf,), maxdgr=100, minit=20, maxit=200, tol=1e-10,
@@ -194,7 +201,7 @@ def nleigs(nep: B200SPMF, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf
     first = cache.get(sigma[0], reusefact == 2)
     v = first.lin_solve(v / np.linalg.norm(v))
     if cache.solvers.get(complex(sigma[0])) is not first:
-        first.lu.close()
+        _release(first)
     cols = kmax + 1
     basis = _Basis(n, cols)
     col0 = np.zeros(n * basis.blocks, dtype=np.complex128)
@@ -320,5 +327,5 @@ def nleigs(nep: B200SPMF, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf
     for blk in [basis, Qb, Rb, tb] + [work[key] for key in ("wc", "bw", "z") if key in work]:
         blk.close()
     for s in cache.solvers.values():
-        s.lu.close()
+        _release(s)
     return lam[conv], X[:, conv], res[conv], details

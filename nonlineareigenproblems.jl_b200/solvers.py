@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import warnings
+
 import numpy as np
 
 from . import _lib
@@ -76,6 +78,20 @@ def _errs(errmeasure, lams, Q):
 # ---------------------------------------------------------------------------------------------
 # contour integration
 # ---------------------------------------------------------------------------------------------
+def _check_node_flags(flags):
+    """Quadrature nodes whose factorisation failed make the moments wrong: the reference gets an accurate UMFPACK solve or
+    a SingularException at such a node (LinSolvers.jl:116), never a silent perturbation.  bit1 = non-finite pivot, bit0 = a
+    zero pivot replaced, bit2 (4) = tiny pivots lifted -- after the library's static-pivoting fallback (bit3) has been tried."""
+    near = np.flatnonzero(flags & 16)
+    if near.size:
+        warnings.warn("%d quadrature node(s) have pivots below 1e-8 max|M_ij|: an eigenvalue lies very close to the contour" % near.size)
+    bad = np.flatnonzero(flags & (1 | 2 | 4))
+    if bad.size:
+        raise _lib.SingularException(_lib.NEPB_E_SINGULAR,
+                                     "factorisation failed at %d quadrature node(s) (first: %d, flags %d): an eigenvalue lies on the "
+                                     "contour or M is singular to working precision there" % (bad.size, bad[0], int(flags[bad[0]])))
+
+
 class ContourIntegrator:
     """The MatrixIntegrator seam (method_contour_common.jl:18-45) for B200 operators: all nodes in one device call."""
 
@@ -173,8 +189,7 @@ def contour_beyn(nep: B200SPMF, Vh=None, sigma=0.0, radius=1.0, N=1000, neigs=2,
     finally:
         if own:
             integ.close()
-    if np.any(flags & 2):
-        raise _lib.SingularException(_lib.NEPB_E_SINGULAR, "non-finite pivot at a quadrature node: an eigenvalue lies on the contour")
+    _check_node_flags(flags)
     A0, A1 = S[:, :, 0], S[:, :, 1]
     lam, V, info = beyn_extract(A0, A1, sigma, radius, k, neigs, tol, rank_drop_tol, errmeasure, sanity_check)
     info["node_flags"] = flags
@@ -401,8 +416,7 @@ def contour_block_SS(nep: B200SPMF, U=None, V=None, sigma=0.0, radius=1.0, N=100
         Shat, flags = integ.integrate(lams, W, V, reduce=world > 1)
     finally:
         integ.close()
-    if np.any(flags & 2):
-        raise _lib.SingularException(_lib.NEPB_E_SINGULAR, "non-finite pivot at a quadrature node: an eigenvalue lies on the contour")
+    _check_node_flags(flags)
     lam, Vec, mprime = block_ss_extract(Shat, np.asarray(U, dtype=np.complex128), sigma, K, rank_drop_tol)
     if return_moments:
         return lam, Vec, Shat, mprime

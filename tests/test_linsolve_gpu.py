@@ -118,10 +118,78 @@ def test_stencil_pep_solve():
 
 
 def test_singular_matrix_is_reported():
+    """An exactly singular matrix: `factorize` throws SingularException in the reference (UMFPACK, LinSolvers.jl:116); here the zero
+    pivot survives the static-pivoting fallback and the solver refuses to be built; the raw handle reports the flags."""
     Z = sp.csc_matrix(np.array([[1.0, 2.0], [2.0, 4.0]]))
     d = B200SPMF([Z], [ONE])
-    s = nepb200.B200FactorizeLinSolver(d, 0.0, umfpack_refinements=0)
-    assert s.status["flags"] & 1  # exactly singular: flagged, like UMFPACK's singular-matrix warning status
+    with pytest.raises(nepb200.SingularException):
+        nepb200.B200FactorizeLinSolver(d, 0.0, umfpack_refinements=0)
+    lu = nepb200.B200LU(d, [0.0])
+    st = lu.status(0)
+    assert st["flags"] & 1 and st["flags"] & 8  # zero pivot, row matching was tried
+    with pytest.raises(nepb200.SingularException):  # a solve with replaced pivots is verified and rejected, never silent
+        lu.solve(np.array([1.0, 0.0]), 0, 2)
+    # structurally singular: no row matching exists
+    d0 = B200SPMF([sp.csc_matrix(np.array([[1.0, 1.0], [0.0, 0.0]]))], [ONE])
+    with pytest.raises(nepb200.SingularException):
+        nepb200.B200LU(d0, [0.0])
+
+
+@pytest.mark.parametrize("transpose", [False, True])
+def test_qdep0_sigma0_static_pivoting(transpose):
+    """qdep0 at sigma = 0, the configuration of test/infbilanczos.jl:11-15 (operator and its transpose): M(0) = A0 + A1 has 20
+    nonzero diagonal entries out of 1000, so pivoting inside the fronts' pivot blocks meets zero pivots; the library falls
+    back to the maximum-product row matching + scaling (flag bit 3) and must then agree with SuperLU's partial pivoting."""
+    A0, A1 = g.load_qdep0_matrices()
+    if transpose:
+        A0, A1 = sp.csc_matrix(A0.T), sp.csc_matrix(A1.T)
+    n = A0.shape[0]
+    dnep = B200SPMF([-sp.identity(n, format="csc"), A0, A1], [Monomial(2), ONE, Exp(-1.0)])
+    Mo = sp.csc_matrix(A0 + A1).astype(complex)
+    rng = np.random.default_rng(5)
+    B = rng.standard_normal((n, 3)) + 1j * rng.standard_normal((n, 3))
+    s = nepb200.B200FactorizeLinSolver(dnep, 0.0)
+    assert s.status["flags"] == 8 and s.status["nperturbed"] == 0
+    X = s.lin_solve(B)
+    assert s.lu.last_berr < 1e-15
+    assert np.linalg.norm(Mo @ X - B) / (abs(Mo).sum(axis=0).max() * np.linalg.norm(X)) < 10 * EPS
+    assert np.linalg.norm(X - sla.splu(Mo).solve(B)) / np.linalg.norm(X) < 1e-9
+    # the operator now prefers the matched analysis: other shifts work through it as well, and without refinement
+    lam = -1.0 + 0.2j
+    M1 = sp.csc_matrix(-lam ** 2 * sp.identity(n) + A0 + np.exp(-lam) * A1)
+    s1 = nepb200.B200FactorizeLinSolver(dnep, lam, umfpack_refinements=0)
+    assert s1.status["flags"] == 8
+    X1 = s1.lin_solve(B)
+    assert np.linalg.norm(M1 @ X1 - B) / (abs(M1).sum(axis=0).max() * np.linalg.norm(X1)) < 1e-12
+    # device-resident solve with refinement (nepb_lu_solve_block_ex)
+    from nepb200 import Block
+    from nepb200.dense import solve_block
+    Bb, Xb = Block.from_host(B), Block(n, 3)
+    solve_block(s, Bb, 0, 3, Xb, 0, alpha=-1.0)
+    assert np.linalg.norm(Xb.download() + X) / np.linalg.norm(X) < 1e-12
+
+
+def test_contour_nodes_with_zero_diagonal():
+    """The contour pipeline takes the same fallback: moments of qdep0 on a small circle around 0 (|lambda|^2 ~ 1e-4 on the
+    diagonal) against a SuperLU loop."""
+    from nepb200.solvers import ContourIntegrator
+    A0, A1 = g.load_qdep0_matrices()
+    n = A0.shape[0]
+    dnep = B200SPMF([-sp.identity(n, format="csc"), A0, A1], [Monomial(2), ONE, Exp(-1.0)])
+    N, k = 8, 3
+    lams = 0.01 * np.exp(2j * np.pi * (np.arange(N) + 0.5) / N)
+    W = np.stack([np.ones(N), lams], axis=1).astype(complex) / N
+    Vh = np.random.default_rng(3).standard_normal((n, k))
+    integ = ContourIntegrator(dnep, k, 2, N)
+    S, flags = integ.integrate(lams, W, Vh, reduce=False)
+    integ.close()
+    assert np.all(flags & 8) and not np.any(flags & 7)
+    ref = np.zeros((n, k, 2), dtype=complex)
+    for i, lam in enumerate(lams):
+        X = sla.splu(sp.csc_matrix(-lam ** 2 * sp.identity(n) + A0 + np.exp(-lam) * A1)).solve(Vh.astype(complex))
+        for j in range(2):
+            ref[:, :, j] += W[i, j] * X
+    assert np.linalg.norm(S - ref) / np.linalg.norm(ref) < 1e-10
 
 
 def test_creator_cache_semantics():

@@ -89,3 +89,48 @@ def test_fast_and_legacy_symbolic_algorithms_agree(monkeypatch):
                 for key in ("nnz_factor", "front_entries", "nfronts", "nlevels", "max_front", "flops", "solve_rows"):
                     assert st[key] == st2[key]
                 assert np.array_equal(st["np"], st2["np"]) and np.array_equal(st["nf"], st2["nf"]) and np.array_equal(st["level"], st2["level"])
+
+
+def test_max_product_matching_is_optimal_and_scaled():
+    """nepb_lu_matching (lu_matching.cpp): the static-pivoting preprocessing that stands in for UMFPACK's numerical pivoting.
+    Integer result (a permutation) checked for optimality against SciPy's sparse assignment solver; the scalings must turn
+    the matrix into an I-matrix (matched entries 1, all others <= 1)."""
+    from scipy.sparse.csgraph import min_weight_full_bipartite_matching
+    rng = np.random.default_rng(11)
+    A0, A1 = g.load_qdep0_matrices()
+    cases = [sp.csc_matrix(A0 + A1), sp.csc_matrix((A0 + A1).T)]  # test/infbilanczos.jl at sigma = 0: 980 zero diagonal entries
+    for n, dens in ((1, 1.0), (6, 0.5), (60, 0.1), (300, 0.02)):
+        # a hidden permutation guarantees structural non-singularity; values over ten orders of magnitude
+        R = sp.random(n, n, dens, random_state=int(rng.integers(1 << 30)), format="csr")
+        Pm = sp.csr_matrix((np.ones(n), (np.arange(n), rng.permutation(n))), shape=(n, n))
+        M = (R + Pm).tocsc()
+        M.data = np.exp(rng.uniform(-12, 12, M.nnz)) * rng.choice([-1.0, 1.0], M.nnz)
+        cases.append(M)
+    for M in cases:
+        n = M.shape[0]
+        roc, dr, dc = nepb200.matching(M)
+        assert sorted(roc.tolist()) == list(range(n))
+        Aabs = abs(M).tocsr()
+        matched = np.asarray(Aabs[roc, np.arange(n)]).ravel()
+        assert np.all(matched > 0)
+        W = Aabs.copy()
+        W.data = 40.0 - np.log(W.data)  # positive weights: SciPy's solver drops explicit zeros
+        r, c = min_weight_full_bipartite_matching(W)
+        best = np.log(np.asarray(Aabs[r, c]).ravel()).sum()
+        assert abs(np.log(matched).sum() - best) <= 1e-9 * max(1.0, abs(best))
+        S = sp.diags(dr) @ Aabs @ sp.diags(dc)
+        assert S.max() <= 1 + 1e-12
+        assert np.allclose(np.asarray(S.tocsr()[roc, np.arange(n)]).ravel(), 1.0, rtol=1e-12)
+    # structurally singular patterns are reported
+    import pytest
+    with pytest.raises(nepb200.SingularException):
+        nepb200.matching(sp.csc_matrix(np.array([[1.0, 1.0, 0.0], [1.0, 1.0, 0.0], [1.0, 1.0, 0.0]])))
+    # static pivoting on the matched, scaled qdep0 matrix is stable without any further row exchange (SuperLU told not to pivot)
+    import scipy.sparse.linalg as sla
+    M = cases[0]
+    roc, dr, dc = nepb200.matching(M)
+    B = (sp.diags(dr) @ M @ sp.diags(dc)).tocsr()[roc, :].tocsc()
+    lu = sla.splu(B, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+    assert np.array_equal(lu.perm_r, lu.perm_c)
+    b = np.ones(M.shape[0])
+    assert np.linalg.norm(B @ lu.solve(b) - b) / np.linalg.norm(b) < 1e-8

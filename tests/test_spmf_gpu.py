@@ -260,3 +260,24 @@ def test_row_tiles_of_the_multicolumn_kernel():
     assert d3.tiles_info() == (0, 0, 0)
     V = rng.standard_normal((400, 8)) + 0j
     assert relerr(d3.compute_MM(np.eye(8), V), C.tocsc() @ V) < RTOL
+
+
+@pytest.mark.parametrize("k,q", [(40, 40), (12, 12), (33, 1), (7, 45), (45, 7), (64, 64), (101, 3)])
+def test_general_mode_square_and_rectangular_blocks(k, q):
+    """Z = sum_i A_i (V C_i) with dense k x q blocks straight through nepb_spmf_apply(COEF_GENERAL): the shapes of
+    infbilanczos' Hankel blocks (q = k, p*q > 64; method_infbilanczos.jl:229-244), of Proj_SPMF_NEP's selector blocks
+    (q = p*k; NEPTypes.jl:724-790) and of compute_Mlincomb at depth 101 (q = 1), against NumPy on gun (p = 4) and qdep0 (p = 3)."""
+    import scipy.sparse as sp
+    from nepb200 import _lib
+    rng = np.random.default_rng(k * 100 + q)
+    K, M, W1, W2 = g.load_gun_matrices()
+    A0, A1 = g.load_qdep0_matrices()
+    for mats in ([K, -M, W1, W2], [-sp.identity(A0.shape[0], format="csc"), A0, A1]):
+        d = B200SPMF(mats, [ONE] * len(mats))
+        n = d.n
+        V = rng.standard_normal((n, k)) + 1j * rng.standard_normal((n, k))
+        Cs = [rng.standard_normal((k, q)) + 1j * rng.standard_normal((k, q)) for _ in mats]
+        Cblk = np.stack([np.asfortranarray(c).T.copy() for c in Cs])  # p blocks, each column-major k x q
+        Z = d.apply(_lib.COEF_GENERAL, V, Cblk, q)
+        Zr = sum(m @ (V @ c) for m, c in zip(mats, Cs))
+        assert relerr(Z, Zr) < 1e-13

@@ -116,12 +116,10 @@ def test_projection_device_matches_oracle():
     assert np.linalg.norm(pp.compute_Mder(lam) - No) <= 1e-12 * np.linalg.norm(No)
 
 
-@pytest.mark.skipif(not os.environ.get("NEPB_RUN_UNVALIDATED"), reason="kernel variant compiled but never run on a device yet: "
-                    "set NEPB_RUN_UNVALIDATED=1 (under a timeout) to try it")
 def test_tiled_spmm_tma_bulk_variant():
     """The opt-in variant of the tiled multi-column SpMM that stages every V row with one TMA bulk copy (cp.async.bulk +
     mbarrier, NEPB_SPMM_BULK=1) must give the same product as the default cp.async variant, bit for bit (same summation
-    order), and agree with the oracle.  Compiled and inspected in round 1 (UBLKCP / SYNCS in the SASS), first run here."""
+    order), and agree with the oracle.  First run on a B200 at the start of round 2 (gpurun_out/r2_first_tma.log: passed)."""
     import scipy.sparse as sp
     from nepb200 import B200SPMF, Monomial
     mats, _ = g.stencil_pep(48)

@@ -11,3 +11,4 @@ mkdir -p gpurun_out
 (NEPB_SPMM_BULK=1 timeout 200 python bench.py --no-cpu-baseline --steps 3 --warmup 3 2>&1 | grep "spmm k=8") | tee gpurun_out/r2_first_bench_bulk.log
 timeout 60 python tools/contour_step.py 3 10 16 16 | tee gpurun_out/r2_first_step16.log
 timeout 60 python tools/contour_step.py 3 5 128 128 | tee gpurun_out/r2_first_step128.log
+(timeout 120 python tools/qdep0_lu_diag.py 2>&1 | tail -40) | tee gpurun_out/r2_first_qdep0.log
