@@ -357,8 +357,7 @@ __host__ __device__ inline TmaSmem tma_smem_layout(int max_cols, int max_nnz, in
     o += (unsigned)max_cols * kt * 16;
     L.sA = o;
     o += ((unsigned)max_nnz * vw * 8 + 16 + 15) & ~15u;  // + slack for the rounded-down start
-    L.sM = o;
-    if (!diag) o += (unsigned)max_nnz * 16;
+    L.sM = o;  // (unused since the combine pass was dropped)
     L.sL = o;
     o += ((unsigned)max_nnz * 2 + 16 + 15) & ~15u;
     L.sRp = o;
@@ -369,14 +368,16 @@ __host__ __device__ inline TmaSmem tma_smem_layout(int max_cols, int max_nnz, in
     return L;
 }
 
-template <int VW, bool CA, bool DIAG, int CPT>
+template <int VW, bool CA, bool DIAG, int CPT, int GC>
 __global__ void __launch_bounds__(256) spmm_tma_kernel(int kt, int ldv, int ldz, int max_cols, int max_nnz, int tile_rows,
                                                        const int4* __restrict__ tiles, const int2* __restrict__ runs,
                                                        const int* __restrict__ tile_cols, const int* __restrict__ rowptr,
                                                        const uint16_t* __restrict__ lidx,
                                                        const double* __restrict__ vals, const double2* __restrict__ V,
                                                        double2* __restrict__ Z, const CoefP cp, const double2* __restrict__ cdiag, int p) {
-    constexpr int GC = 8;
+    // GC lanes per row, lane gc owns the dense columns gc, gc + GC, ..  Every shared-memory wavefront DELIVERS at most 128
+    // bytes to registers, so a 16-byte broadcast to the GC lanes of a row costs GC/8 of a wavefront per nonzero on top of the
+    // k/8 wavefronts of the V row itself: GC = 4 halves the coefficient / index traffic of GC = 8 (profiles/r2_ncu_spmm_tma*.txt).
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TmaSmem L = tma_smem_layout(max_cols, max_nnz, kt, VW, DIAG, tile_rows);
     double2* sV = (double2*)(smem_raw + L.sV);
@@ -435,16 +436,7 @@ __global__ void __launch_bounds__(256) spmm_tma_kernel(int kt, int ldv, int ldz,
                          : "memory");
         }
     }
-    double2* sM = (double2*)(smem_raw + L.sM);
-    if constexpr (!DIAG) {  // combined coefficient of every nonzero, once
-        for (int e = tid; e < nnz; e += nth) {
-            double v[VW];
-#pragma unroll
-            for (int t = 0; t < VW; ++t) v[t] = sA[e * VW + t];
-            sM[e] = combine<VW, CA>(v, [&](int i) { return cp.c[i]; });
-        }
-    }
-    __syncthreads();
+    __syncthreads();  // the row pointers
     int start = 0, end = 0;
     if (r < nrows) {
         start = sRp[r];
@@ -453,23 +445,69 @@ __global__ void __launch_bounds__(256) spmm_tma_kernel(int kt, int ldv, int ldz,
     double2 acc[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) acc[j] = make_double2(0.0, 0.0);
-#pragma unroll 2
-    for (int idx = start; idx < end; ++idx) {
-        const double2* xr = sV + (int)sL[idx] * kt + gc;
-        if constexpr (!DIAG) {
-            const double2 m = sM[idx];
+    // Row products straight from the raw term values (two 16-byte broadcast reads per nonzero for p = 4 real terms; no separate
+    // combine pass: its strided shared-memory reads cost a full wavefront per nonzero, profiles/r2_ncu_spmm_tma_v1.txt).
+    // UN nonzeros per trip with all loads issued before the arithmetic.
+    constexpr int UN = CPT >= 3 ? 2 : 4;
+    for (int base = start; base < end; base += UN) {
+        int li[UN];
+        double v[UN][VW];
+        double2 x[UN][CPT];
 #pragma unroll
-            for (int j = 0; j < CPT; ++j)
-                if (gc + j * GC < kt) cfma(acc[j], m, xr[j * GC]);
-        } else {
-            double v[VW];
+        for (int u = 0; u < UN; ++u) li[u] = (base + u < end) ? (int)sL[base + u] : -1;
 #pragma unroll
-            for (int t = 0; t < VW; ++t) v[t] = sA[idx * VW + t];
+        for (int u = 0; u < UN; ++u) {
+            if (li[u] >= 0) {
+                const double* vp = sA + (size_t)(base + u) * VW;
+                if constexpr (VW % 2 == 0) {
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-                if (gc + j * GC < kt) {
-                    const double2 m = combine<VW, CA>(v, [&](int i) { return cd[j][i]; });
-                    cfma(acc[j], m, xr[j * GC]);
+                    for (int t = 0; t < VW; t += 2) {
+                        double2 w;
+                        if (a_skip == 0) w = *(const double2*)(vp + t);  // uniform branch: 16-byte aligned slice
+                        else w = make_double2(vp[t], vp[t + 1]);
+                        v[u][t] = w.x;
+                        v[u][t + 1] = w.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < VW; ++t) v[u][t] = vp[t];
+                }
+                const double2* xr = sV + li[u] * kt + gc;
+                if constexpr (GC == 8) {
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) x[u][j] = (gc + j * GC < kt) ? xr[j * GC] : make_double2(0.0, 0.0);
+                } else {
+                    // GC = 4: a quarter-warp (one LDS.128 wavefront) serves two rows, 64 bytes each; the two pieces must fall into
+                    // different halves of the 32 banks.  The half of piece j is (li*kt/4 + j) mod 2: neighbouring pieces are
+                    // read in swapped order when (row parity + li*kt/4) is odd, and swapped back in registers.
+                    const int s = (r + ((li[u] * kt) >> 2)) & 1;
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) {
+                        const int jj = ((j | 1) < CPT) ? (j ^ s) : j;  // pairs (0,1), (2,3), ..; an odd last piece stays
+                        x[u][j] = (gc + jj * GC < kt) ? xr[jj * GC] : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int j = 0; j + 1 < CPT; j += 2) {
+                        const double2 a = x[u][j], b = x[u][j + 1];
+                        x[u][j] = s ? b : a;
+                        x[u][j + 1] = s ? a : b;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (li[u] >= 0) {
+                if constexpr (!DIAG) {
+                    const double2 m = combine<VW, CA>(v[u], [&](int i) { return cp.c[i]; });
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) cfma(acc[j], m, x[u][j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) {
+                        const double2 m = combine<VW, CA>(v[u], [&](int i) { return cd[j][i]; });
+                        cfma(acc[j], m, x[u][j]);
+                    }
                 }
             }
         }
@@ -774,7 +812,7 @@ static int spmf_build_tiles(const nepb_spmf* h, int which) {
     nepb_spmf::TileSet& T = h->tiling[which];
     if (T.state) return T.state;
     const int tile_rows = which == 0 ? 32 : 16;
-    const int tile_cols_max = 6 * tile_rows;
+    const int tile_cols_max = which == 0 ? 6 * tile_rows : 7 * tile_rows;  // 16 rows of a 5-line stencil touch 100 columns
     const int64_t n = h->n;
     const int32_t* rp = h->h_rowptr;
     const int32_t* ci = h->h_colind;
@@ -921,26 +959,35 @@ static int launch_tiled_vw(const nepb_spmf* h, const nepb_spmf::TileSet& T, int 
 }
 
 template <int VW, bool CA, bool DIAG>
-static int launch_tma_vw(const nepb_spmf* h, const nepb_spmf::TileSet& T, int tile_rows, int kt, int ldv, int ldz, const double2* V,
+static int launch_tma_vw(const nepb_spmf* h, const nepb_spmf::TileSet& T, int tile_rows, int gc, int kt, int ldv, int ldz, const double2* V,
                          double2* Z, const CoefP& cp, const double2* cdiag) {
     const TmaSmem L = tma_smem_layout(T.max_cols, T.max_nnz, kt, VW, DIAG, tile_rows);
-    const int threads = 8 * tile_rows;
-#define NEPB_TMA(CPT_)                                                                                                                  \
+#define NEPB_TMA(CPT_, GC_)                                                                                                             \
     do {                                                                                                                                \
         static size_t attr_done[16] = {0};                                                                                              \
         int dev = 0;                                                                                                                    \
         cudaGetDevice(&dev);                                                                                                            \
         if (L.total > 48 * 1024 && L.total > attr_done[dev & 15]) {                                                                     \
-            NEPB_CUDA(cudaFuncSetAttribute(spmm_tma_kernel<VW, CA, DIAG, CPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
+            NEPB_CUDA(cudaFuncSetAttribute(spmm_tma_kernel<VW, CA, DIAG, CPT_, GC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
             attr_done[dev & 15] = L.total;                                                                                              \
         }                                                                                                                               \
-        NEPB_LAUNCH((spmm_tma_kernel<VW, CA, DIAG, CPT_>), (unsigned)T.ntiles, threads, L.total, kt, ldv, ldz, T.max_cols, T.max_nnz,   \
-                    tile_rows, T.tiles.p, T.runs.p, T.cols.p, h->d_rowptr.p, T.lidx.p, h->d_vals.p, V, Z, cp, cdiag, h->p);                       \
+        NEPB_LAUNCH((spmm_tma_kernel<VW, CA, DIAG, CPT_, GC_>), (unsigned)T.ntiles, GC_ * tile_rows, L.total, kt, ldv, ldz, T.max_cols, \
+                    T.max_nnz, tile_rows, T.tiles.p, T.runs.p, T.cols.p, h->d_rowptr.p, T.lidx.p, h->d_vals.p, V, Z, cp, cdiag, h->p);  \
     } while (0)
-    if (kt <= 8) NEPB_TMA(1);
-    else if (kt <= 16) NEPB_TMA(2);
-    else if (kt <= 24) NEPB_TMA(3);
-    else NEPB_TMA(4);
+    if (gc == 4) {
+        if (kt <= 4) NEPB_TMA(1, 4);
+        else if (kt <= 8) NEPB_TMA(2, 4);
+        else if (kt <= 12) NEPB_TMA(3, 4);
+        else if (kt <= 16) NEPB_TMA(4, 4);
+        else if (kt <= 20) NEPB_TMA(5, 4);
+        else if (kt <= 24) NEPB_TMA(6, 4);
+        else NEPB_TMA(8, 4);
+    } else {
+        if (kt <= 8) NEPB_TMA(1, 8);
+        else if (kt <= 16) NEPB_TMA(2, 8);
+        else if (kt <= 24) NEPB_TMA(3, 8);
+        else NEPB_TMA(4, 8);
+    }
 #undef NEPB_TMA
     return 1;
 }
@@ -948,22 +995,26 @@ static int launch_tma_vw(const nepb_spmf* h, const nepb_spmf::TileSet& T, int ti
 // the TMA-staged tiled product (default for 5..32 columns when the operands allow bulk copies); 0 = does not apply
 static int launch_tma(const nepb_spmf* h, bool diag, int kt, int ldv, int ldz, const double2* V, double2* Z, const CoefP& cp,
                       const double2* cdiag) {
-    static const bool enabled = !(getenv("NEPB_SPMM_TMA") && atoi(getenv("NEPB_SPMM_TMA")) == 0);
+    const bool enabled = !(getenv("NEPB_SPMM_TMA") && atoi(getenv("NEPB_SPMM_TMA")) == 0);  // read per call: tests / tools toggle it
     if (!enabled || kt < 5 || getenv("NEPB_SPMM_CFG") || getenv("NEPB_SPMM_BULK")) return 0;
     if (((uintptr_t)V & 15) != 0) return 0;  // bulk copies need 16-byte aligned sources (rows are ldv*16 bytes apart)
-    int which = kt > 12 ? 1 : 0;
-    if (const char* e = getenv("NEPB_SPMM_TILE_ROWS")) which = atoi(e) == 16 ? 1 : 0;
+    // measured on C4 (profiles/r2_spmm_variants.txt): 16-row tiles (twice the resident CTAs = pipeline stages) beat 32-row
+    // tiles at every width, and 8 lanes per row beat 4 (fewer wavefronts, but too few warps to hide the latencies)
+    int which = 1;
+    if (const char* e = getenv("NEPB_SPMM_TILE_ROWS")) which = atoi(e) == 32 ? 0 : 1;
     if (spmf_build_tiles(h, which) != 1) return 0;
     const nepb_spmf::TileSet& T = h->tiling[which];
     const int tile_rows = which == 0 ? 32 : 16;
+    int gc = 8;
+    if (const char* e = getenv("NEPB_SPMM_GC")) gc = atoi(e) == 4 ? 4 : 8;
     if (tma_smem_layout(T.max_cols, T.max_nnz, kt, h->vw, diag, tile_rows).total > 200 * 1024) return 0;
     const int vw = h->vw;
     const bool ca = h->is_complex;
     int rc = 0;
 #define NEPB_VW_TMA(VW_, CA_)                                                                                  \
     if (!rc && vw == VW_ && ca == CA_)                                                                          \
-        rc = diag ? launch_tma_vw<VW_, CA_, true>(h, T, tile_rows, kt, ldv, ldz, V, Z, cp, cdiag)                \
-                  : launch_tma_vw<VW_, CA_, false>(h, T, tile_rows, kt, ldv, ldz, V, Z, cp, cdiag);
+        rc = diag ? launch_tma_vw<VW_, CA_, true>(h, T, tile_rows, gc, kt, ldv, ldz, V, Z, cp, cdiag)            \
+                  : launch_tma_vw<VW_, CA_, false>(h, T, tile_rows, gc, kt, ldv, ldz, V, Z, cp, cdiag);
     NEPB_VW_TMA(2, false)
     NEPB_VW_TMA(3, false)
     NEPB_VW_TMA(4, false)
@@ -979,7 +1030,7 @@ static int launch_tma(const nepb_spmf* h, bool diag, int kt, int ldv, int ldz, c
 // tiled path for 5..32 columns (returns 0 when it does not apply: few columns, unsupported value layout, no tiles)
 static int launch_tiled(const nepb_spmf* h, bool diag, int kt, int ldv, int ldz, const double2* V, double2* Z, const CoefP& cp,
                         const double2* cdiag) {
-    static const bool enabled = !(getenv("NEPB_SPMM_TILED") && atoi(getenv("NEPB_SPMM_TILED")) == 0);
+    const bool enabled = !(getenv("NEPB_SPMM_TILED") && atoi(getenv("NEPB_SPMM_TILED")) == 0);
     if (!enabled || kt < 5 || getenv("NEPB_SPMM_CFG")) return 0;
     // Measured on config C4 (profiles/r1_spmm_tiled.txt): at k = 8 the tiled kernel runs at 48 % of the HBM roofline against
     // 33 % untiled; from k ~ 16 on the row products are bound by the shared-memory pipe either way (one 128-byte wavefront per

@@ -252,6 +252,18 @@ def test_row_tiles_of_the_multicolumn_kernel():
                 assert relerr(d2.compute_MM((0.1 + 0.3j) * np.eye(k), V), (A + (0.1 + 0.3j) * B) @ V) < RTOL
         finally:
             del os.environ["NEPB_SPMM_TILE_ROWS"]
+    # the other kernel variants behind the same call: the round-1 cp.async tiled kernel, 4 lanes per row (swizzled reads)
+    for env in ({"NEPB_SPMM_TMA": "0"}, {"NEPB_SPMM_GC": "4"}, {"NEPB_SPMM_GC": "4", "NEPB_SPMM_TILE_ROWS": "32"}):
+        os.environ.update(env)
+        try:
+            for k in (5, 8, 12, 20, 24, 32):
+                V = rng.standard_normal((n2, k)) + 1j * rng.standard_normal((n2, k))
+                assert relerr(d2.compute_MM((0.1 + 0.3j) * np.eye(k), V), (A + (0.1 + 0.3j) * B) @ V) < RTOL
+                lams = rng.standard_normal(k) + 1j * rng.standard_normal(k)
+                assert relerr(d2.compute_MM(np.diag(lams), V), A @ V + (B @ V) * lams[None, :]) < RTOL
+        finally:
+            for key in env:
+                del os.environ[key]
     # one dense row: no tiling possible
     C = sp.lil_matrix((400, 400))
     C[7, :] = 1.0
