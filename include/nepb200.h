@@ -96,6 +96,11 @@ int nepb_block_destroy(nepb_block* b);
 /* copy columns [k0, k0+kc) from/to a host column-major array (ld in complex elements) */
 int nepb_block_upload(nepb_block* b, int k0, int kc, const double* host, int64_t ld);
 int nepb_block_download(const nepb_block* b, int k0, int kc, double* host, int64_t ld);
+/* Page-lock a host array that is passed to the host-buffer entry points repeatedly (bases, probes, moments): its transfers
+ * then run as direct DMA at PCIe rate.  Unregistered (pageable) arrays go through a pinned three-slot ring with the host copy,
+ * the DMA and the layout change overlapped (csrc/hostcopy.cu). */
+int nepb_host_register(void* ptr, int64_t bytes);
+int nepb_host_unregister(void* ptr);
 /* raw device pointer of the row-major n x k storage (complex interleaved) */
 void* nepb_block_dev_ptr(nepb_block* b);
 /* same product with operands already in HBM: no host traffic, asynchronous on the library stream */
@@ -190,7 +195,9 @@ int nepb_block_colnorms(const nepb_block* A, int c0, int nc, int64_t rows, doubl
 typedef struct nepb_contour nepb_contour;
 int nepb_contour_create(const nepb_spmf* h, int k, int mg, int batch, nepb_contour** out);
 int nepb_contour_destroy(nepb_contour* c);
-/* reduce != 0: sum the moments over all ranks of the communicator (one ncclAllReduce, in place in HBM).
+/* reduce != 0: sum the moments over all ranks of the communicator (one ncclAllReduce, in place in HBM); reduce == 2: only
+ * rank 0 copies the moments back to its host array S (the extraction of method_beyncontour.jl:114-184 runs once), the other
+ * ranks leave S untouched.
  * node_flags[nnodes] (optional): bit0 zero pivot, bit1 non-finite pivot, bit2 perturbed pivots, bit3 (8) the static-pivoting
  * row matching is in use (the integration is repeated once on a matched analysis when a node on the plain pattern shows
  * any of the other bits), bit4 (16) a pivot below 1e-8 max|M_ij| (the node is close to an eigenvalue). */

@@ -76,6 +76,8 @@ SIGNATURES = {
     "nepb_block_upload": (c_int, [vp, c_int, c_int, vp, c_i64]),
     "nepb_block_download": (c_int, [vp, c_int, c_int, vp, c_i64]),
     "nepb_block_dev_ptr": (vp, [vp]),
+    "nepb_host_register": (c_int, [vp, c_i64]),
+    "nepb_host_unregister": (c_int, [vp]),
     "nepb_spmf_apply_block": (c_int, [vp, c_int, vp, c_int, vp, vp]),
     "nepb_spmf_apply_bytes": (c_i64, [vp, c_int, c_int, c_int]),
     "nepb_spmf_tiles_info": (c_int, [vp, P(c_i64), P(c_i64), P(c_int)]),

@@ -436,8 +436,11 @@ int nepb_contour_integrate(nepb_contour* c, int nnodes, const double* coef, cons
     if (rc) return rc;
     rc = nepb_contour_integrate_dev(c, nnodes, coef, weights, reduce);
     if (rc) return rc;
-    rc = nepb_contour_get_moments(c, S);
-    if (rc) return rc;
+    // reduce = 2: the extraction happens on rank 0 only (method_beyncontour.jl:114-184 runs once), the other ranks skip the download
+    if (!(reduce == 2 && g_rank != 0)) {
+        rc = nepb_contour_get_moments(c, S);
+        if (rc) return rc;
+    }
     if (node_flags) memcpy(node_flags, c->node_flags.data(), sizeof(int) * nnodes);
     return NEPB_OK;
 }

@@ -722,35 +722,6 @@ __global__ void __launch_bounds__(256) mder_kernel(int64_t nnz, int p, int ca, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// layout changes: host column-major (ld) <-> device row-major (k), complex elements
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) colmajor_to_rowmajor_kernel(int64_t n, int kc, const double2* __restrict__ src, int64_t lds,
-                                                                   double2* __restrict__ dst, int ldd, int k0) {
-    __shared__ double2 tile[32][33];
-    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;  // 32 x 8
-    const int64_t r0 = (int64_t)blockIdx.x * 32;
-    const int c0 = blockIdx.y * 32;
-    for (int j = ty; j < 32; j += 8)
-        if (r0 + tx < n && c0 + j < kc) tile[j][tx] = src[(size_t)(c0 + j) * lds + r0 + tx];
-    __syncthreads();
-    for (int j = ty; j < 32; j += 8)
-        if (r0 + j < n && c0 + tx < kc) dst[(size_t)(r0 + j) * ldd + k0 + c0 + tx] = tile[tx][j];
-}
-
-__global__ void __launch_bounds__(256) rowmajor_to_colmajor_kernel(int64_t n, int kc, const double2* __restrict__ src, int lds, int k0,
-                                                                   double2* __restrict__ dst, int64_t ldd) {
-    __shared__ double2 tile[32][33];
-    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-    const int64_t r0 = (int64_t)blockIdx.x * 32;
-    const int c0 = blockIdx.y * 32;
-    for (int j = ty; j < 32; j += 8)
-        if (r0 + j < n && c0 + tx < kc) tile[j][tx] = src[(size_t)(r0 + j) * lds + k0 + c0 + tx];
-    __syncthreads();
-    for (int j = ty; j < 32; j += 8)
-        if (r0 + tx < n && c0 + j < kc) dst[(size_t)(c0 + j) * ldd + r0 + tx] = tile[tx][j];
-}
-
-// ---------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------
 struct TileCfg {
@@ -1192,25 +1163,8 @@ int spmf_apply_device_ld(const nepb_spmf* h, int mode, int k, int q, const doubl
     return launch_stacked(h, q, (const double2*)h->d_tmp_x.p, dZ, ldz);
 }
 
-int upload_colmajor(int64_t n, int kc, const double* host, int64_t ld, DevBuf<double>& stage, double* dst, int ldd, int k0) {
-    // host column-major -> staging (column-major, ld = n) -> row-major
-    NEPB_CUDA(stage.reserve((size_t)2 * n * kc));
-    NEPB_CUDA(cudaMemcpy2DAsync(stage.p, (size_t)n * 16, host, (size_t)ld * 16, (size_t)n * 16, kc, cudaMemcpyHostToDevice, stream()));
-    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((kc + 31) / 32));
-    NEPB_LAUNCH(colmajor_to_rowmajor_kernel, grid, 256, 0, n, kc, (const double2*)stage.p, n, (double2*)dst, ldd, k0);
-    NEPB_LAUNCH_CHECK();
-    return NEPB_OK;
-}
-
-int download_colmajor(int64_t n, int kc, const double* src, int lds, int k0, DevBuf<double>& stage, double* host, int64_t ld) {
-    NEPB_CUDA(stage.reserve((size_t)2 * n * kc));
-    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((kc + 31) / 32));
-    NEPB_LAUNCH(rowmajor_to_colmajor_kernel, grid, 256, 0, n, kc, (const double2*)src, lds, k0, (double2*)stage.p, n);
-    NEPB_LAUNCH_CHECK();
-    NEPB_CUDA(cudaMemcpy2DAsync(host, (size_t)ld * 16, stage.p, (size_t)n * 16, (size_t)n * 16, kc, cudaMemcpyDeviceToHost, stream()));
-    NEPB_CUDA(cudaStreamSynchronize(stream()));
-    return NEPB_OK;
-}
+int upload_colmajor(int64_t n, int kc, const double* host, int64_t ld, DevBuf<double>& stage, double* dst, int ldd, int k0);    // hostcopy.cu
+int download_colmajor(int64_t n, int kc, const double* src, int lds, int k0, DevBuf<double>& stage, double* host, int64_t ld);
 
 }  // namespace nepb
 

@@ -229,8 +229,8 @@ class B200SPMF:
         return M if self.issparse() else M.toarray()
 
     # -- raw kernel access ----------------------------------------------------------------------------
-    def apply(self, mode, V, Cblk, q):
-        """Z = sum_i A_i (V C_i), host arrays in / out."""
+    def apply(self, mode, V, Cblk, q, out=None):
+        """Z = sum_i A_i (V C_i), host arrays in / out (`out`: optional preallocated n x q column-major result)."""
         V = _lib.as_c128_f(V)
         if V.ndim == 1:
             V = V.reshape(-1, 1, order="F")
@@ -238,7 +238,12 @@ class B200SPMF:
         if n != self.n:
             raise ValueError("V has %d rows, the NEP has size %d" % (n, self.n))
         Cblk = np.ascontiguousarray(Cblk, dtype=np.complex128)
-        Z = np.empty((n, q), dtype=np.complex128, order="F")
+        if out is None:
+            Z = np.empty((n, q), dtype=np.complex128, order="F")
+        else:
+            Z = out
+            if Z.shape != (n, q) or Z.dtype != np.complex128 or not Z.flags.f_contiguous:
+                raise ValueError("`out` must be a column-major complex128 array of shape (%d, %d)" % (n, q))
         check(lib.nepb_spmf_apply(self._h, mode, k, q, ptr(V), n, ptr(Cblk), ptr(Z), n))
         return Z
 

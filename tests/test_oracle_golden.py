@@ -225,3 +225,31 @@ def test_oracle_docstring_literals_dep0_100_and_qdep0():
     q = o.nep_gallery("qdep0")
     lam, v = s.resinv(q, lam=-1.0, v=np.ones(q.n), tol=1e-13, maxit=200)
     assert abs(lam - (-1.002466988585764)) < 1e-10
+
+
+def test_c_restatement_of_compute_MM_matches_the_numpy_oracle():
+    """oracle/csrc/spmf_mm.c (the all-core CPU baseline of bench.py): the reference's compute_MM loop (NEPTypes.jl:296-316)
+    in C, checked against oracle.nep.compute_MM on gun and against a direct SciPy product on the synthetic stencil PEP."""
+    import os
+    import subprocess
+    import scipy.sparse as sp
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "oracle")], check=True, capture_output=True)
+    from oracle.cspmf import CSpmf
+    K, M, W1, W2 = g.load_gun_matrices()
+    onep = o.nep_gallery("nlevp_native_gun")
+    lam = 250.0 ** 2 + 1j
+    f = [1.0, lam, 1j * np.sqrt(lam), 1j * np.sqrt(lam - 108.8774 ** 2)]
+    rng = np.random.default_rng(0)
+    V = rng.standard_normal((onep.n, 5)) + 1j * rng.standard_normal((onep.n, 5))
+    Zo = o.compute_MM(onep, lam * np.eye(5), V)
+    c = CSpmf([K, -M, W1, W2])
+    for fn in (c.mm_csc, c.mm_csr):
+        for threads in (1, 3):
+            assert np.linalg.norm(fn(f, V, threads) - Zo) <= 1e-14 * np.linalg.norm(Zo)
+    mats, _ = g.stencil_pep(40)
+    lam = 0.3 + 0.2j
+    c2 = CSpmf(mats)
+    v = rng.standard_normal(1600) + 1j * rng.standard_normal(1600)
+    Zr = sum(m * lam ** i for i, m in enumerate(mats)) @ v
+    assert np.linalg.norm(c2.mm_csr([lam ** i for i in range(4)], v, 2)[:, 0] - Zr) <= 1e-14 * np.linalg.norm(Zr)

@@ -293,3 +293,34 @@ def test_general_mode_square_and_rectangular_blocks(k, q):
         Z = d.apply(_lib.COEF_GENERAL, V, Cblk, q)
         Zr = sum(m @ (V @ c) for m, c in zip(mats, Cs))
         assert relerr(Z, Zr) < 1e-13
+
+
+def test_host_buffer_pipeline_roundtrip():
+    """csrc/hostcopy.cu: column-major host arrays (pageable, with a leading dimension larger than n, and page-locked through
+    nepb_host_register) through the pinned three-slot ring into row-major device blocks and back, bit for bit; sizes chosen so
+    that several chunks (and several slot reuses) occur."""
+    from nepb200 import Block, _lib
+    rng = np.random.default_rng(17)
+    for n, k in ((300_000, 23), (70_001, 9), (1_200_000, 3), (33, 5)):
+        ld = n + 7
+        buf = np.zeros((ld, k), dtype=np.complex128, order="F")
+        buf[:n, :] = rng.standard_normal((n, k)) + 1j * rng.standard_normal((n, k))
+        b = Block(n, k + 2)
+        _lib.check(_lib.lib.nepb_block_upload(b._h, 1, k, _lib.ptr(buf), ld))
+        out = np.full((ld, k), np.nan + 0j, dtype=np.complex128, order="F")
+        _lib.check(_lib.lib.nepb_block_download(b._h, 1, k, _lib.ptr(out), ld))
+        assert np.array_equal(out[:n], buf[:n]) and np.all(np.isnan(out[n:].real))
+        assert np.array_equal(b.download(1, k), buf[:n])
+        # registered (page-locked) host memory: direct DMA
+        _lib.check(_lib.lib.nepb_host_register(_lib.ptr(buf), buf.nbytes))
+        _lib.check(_lib.lib.nepb_host_register(_lib.ptr(out), out.nbytes))
+        try:
+            buf[:n, :] *= 2.0
+            out[:] = 0
+            _lib.check(_lib.lib.nepb_block_upload(b._h, 2, k, _lib.ptr(buf), ld))
+            _lib.check(_lib.lib.nepb_block_download(b._h, 2, k, _lib.ptr(out), ld))
+            assert np.array_equal(out[:n], buf[:n]) and np.all(out[n:] == 0)
+        finally:
+            _lib.check(_lib.lib.nepb_host_unregister(_lib.ptr(buf)))
+            _lib.check(_lib.lib.nepb_host_unregister(_lib.ptr(out)))
+        b.close()
