@@ -14,8 +14,8 @@ from .functions import ScalarFunction, Monomial, Exp, PowShift, Callable, ONE, I
 from .neptypes import SPMF_NEP, PEP, DEP, SumNEP, B200SPMF, Block, B200ProjSPMF, create_proj_NEP  # noqa: F401
 from .linsolve import (B200LU, B200FactorizeLinSolver, B200BackslashLinSolver, B200LinSolverCreator, matching,  # noqa: F401
                        B200BackslashLinSolverCreator, DefaultLinSolverCreator, LinSolverCache, LinSolver, LinSolverCreator,
-                       symbolic_info, symbolic_get, analyse_pattern)
-from .solvers import (contour_block_SS, block_ss_quadrature, block_ss_extract, contour_beyn, ContourIntegrator, beyn_extract, beyn_quadrature, iar, tiar, resinv, infbilanczos, compute_rf, dgks_host,  # noqa: F401
+                       symbolic_info, symbolic_get, analyse_pattern, GMRESLinSolver, GMRESLinSolverCreator, gmres)
+from .solvers import (contour_block_SS, block_ss_quadrature, block_ss_extract, contour_beyn, ContourIntegrator, beyn_extract, beyn_quadrature, iar, tiar, resinv, infbilanczos, ilan, compute_rf, dgks_host,  # noqa: F401
                       ResidualErrmeasure, StandardSPMFErrmeasure, DefaultErrmeasure, NoConvergenceException,
                       LostOrthogonalityException)
 from .dense import (dgks, block_gemm, copy_cols, colnorms, solve_block, mlincomb_block, residual_errors,  # noqa: F401

@@ -161,6 +161,94 @@ class B200BackslashLinSolver(LinSolver):
             lu.close()
 
 
+def gmres(matvec, b, tol, restart=20, maxiter=None, Pl=None, log=False):
+    """Restarted GMRES with modified Gram-Schmidt and Givens rotations -- the algorithm behind IterativeSolvers.gmres! 0.9
+    (restart = min(20, n), maxiter = n, left preconditioner Pl, stopping when the preconditioned residual has dropped by `tol`
+    relative to the initial one).  `matvec` is the LinearMap of LinSolvers.jl:176-178."""
+    b = np.asarray(b, dtype=np.complex128)
+    n = b.shape[0]
+    restart = min(restart, n)
+    maxiter = n if maxiter is None else maxiter
+    if Pl is None:
+        prec = lambda r: r
+    elif callable(Pl):
+        prec = Pl
+    elif hasattr(Pl, "solve"):
+        prec = Pl.solve
+    else:
+        Pm = np.asarray(Pl.todense() if hasattr(Pl, "todense") else Pl)
+        diag_only = np.count_nonzero(Pm - np.diag(np.diag(Pm))) == 0
+        prec = (lambda r, d=np.diag(Pm): r / d) if diag_only else (lambda r: np.linalg.solve(Pm, r))
+    x = np.zeros(n, dtype=np.complex128)
+    r = prec(b - matvec(x))
+    beta0 = np.linalg.norm(r)
+    history = [beta0]
+    if beta0 == 0:
+        return (x, history) if log else x
+    it = 0
+    while it < maxiter:
+        beta = np.linalg.norm(r)
+        V = np.zeros((n, restart + 1), dtype=np.complex128)
+        H = np.zeros((restart + 1, restart), dtype=np.complex128)
+        cs, sn = np.zeros(restart, dtype=np.complex128), np.zeros(restart, dtype=np.complex128)
+        g = np.zeros(restart + 1, dtype=np.complex128)
+        g[0] = beta
+        V[:, 0] = r / beta
+        j_used = 0
+        done = False
+        for j in range(restart):
+            w = prec(matvec(V[:, j]))
+            for i in range(j + 1):  # modified Gram-Schmidt
+                H[i, j] = np.vdot(V[:, i], w)
+                w = w - H[i, j] * V[:, i]
+            H[j + 1, j] = np.linalg.norm(w)
+            if H[j + 1, j] != 0:
+                V[:, j + 1] = w / H[j + 1, j]
+            for i in range(j):  # earlier rotations
+                t = cs[i] * H[i, j] + sn[i] * H[i + 1, j]
+                H[i + 1, j] = -np.conj(sn[i]) * H[i, j] + cs[i] * H[i + 1, j]
+                H[i, j] = t
+            a, c = H[j, j], H[j + 1, j]
+            d = np.sqrt(abs(a) ** 2 + abs(c) ** 2)
+            cs[j], sn[j] = (abs(a) / d, (a / abs(a)) * np.conj(c) / d) if a != 0 else (0.0, 1.0)
+            H[j, j] = cs[j] * a + sn[j] * c
+            H[j + 1, j] = 0.0
+            g[j + 1] = -np.conj(sn[j]) * g[j]
+            g[j] = cs[j] * g[j]
+            j_used = j + 1
+            it += 1
+            history.append(abs(g[j + 1]))
+            if abs(g[j + 1]) <= tol * beta0 or it >= maxiter:
+                done = abs(g[j + 1]) <= tol * beta0
+                break
+        y = np.linalg.solve(np.triu(H[:j_used, :j_used]), g[:j_used])
+        x = x + V[:, :j_used] @ y
+        if done:
+            break
+        r = prec(b - matvec(x))
+    return (x, history) if log else x
+
+
+class GMRESLinSolver(LinSolver):
+    """GMRESLinSolver (LinSolvers.jl:171-188): GMRES on the linear map v -> compute_Mlincomb(nep, lambda, v); every product is one
+    fused device SpMM.  `lin_solve(b; tol=eps)` takes vector right-hand sides only, as in the reference."""
+
+    def __init__(self, nep, lam, kwargs=None):
+        self.nep, self.lam = nep, lam
+        self.kwargs = dict(kwargs or {})
+        self.A = lambda v: nep.compute_Mlincomb(lam, v)
+
+    def lin_solve(self, b, tol=np.finfo(float).eps):
+        b = np.asarray(b)
+        if b.ndim != 1:
+            raise TypeError("GMRESLinSolver.lin_solve takes a vector right-hand side (LinSolvers.jl:183)")
+        kw = dict(self.kwargs)
+        tol = kw.pop("tol", tol)  # the creator's keyword wins, as `solver.kwargs...` is splatted last in the reference
+        tol = kw.pop("reltol", tol)
+        kw.pop("log", None)
+        return gmres(self.A, b, tol, restart=kw.pop("restart", 20), maxiter=kw.pop("maxiter", None), Pl=kw.pop("Pl", None))
+
+
 # ---------------------------------------------------------------------------------------------
 # creators
 # ---------------------------------------------------------------------------------------------
@@ -198,6 +286,16 @@ class B200LinSolverCreator(LinSolverCreator):
 class B200BackslashLinSolverCreator(LinSolverCreator):
     def create_linsolver(self, nep, lam):
         return B200BackslashLinSolver(nep, lam)
+
+
+class GMRESLinSolverCreator(LinSolverCreator):
+    """GMRESLinSolverCreator(;kwargs...) (LinSolverCreators.jl:124-145): the keywords are stored and handed to gmres."""
+
+    def __init__(self, **kwargs):
+        self.kwargs = kwargs
+
+    def create_linsolver(self, nep, lam):
+        return GMRESLinSolver(nep, lam, self.kwargs)
 
 
 DefaultLinSolverCreator = B200LinSolverCreator

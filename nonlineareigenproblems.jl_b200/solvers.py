@@ -528,3 +528,138 @@ def infbilanczos(nep, nept, maxit=30, linsolvercreator=None, linsolvertcreator=N
                 if conv_eig >= neigs or neigs == np.inf:
                     return lam, Q, TT
     raise NoConvergenceException(lam, Q, err, "Number of iterations exceeded. maxit=%d." % maxit)
+
+
+# ---------------------------------------------------------------------------------------------
+# ilan (src/method_ilan.jl:56-261): infinite Lanczos for symmetric NEPs
+# ---------------------------------------------------------------------------------------------
+class _DenseLinSolverCreator:
+    """Linear solves of the small dense projected problem (the reference's `factorize` of a dense matrix, LinSolvers.jl:116)."""
+
+    class _Solver:
+        def __init__(self, M):
+            import scipy.linalg as L
+            self._lu = L.lu_factor(np.asarray(M, dtype=np.complex128))
+            self._solve = L.lu_solve
+
+        def lin_solve(self, b, tol=0):
+            return self._solve(self._lu, np.asarray(b, dtype=np.complex128))
+
+    def create_linsolver(self, nep, lam):
+        return self._Solver(nep.compute_Mder(lam))
+
+
+def ilan_symmetrizer_coefficients(m):
+    """symmetrizer_coefficients (method_ilan.jl:419-426)."""
+    G = np.zeros((m + 1, m + 1))
+    G[:, 0] = 1.0 / np.arange(1, m + 2)
+    for j in range(1, m + 1):
+        G[:, j] = G[:, j - 1] * j / (np.arange(1, m + 2) + j)
+    return G
+
+
+def ilan_inner_solve(pnep, neigs, tol=1e-13, maxit=80):
+    """inner_solve(::IARInnerSolver, ...) on the projected problem (inner_solver.jl:308-346; the default for a projected SPMF,
+    :249-250): iar from ones at sigma = 0; a NoConvergenceException still hands back what converged."""
+    n = pnep.n
+    try:
+        resid = lambda l, w: float(np.linalg.norm(pnep.compute_Mlincomb(l, w)) / np.linalg.norm(w))  # ResidualErrmeasure(pnep)
+        lam, V, _ = iar(pnep, sigma=0.0, neigs=neigs, tol=tol, maxit=maxit, v=np.ones(n), linsolvercreator=_DenseLinSolverCreator(),
+                        errmeasure=resid)
+        return lam, V
+    except NoConvergenceException as e:
+        return np.asarray(e.lam), np.asarray(e.v)
+
+
+def ilan(nep: B200SPMF, maxit=30, linsolvercreator=None, tol=np.finfo(float).eps * 10000, neigs=6, errmeasure=None, sigma=0.0, gamma=1.0,
+         v=None, check_error_every=30, proj_solve=True, inner_tol=1e-13, inner_maxit=80, orthmethod=dgks_host):
+    """ilan with the SPMF B-multiplication (compute_Bmul_method_SPMF_NEP, method_ilan.jl:330-352,379-388) on the device operator.
+
+    Per iteration the device does: compute_Mlincomb (GENERAL, q = 1), the shifted solve, and `Bmult!` -- the reference's loop of
+    p dense products Qn (G .* FDH_t) followed by p sparse products (:383-387) is ONE fused multi-term product
+    Z = sum_t A_t (Qn C_t) with C_t = (G .* FDH_t)[1:k+1, 1:k+1].  The three-term recurrence (bilinear forms without conjugation,
+    `mat_sum`, :279-288), the DGKS step on the first blocks and the extraction (projected problem through B200ProjSPMF -- all
+    A_t V in one fused pass -- solved with iar, or Ritz pairs of H) follow the reference on the host."""
+    n, m = nep.n, maxit
+    sigma, gamma = complex(sigma), complex(gamma)
+    errmeasure = errmeasure or DefaultErrmeasure(nep)
+    V = np.zeros((n, m + 1), dtype=np.complex128, order="F")
+    Q = np.zeros((n, m + 1), dtype=np.complex128, order="F")
+    Qp = np.zeros((n, m + 1), dtype=np.complex128, order="F")
+    Qn = np.zeros((n, m + 1), dtype=np.complex128, order="F")
+    H = np.zeros((m + 1, m), dtype=np.complex128)
+    HH = np.zeros((m + 1, m), dtype=np.complex128)
+    om = np.zeros(m + 1, dtype=np.complex128)
+    a = gamma ** np.arange(2 * m + 3)
+    a[0] = 0
+    M0inv = (linsolvercreator or B200LinSolverCreator()).create_linsolver(nep, sigma)
+    err = np.full((m, m), np.nan)
+    W = np.zeros((n, m + 1), dtype=np.complex128)
+    QQ = np.zeros((n, m + 1), dtype=np.complex128)
+    # FDH_t[i, j] = fD[i + j, t] (1-based) = gamma^r f_t^(r)(sigma), r = i + j - 1: the first column of f_t(SS) for the bidiagonal SS
+    G = ilan_symmetrizer_coefficients(m)
+    r = np.arange(m + 1)[:, None] + np.arange(m + 1)[None, :] + 1
+    fD = np.array([[gamma ** j * complex(f.derivative(sigma, j)) for j in range(2 * m + 2)] for f in nep.fi])  # p x (2m+2)
+    GF = [G * fD[t][r] for t in range(nep.p)]
+    v = np.random.default_rng(0).standard_normal(n) if v is None else np.asarray(v, dtype=np.complex128)
+    Q[:, 0] = v / np.linalg.norm(v)
+    om[0] = np.vdot(Q[:, 0], nep.compute_Mlincomb(0.0, np.stack([Q[:, 0], Q[:, 0]], axis=1), np.array([0.0, 1.0])))  # (:122: at 0)
+    V[:, 0] = Q[:, 0]
+    k, conv_eig = 1, 0
+    lam = np.zeros(0, dtype=np.complex128)
+    while k <= m and conv_eig < neigs:
+        if not proj_solve:
+            QQ[:, k - 1] = Q[:, 0]
+        Qn[:, 1:k + 1] = Q[:, :k] / np.arange(1, k + 1)[None, :]
+        Qn[:, 0] = nep.compute_Mlincomb(sigma, Qn[:, :k + 1], a[:k + 1])
+        Qn[:, 0] = -M0inv.lin_solve(Qn[:, 0].copy())
+        Cblk = np.stack([np.asfortranarray(GF[t][:k + 1, :k + 1]).reshape(-1, order="F") for t in range(nep.p)])
+        Z = nep.apply(_lib.COEF_GENERAL, Qn[:, :k + 1], Cblk, k + 1)  # Bmult!
+        beta = np.sum(Z[:, :k] * Qp[:, :k]) if k > 1 else 0.0
+        alpha = np.sum(Z[:, :k] * Q[:, :k])
+        eta = np.sum(Z[:, :k + 1] * Qn[:, :k + 1])
+        H[k - 1, k - 1] = alpha / om[k - 1]
+        if k > 1:
+            H[k - 2, k - 1] = beta / om[k - 2]
+        Qn[:, :k] -= H[k - 1, k - 1] * Q[:, :k]
+        if k > 1:
+            Qn[:, :k] -= H[k - 2, k - 1] * Qp[:, :k]
+        H[k, k - 1] = np.linalg.norm(Qn)
+        Qn[:, :k + 1] /= H[k, k - 1]
+        om[k] = eta - 2 * alpha * H[k - 1, k - 1] + om[k - 1] * H[k - 1, k - 1] ** 2
+        if k > 1:
+            om[k] = om[k] - 2 * beta * H[k - 2, k - 1] + om[k - 2] * H[k - 2, k - 1] ** 2
+        om[k] = om[k] / H[k, k - 1] ** 2
+        V[:, k] = Qn[:, 0]
+        HH[k, k - 1] = orthmethod(V[:, :k], V[:, k], HH[:k, k - 1])
+        if k % check_error_every == 0 or k == m:
+            if not proj_solve:
+                D, Wr = np.linalg.eig(H[:k, :k])
+                W[:, :k] = QQ[:, :k] @ Wr
+                lam = sigma + gamma / D
+            else:
+                from .neptypes import create_proj_NEP
+                VV = V[:, :k + 1]
+                pnep = create_proj_NEP(nep, k + 1).set_projectmatrices(VV, VV)
+                pnep.n = k + 1
+                lproj, Wproj = ilan_inner_solve(pnep, m, inner_tol, inner_maxit)
+                lam = np.asarray(lproj, dtype=np.complex128)
+                q = min(len(lam), m)
+                W[:, :q] = VV @ np.asarray(Wproj)[:, :q]
+            nl = len(lam)
+            err[k - 1, :nl] = _errs(errmeasure, lam, W[:, :nl]) if nl else []
+            conv_eig = int(np.count_nonzero(err[k - 1, :nl] < tol))
+            idx = np.argsort(err[k - 1, :k], kind="stable")
+            err[k - 1, :k] = err[k - 1, idx]
+            if k == m or conv_eig >= neigs:
+                nrof = int(min(conv_eig, neigs))
+                lam = lam[idx[:nrof]]
+                W = W[:, idx[:len(lam)]]
+        k += 1
+        Qp[:] = Q
+        Q[:] = Qn
+        Qn[:] = 0
+    k -= 1
+    if conv_eig < neigs and neigs != np.inf:
+        raise NoConvergenceException(lam, Q, err[k - 1, :k], "Number of iterations exceeded. maxit=%d." % maxit)
+    return lam, W, err, V[:, :k + 1], H[:k, :k - 1], om[:k], HH[:k, :k]

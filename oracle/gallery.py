@@ -173,3 +173,19 @@ def stencil_block(rng: MSWS_RNG, n: int, k: int) -> np.ndarray:
             im = 1 - 2 * gen_rng_float(rng)
             V[r, c] = complex(re, im)
     return V
+
+
+def dep_symm_double_matrices(n=100):
+    """nep_gallery("dep_symm_double", n) (src/gallery_extra/gallery_examples.jl:13-30): symmetric DEP of size n^2 with double
+    eigenvalues, A = kron(L, L) + diag(8 sin x sin y), B = diag(-100 |sin(x + y)|), delays (0, 2)."""
+    import scipy.sparse as sp
+    LL = -sp.diags(2 * np.ones(n)) + sp.diags(np.ones(n - 1), -1) + sp.diags(np.ones(n - 1), 1)
+    x = np.linspace(0, np.pi, n)
+    h = x[1] - x[0]
+    LL = LL / h ** 2
+    LL = sp.kron(LL, LL)
+    b = -100 * np.abs(np.sin(x[:, None] + x[None, :]))
+    a = 8 * np.sin(x[:, None]) * np.sin(x[None, :])
+    B = sp.diags(b.reshape(-1, order="F"))
+    A = LL + sp.diags(a.reshape(-1, order="F"))
+    return sp.csc_matrix(A), sp.csc_matrix(B), [0.0, 2.0]

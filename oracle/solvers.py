@@ -646,3 +646,130 @@ def infbilanczos(nep, nept, maxit=30, linsolvercreator=None, linsolvertcreator=N
                 if conv_eig >= neigs or neigs == np.inf:
                     return lam, Q, TT
     raise NoConvergenceException(lam, Q, err, "Number of iterations exceeded. maxit=%d." % maxit)
+
+
+# --------------------------------------------------------------------------------------------
+# ilan (src/method_ilan.jl): infinite Lanczos for symmetric NEPs, SPMF B-multiplication
+# --------------------------------------------------------------------------------------------
+def symmetrizer_coefficients(m):
+    """method_ilan.jl:419-426."""
+    G = np.zeros((m + 1, m + 1))
+    G[:, 0] = 1.0 / np.arange(1, m + 2)
+    for j in range(1, m + 1):
+        for i in range(1, m + 2):
+            G[i - 1, j] = G[i - 1, j - 1] * j / (i + j)
+    return G
+
+
+def ilan_precompute_spmf(nep, m, sigma, gamma):
+    """method_ilan.jl:330-352: FDH[t][i,j] = fD[i+j, t] with fD[:, t] = f_t(SS)[:, 1], SS = sigma I + subdiag(gamma (1:2m+1))."""
+    fv = o.get_fv(nep)
+    SS = np.diag(sigma * np.ones(2 * m + 2, dtype=np.complex128)) + np.diag(gamma * np.arange(1, 2 * m + 2, dtype=np.complex128), -1)
+    fD = np.stack([np.asarray(f(SS), dtype=np.complex128)[:, 0] for f in fv], axis=1)
+    idx = np.arange(1, m + 2)[:, None] + np.arange(1, m + 2)[None, :]  # 1-based i + j, used as the 1-based row index of fD
+    FDH = [fD[idx - 1, t] for t in range(len(fv))]
+    return FDH, symmetrizer_coefficients(m)
+
+
+def ilan_bmult_spmf(k, Qn, Av, FDH, G):
+    """Bmult! for SPMF (method_ilan.jl:379-388): Z = sum_t A_t (Qn[:, 1:k+1] (G .* FDH_t)[1:k+1, 1:k+1])."""
+    Z = np.zeros((Qn.shape[0], k + 1), dtype=np.complex128)
+    for t, A in enumerate(Av):
+        Z += o._dot(A, Qn[:, :k + 1] @ (G[:k + 1, :k + 1] * FDH[t][:k + 1, :k + 1]))
+    return Z
+
+
+def inner_solve_iar(pnep, neigs, tol=1e-13, maxit=80):
+    """inner_solve(::IARInnerSolver, ...) (inner_solver.jl:308-346): iar on the projected problem from ones, sigma = 0; whatever
+    converged is returned when the wanted number is not reached."""
+    n = pnep.n
+    try:
+        lam, V, _ = iar(pnep, sigma=0.0, neigs=neigs, tol=tol, maxit=maxit, v=np.ones(n), errmeasure=o.residual_errmeasure(pnep))
+        return lam, V
+    except NoConvergenceException as e:
+        return np.asarray(e.lam), np.asarray(e.v)
+
+
+def ilan(nep, maxit=30, linsolvercreator=None, tol=np.finfo(float).eps * 10000, neigs=6, errmeasure=None, sigma=0.0, gamma=1.0, v=None,
+         check_error_every=30, proj_solve=True, inner_tol=1e-13, inner_maxit=80, orth=orthogonalize_and_normalize_dgks):
+    """method_ilan.jl:56-261 with the SPMF B-multiplication (compute_Bmul_method_SPMF_NEP; a DEP is taken through its SPMF
+    form, which the reference's test "Different format" shows to be the same iteration)."""
+    n, m = nep.n, maxit
+    sigma, gamma = complex(sigma), complex(gamma)
+    errmeasure = errmeasure or default_errmeasure(nep)
+    V = np.zeros((n, m + 1), dtype=np.complex128)
+    Q = np.zeros((n, m + 1), dtype=np.complex128)
+    Qp = np.zeros((n, m + 1), dtype=np.complex128)
+    Qn = np.zeros((n, m + 1), dtype=np.complex128)
+    H = np.zeros((m + 1, m), dtype=np.complex128)
+    HH = np.zeros((m + 1, m), dtype=np.complex128)
+    om = np.zeros(m + 1, dtype=np.complex128)
+    a = gamma ** np.arange(2 * m + 3)
+    a[0] = 0
+    M0inv = (linsolvercreator or FactorizeLinSolverCreator()).create_linsolver(nep, sigma)
+    err = np.full((m, m), np.nan)
+    W = np.zeros((n, m + 1), dtype=np.complex128)
+    QQ = np.zeros((n, m + 1), dtype=np.complex128)
+    FDH, G = ilan_precompute_spmf(nep, m, sigma, gamma)
+    Av = o.get_Av(nep)
+    v = np.asarray(v, dtype=np.complex128)
+    Q[:, 0] = v / np.linalg.norm(v)
+    om[0] = np.vdot(Q[:, 0], o.compute_Mlincomb(nep, 0, np.stack([Q[:, 0], Q[:, 0]], axis=1), np.array([0, 1])))  # (:122; at 0, not sigma)
+    V[:, 0] = Q[:, 0]
+    k, conv_eig = 1, 0
+    lam = np.zeros(0, dtype=np.complex128)
+    while k <= m and conv_eig < neigs:
+        if not proj_solve:
+            QQ[:, k - 1] = Q[:, 0]
+        Qn[:, 1:k + 1] = Q[:, :k] / np.arange(1, k + 1)[None, :]
+        Qn[:, 0] = o.compute_Mlincomb(nep, sigma, Qn[:, :k + 1], a[:k + 1])
+        Qn[:, 0] = -M0inv.lin_solve(Qn[:, 0].copy())
+        Z = ilan_bmult_spmf(k, Qn, Av, FDH, G)
+        beta = np.sum(Z[:, :k] * Qp[:, :k]) if k > 1 else 0.0
+        alpha = np.sum(Z[:, :k] * Q[:, :k])
+        eta = np.sum(Z[:, :k + 1] * Qn[:, :k + 1])
+        H[k - 1, k - 1] = alpha / om[k - 1]
+        if k > 1:
+            H[k - 2, k - 1] = beta / om[k - 2]
+        Qn[:, :k] -= H[k - 1, k - 1] * Q[:, :k]
+        if k > 1:
+            Qn[:, :k] -= H[k - 2, k - 1] * Qp[:, :k]
+        H[k, k - 1] = np.linalg.norm(Qn)
+        Qn[:, :k + 1] /= H[k, k - 1]
+        om[k] = eta - 2 * alpha * H[k - 1, k - 1] + om[k - 1] * H[k - 1, k - 1] ** 2
+        if k > 1:
+            om[k] = om[k] - 2 * beta * H[k - 2, k - 1] + om[k - 2] * H[k - 2, k - 1] ** 2
+        om[k] = om[k] / H[k, k - 1] ** 2
+        V[:, k] = Qn[:, 0]
+        HH[k, k - 1] = orth(V[:, :k], V[:, k], HH[:k, k - 1])
+        if k % check_error_every == 0 or k == m:
+            if not proj_solve:
+                D, Wr = np.linalg.eig(H[:k, :k])
+                W[:, :k] = QQ[:, :k] @ Wr
+                lam = sigma + gamma / D
+            else:
+                VV = V[:, :k + 1]
+                pnep = o.create_proj_NEP(nep, k + 1)
+                pnep.set_projectmatrices(VV, VV)
+                lproj, Wproj = inner_solve_iar(pnep.nep_proj, m, inner_tol, inner_maxit)
+                q = len(lproj)
+                lam = np.asarray(lproj, dtype=np.complex128)
+                q = min(q, m)
+                W[:, :q] = VV @ np.asarray(Wproj)[:, :q]
+            nl = len(lam)
+            err[k - 1, :nl] = [errmeasure(lam[s], W[:, s]) for s in range(nl)]
+            conv_eig = int(np.count_nonzero(err[k - 1, :nl] < tol))
+            idx = np.argsort(err[k - 1, :k], kind="stable")  # NaNs (unused slots) sort last, as in Julia
+            err[k - 1, :k] = err[k - 1, idx]
+            if k == m or conv_eig >= neigs:
+                nrof = int(min(conv_eig, neigs))
+                lam = lam[idx[:nrof]]
+                W = W[:, idx[:len(lam)]]
+        k += 1
+        Qp[:] = Q
+        Q[:] = Qn
+        Qn[:] = 0
+    k -= 1
+    if conv_eig < neigs and neigs != np.inf:
+        raise NoConvergenceException(lam, Q, err[k - 1, :k], "Number of iterations exceeded. maxit=%d." % maxit)
+    return lam, W, err, V[:, :k + 1], H[:k, :k - 1], om[:k], HH[:k, :k]

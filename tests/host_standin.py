@@ -5,7 +5,7 @@ import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as sla
 
-from nepb200 import _lib
+from nepb200 import _lib, B200SPMF
 
 
 class HostOperator:
@@ -13,6 +13,10 @@ class HostOperator:
 
     def __init__(self, A, fi):
         self.A, self.fi, self.p, self.n = A, fi, len(A), A[0].shape[0]
+
+    # host-side coefficient logic of the real operator (needs only fi / p / n / apply)
+    lincomb_coefficients = B200SPMF.lincomb_coefficients
+    compute_Mlincomb = B200SPMF.compute_Mlincomb
 
     def get_fv(self):
         return self.fi

@@ -222,3 +222,29 @@ def test_symbolic_from_handle_matches_host_analysis():
     assert np.array_equal(perm, perm2) and np.array_equal(parent, parent2)
     assert sn_ptr[0] == 0 and sn_ptr[-1] == dnep.n and np.all(np.diff(sn_ptr) > 0)
     assert np.all((sn_parent == -1) | (sn_parent > np.arange(len(sn_parent))))
+
+
+def test_gmres_linsolver_on_the_device_operator():
+    """GMRESLinSolver (LinSolvers.jl:171-188, creator LinSolverCreators.jl:124-145) on the SPMF of test/newlinsolve.jl:5-12
+    (tridiagonal A, B = I, C = diag((1:n)/n), f = 1, s, exp(s); lambda0 = -1.02; preconditioner Pl = Diagonal(M(lambda0)),
+    tol = 1e-6): every matrix-vector product is a device SpMM through compute_Mlincomb; the result must agree with the
+    device LU to the GMRES tolerance, vector right-hand sides only."""
+    n, al, lam0 = 100, 0.01, -1.02
+    A = sp.diags([np.ones(n), al * np.ones(n - 1), al * np.ones(n - 1)], [0, 1, -1], format="csc")
+    B = sp.identity(n, format="csc")
+    Cm = sp.diags(np.arange(1, n + 1) / n, format="csc")
+    dnep = B200SPMF([A, B, Cm], [ONE, IDENTITY, Exp(1.0)])
+    D0 = sp.diags(dnep.compute_Mder(lam0).diagonal())
+    creator = nepb200.GMRESLinSolverCreator(Pl=D0, tol=1e-6, log=True)
+    solver = creator.create_linsolver(dnep, lam0)
+    assert isinstance(solver, nepb200.GMRESLinSolver)
+    b = np.ones(n, dtype=complex)
+    x = solver.lin_solve(b)
+    xd = nepb200.B200FactorizeLinSolver(dnep, lam0).lin_solve(b)
+    Mo = (A + lam0 * B + np.exp(lam0) * Cm).tocsc()
+    assert np.linalg.norm(D0.power(-1) @ (Mo @ x - b)) <= 1e-6 * np.linalg.norm(D0.power(-1) @ b) * 1.001
+    assert np.linalg.norm(x - xd) / np.linalg.norm(xd) < 1e-4
+    tight = nepb200.GMRESLinSolverCreator(Pl=D0).create_linsolver(dnep, lam0).lin_solve(b, tol=1e-12)
+    assert np.linalg.norm(tight - xd) / np.linalg.norm(xd) < 1e-9
+    with pytest.raises(TypeError):
+        solver.lin_solve(np.ones((n, 2)))

@@ -158,3 +158,40 @@ def test_contour_block_SS_dep0():
         assert mp == mpo
         assert np.linalg.norm(o.compute_Mlincomb(onep, lam[0], Vec[:, 0])) < np.sqrt(np.finfo(float).eps)
         assert max(min(abs(lam - x)) for x in lo) < 1e-8 * max(1.0, np.max(abs(lo)))
+
+
+def test_ilan_device_matches_oracle():
+    """ilan (src/method_ilan.jl) with the device operator: compute_Mlincomb, the shifted solve and
+    `Bmult!` (one fused multi-term product with the k+1 x k+1 blocks G .* FDH_t) run on the B200, the recurrences on the host.
+    The docstring example (dep_symm_double(10): 3 eigenpairs, first eigenvalue 0.03409997385842267, residual < 1e-5 as in
+    test/ilan.jl:25-30) and the early Lanczos factorisation against the oracle; Ritz extraction from H as well."""
+    import scipy.sparse as sp
+    from nepb200 import B200SPMF, Monomial, ONE, Exp
+    A, B, tau = g.dep_symm_double_matrices(10)
+    n = A.shape[0]
+    onep = o.DEP([A, B], tau)
+    dnep = B200SPMF([-sp.identity(n, format="csc"), A, B], [Monomial(1), ONE, Exp(-tau[1])])
+    lam, W, *_ = nepb200.ilan(dnep, v=np.ones(n), tol=1e-5, neigs=3)
+    assert len(lam) == 3
+    assert np.min(np.abs(lam - 0.03409997385842267)) < 1e-9
+    for l, w in zip(lam, W.T):
+        assert np.linalg.norm(o.compute_Mlincomb(onep, l, w)) / np.linalg.norm(w) < 1e-5
+    A, B, tau = g.dep_symm_double_matrices(8)
+    n = A.shape[0]
+    onep = o.DEP([A, B], tau)
+    dnep = B200SPMF([-sp.identity(n, format="csc"), A, B], [Monomial(1), ONE, Exp(-tau[1])])
+    for proj_solve in (True, False):
+        kw = dict(sigma=0.0, gamma=1.0, neigs=3, maxit=20, tol=1e-6, check_error_every=20, v=np.ones(n), proj_solve=proj_solve)
+        lo, Wo, _, Vo, Ho, omo, HHo = osol.ilan(onep, errmeasure=o.residual_errmeasure(onep), **kw)
+        lam, W, _, V, H, om, HH = nepb200.ilan(dnep, errmeasure=nepb200.ResidualErrmeasure(dnep), **kw)
+        kk = 6  # the recurrence is not re-orthogonalised: rounding differences grow tenfold per step (tests/test_ilan.py)
+        assert np.linalg.norm(V[:, :kk] - Vo[:, :kk]) < 1e-8
+        assert np.linalg.norm(H[:kk, :kk] - Ho[:kk, :kk]) < 1e-8 * np.linalg.norm(Ho[:kk, :kk])
+        assert np.linalg.norm(om[:kk] - omo[:kk]) < 1e-8 * np.linalg.norm(omo[:kk])
+        assert len(lam) == len(lo) == 3
+        for x in lam:
+            assert np.min(np.abs(lo - x)) < 1e-7
+        for l, w in zip(lam, W.T):
+            assert np.linalg.norm(o.compute_Mlincomb(onep, l, w)) / np.linalg.norm(w) < 1e-6
+    with pytest.raises(nepb200.NoConvergenceException):
+        nepb200.ilan(dnep, neigs=2, maxit=3, tol=np.finfo(float).eps * 100, check_error_every=np.inf, v=np.ones(n))
