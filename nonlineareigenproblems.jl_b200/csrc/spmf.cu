@@ -442,81 +442,136 @@ __global__ void __launch_bounds__(256) spmm_tma_kernel(int kt, int ldv, int ldz,
         start = sRp[r];
         end = sRp[r + 1];
     }
-    double2 acc[CPT];
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) acc[j] = make_double2(0.0, 0.0);
     // Row products straight from the raw term values (two 16-byte broadcast reads per nonzero for p = 4 real terms; no separate
-    // combine pass: its strided shared-memory reads cost a full wavefront per nonzero, profiles/r2_ncu_spmm_tma_v1.txt).
-    // UN nonzeros per trip with all loads issued before the arithmetic.
-    constexpr int UN = CPT >= 3 ? 2 : 4;
-    for (int base = start; base < end; base += UN) {
-        int li[UN];
-        double v[UN][VW];
-        double2 x[UN][CPT];
+    // combine pass: its strided shared-memory reads cost a full wavefront per nonzero, profiles/r2_ncu_spmm_tma.txt).
+    // Full trips of UN nonzeros run without predicates (every load first, then the arithmetic, two accumulator sets so that
+    // consecutive nonzeros do not form one dependent DFMA chain); the row's remainder is handled one nonzero at a time.
+    // Lanes whose column lies beyond kt read whatever follows in shared memory and never store it.
+    double2 acc[2][CPT];
 #pragma unroll
-        for (int u = 0; u < UN; ++u) li[u] = (base + u < end) ? (int)sL[base + u] : -1;
+    for (int j = 0; j < CPT; ++j) acc[0][j] = acc[1][j] = make_double2(0.0, 0.0);
+    auto load_vals_s = [&](int idx, double (&v)[VW]) {
+        const double* vp = sA + (size_t)idx * VW;
+        if constexpr (VW % 2 == 0) {
 #pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            if (li[u] >= 0) {
-                const double* vp = sA + (size_t)(base + u) * VW;
-                if constexpr (VW % 2 == 0) {
+            for (int t = 0; t < VW; t += 2) {
+                double2 w;
+                if (a_skip == 0) w = *(const double2*)(vp + t);  // uniform branch: 16-byte aligned slice
+                else w = make_double2(vp[t], vp[t + 1]);
+                v[t] = w.x;
+                v[t + 1] = w.y;
+            }
+        } else {
 #pragma unroll
-                    for (int t = 0; t < VW; t += 2) {
-                        double2 w;
-                        if (a_skip == 0) w = *(const double2*)(vp + t);  // uniform branch: 16-byte aligned slice
-                        else w = make_double2(vp[t], vp[t + 1]);
-                        v[u][t] = w.x;
-                        v[u][t + 1] = w.y;
-                    }
-                } else {
+            for (int t = 0; t < VW; ++t) v[t] = vp[t];
+        }
+    };
+    auto load_x = [&](int li, double2 (&x)[CPT], int ncp) {
+        const double2* xr = sV + li * kt + gc;
+        if constexpr (GC == 8) {
 #pragma unroll
-                    for (int t = 0; t < VW; ++t) v[u][t] = vp[t];
-                }
-                const double2* xr = sV + li[u] * kt + gc;
-                if constexpr (GC == 8) {
+            for (int j = 0; j < CPT; ++j)
+                if (j < ncp) x[j] = xr[j * GC];
+        } else {
+            // GC = 4: a quarter-warp (one LDS.128 wavefront) serves two rows, 64 bytes each; the two pieces must fall into
+            // different halves of the 32 banks.  The half of piece j is (li*kt/4 + j) mod 2: neighbouring pieces are
+            // read in swapped order when (row parity + li*kt/4) is odd, and swapped back in registers.
+            const int sw = (r + ((li * kt) >> 2)) & 1;
 #pragma unroll
-                    for (int j = 0; j < CPT; ++j) x[u][j] = (gc + j * GC < kt) ? xr[j * GC] : make_double2(0.0, 0.0);
-                } else {
-                    // GC = 4: a quarter-warp (one LDS.128 wavefront) serves two rows, 64 bytes each; the two pieces must fall into
-                    // different halves of the 32 banks.  The half of piece j is (li*kt/4 + j) mod 2: neighbouring pieces are
-                    // read in swapped order when (row parity + li*kt/4) is odd, and swapped back in registers.
-                    const int s = (r + ((li[u] * kt) >> 2)) & 1;
+            for (int j = 0; j < CPT; ++j) {
+                const int jj = ((j | 1) < CPT) ? (j ^ sw) : j;  // pairs (0,1), (2,3), ..; an odd last piece stays
+                x[j] = (gc + jj * GC < kt) ? xr[jj * GC] : make_double2(0.0, 0.0);
+            }
 #pragma unroll
-                    for (int j = 0; j < CPT; ++j) {
-                        const int jj = ((j | 1) < CPT) ? (j ^ s) : j;  // pairs (0,1), (2,3), ..; an odd last piece stays
-                        x[u][j] = (gc + jj * GC < kt) ? xr[jj * GC] : make_double2(0.0, 0.0);
-                    }
+            for (int j = 0; j + 1 < CPT; j += 2) {
+                const double2 xa = x[j], xb = x[j + 1];
+                x[j] = sw ? xb : xa;
+                x[j + 1] = sw ? xa : xb;
+            }
+        }
+    };
+    auto fma_one = [&](const double (&v)[VW], const double2 (&x)[CPT], double2 (&ac)[CPT], int ncp) {
+        if constexpr (!DIAG) {
+            const double2 m = combine<VW, CA>(v, [&](int i) { return cp.c[i]; });
 #pragma unroll
-                    for (int j = 0; j + 1 < CPT; j += 2) {
-                        const double2 a = x[u][j], b = x[u][j + 1];
-                        x[u][j] = s ? b : a;
-                        x[u][j + 1] = s ? a : b;
-                    }
+            for (int j = 0; j < CPT; ++j)
+                if (j < ncp) cfma(ac[j], m, x[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                if (j < ncp) {
+                    const double2 m = combine<VW, CA>(v, [&](int i) { return cd[j][i]; });
+                    cfma(ac[j], m, x[j]);
                 }
             }
         }
+    };
+    // PAIR (17..20 columns, 8 lanes per row): the third 128-byte piece of a V row holds only columns 16..19, i.e. lanes 0-3.
+    // Two consecutive nonzeros share ONE third load: lanes 0-3 take columns 16..19 of the first, lanes 4-7 those of the second
+    // (separate accumulator, folded into lanes 0-3 at the end): 2.5 instead of 3 wavefronts per nonzero for the V rows.
+    const bool pair = GC == 8 && CPT == 3 && !DIAG && kt <= 20;
+    double2 acc3 = make_double2(0.0, 0.0);
+    constexpr int UN = CPT >= 3 ? 2 : 4;
+    int base = start;
+    if (pair) {
+        for (; base + 2 <= end; base += 2) {
+            const int la = (int)sL[base], lb = (int)sL[base + 1];
+            double va[VW], vb[VW];
+            double2 xa[CPT], xb[CPT];
+            load_vals_s(base, va);
+            load_vals_s(base + 1, vb);
+            load_x(la, xa, 2);
+            load_x(lb, xb, 2);
+            const double2 x3 = sV[((gc < 4) ? la : lb) * kt + 16 + (gc & 3)];
+            const double2 ma = combine<VW, CA>(va, [&](int i) { return cp.c[i]; });
+            const double2 mb = combine<VW, CA>(vb, [&](int i) { return cp.c[i]; });
 #pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            if (li[u] >= 0) {
-                if constexpr (!DIAG) {
-                    const double2 m = combine<VW, CA>(v[u], [&](int i) { return cp.c[i]; });
-#pragma unroll
-                    for (int j = 0; j < CPT; ++j) cfma(acc[j], m, x[u][j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < CPT; ++j) {
-                        const double2 m = combine<VW, CA>(v[u], [&](int i) { return cd[j][i]; });
-                        cfma(acc[j], m, x[u][j]);
-                    }
-                }
+            for (int j = 0; j < 2; ++j) {
+                cfma(acc[0][j], ma, xa[j]);
+                cfma(acc[1][j], mb, xb[j]);
             }
+            cfma(acc3, (gc < 4) ? ma : mb, x3);
+        }
+    } else {
+        for (; base + UN <= end; base += UN) {
+            int li[UN];
+            double v[UN][VW];
+            double2 x[UN][CPT];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) li[u] = (int)sL[base + u];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                load_vals_s(base + u, v[u]);
+                load_x(li[u], x[u], CPT);
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) fma_one(v[u], x[u], acc[u & 1], CPT);
+        }
+    }
+    for (; base < end; ++base) {
+        double v[VW];
+        double2 x[CPT];
+        load_vals_s(base, v);
+        load_x((int)sL[base], x, CPT);
+        fma_one(v, x, acc[0], CPT);
+    }
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        acc[0][j].x += acc[1][j].x;
+        acc[0][j].y += acc[1][j].y;
+    }
+    if (pair) {  // lanes 4-7 hand their share of columns 16..19 to lanes 0-3 of the same row
+        const double tx = __shfl_down_sync(0xffffffffu, acc3.x, 4), ty = __shfl_down_sync(0xffffffffu, acc3.y, 4);
+        if (gc < 4) {
+            acc[0][2].x += acc3.x + tx;
+            acc[0][2].y += acc3.y + ty;
         }
     }
     if (r < nrows) {
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
             const int c = gc + j * GC;
-            if (c < kt) Z[(size_t)(row0 + r) * ldz + c] = acc[j];
+            if (c < kt) Z[(size_t)(row0 + r) * ldz + c] = acc[0][j];
         }
     }
 }
