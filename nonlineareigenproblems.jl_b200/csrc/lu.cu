@@ -893,6 +893,181 @@ __global__ void __launch_bounds__(256) lu_backward_chain_kernel(LuDev d, const i
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Chains of in-place fronts (the links of a supernode split at 32 pivot columns; the 886-row dense root of gun is 28 of them)
+// solved by ONE thread-block cluster per (chain, shift) instead of one launch per link and direction.
+// All links of a chain live in one dense column-major array, so the chain is a dense blocked triangular solve.  Link q is
+// owned by CTA q mod C of the cluster; the algorithm is right-looking: as soon as the owner has finished the pivot rows of a
+// link (one product with the stored inverse of the pivot block) it publishes them in HBM/L2, the cluster synchronises once
+// (barrier.cluster, release/acquire), and every CTA applies that link's block column (backward: U, forward: L) to the rows
+// of the links it owns -- no reductions across CTAs, one hardware barrier per link, ~5 us per link instead of the
+// ~75 us of per-level launches (profiles/r2_contour_latency_steps.txt).  Rows that belong to ancestors above the chain
+// (a chain that does not end at the root) are handled in 32-row blocks dealt round-robin to the CTAs.
+// Data written by other CTAs of the cluster is read with ld.global.cg (L2), never through the non-coherent path.
+// ---------------------------------------------------------------------------------------------
+constexpr int CHAIN_C = 8;  // CTAs per cluster (portable maximum)
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+// Y[r, :] -= sum_t A(r, t) X[t, :] for r < R <= 32, t < T <= 32.  A(r, t) = A0[r*sr + t*st] (factor entries, read-only);
+// X rows: Xg[xrow(t)*k ..] with xrow(t) = xrows ? xrows[t] : x0 + t; Y rows: Yg[(y0 + r)*k ..].  sA, sX: shared staging.
+__device__ __forceinline__ void chain_block_update(double2* Yg, int y0, const double2* __restrict__ A0, size_t sr, size_t st, int R, int T,
+                                                   const double2* Xg, int x0, const int* __restrict__ xrows, int k, double2* sA, double2* sX) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    __syncthreads();
+    if (sr == 1) {  // rows contiguous in memory
+        for (int idx = tid; idx < R * T; idx += nth) {
+            const int r = idx % R, t = idx / R;
+            sA[t * 33 + r] = A0[(size_t)r + (size_t)t * st];
+        }
+    } else {        // columns (t) contiguous in memory
+        for (int idx = tid; idx < R * T; idx += nth) {
+            const int t = idx % T, r = idx / T;
+            sA[t * 33 + r] = A0[(size_t)r * sr + (size_t)t * st];
+        }
+    }
+    for (int idx = tid; idx < T * k; idx += nth) {
+        const int t = idx / k, c = idx % k;
+        const int xr = xrows ? xrows[t] : x0 + t;
+        sX[idx] = __ldcg(Xg + (size_t)xr * k + c);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < R * k; idx += nth) {
+        const int r = idx / k, c = idx % k;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int t = 0; t < T; ++t) cfma2(acc, sA[t * 33 + r], sX[t * k + c]);
+        double2* y = Yg + (size_t)(y0 + r) * k + c;
+        double2 o = __ldcg(y);
+        o.x -= acc.x;
+        o.y -= acc.y;
+        *y = o;
+    }
+}
+
+// backward: items[blockIdx.x / C] = (first index into chain_fronts, links); links are stored bottom-up
+__global__ void __launch_bounds__(256) lu_backward_chain_cluster_kernel(LuDev d, const int2* __restrict__ items, const int* __restrict__ chain_fronts,
+                                                                        const double2* __restrict__ fronts, double2* Xp, int k) {
+    extern __shared__ double2 csm[];
+    double2* sA = csm;                 // 32 x 33
+    double2* sX = sA + 32 * 33;        // 32 x k
+    double2* sY = sX + 32 * k;         // 32 x k
+    const int2 it = items[blockIdx.x / CHAIN_C];
+    const int rank = (int)cluster_cta_rank();
+    const int b = blockIdx.y, m = it.y, tid = threadIdx.x, nth = blockDim.x;
+    const int* cf = chain_fronts + it.x;
+    double2* Xb = Xp + (size_t)b * d.n * k;
+    const double2* Fb = fronts + (size_t)b * d.front_total;
+    // rows of ancestors above the chain: their solution is final; every owner removes them from its links first
+    const int top = cf[m - 1];
+    const int nE = d.nf[top] - d.np[top];
+    if (nE > 0) {
+        for (int i = rank; i < m; i += CHAIN_C) {
+            const int s = cf[i];
+            const int np = d.np[s], ncb = d.nf[s] - np, ld = d.ld[s];
+            const double2* F = Fb + d.front_off[s];
+            const int* rows = d.rows + d.row_ptr[s] + np;
+            for (int x = ncb - nE; x < ncb; x += 32)
+                chain_block_update(Xb, d.sn_ptr[s], F + (size_t)(np + x) * ld, 1, ld, np, min(32, ncb - x), Xb, 0, rows + x, k, sA, sX);
+        }
+    }
+    for (int j = m - 1; j >= 0; --j) {
+        const int sj = cf[j];
+        const int npj = d.np[sj], c0j = d.sn_ptr[sj];
+        if (j % CHAIN_C == rank) {  // x_j = inv(U11) y_j
+            const int ld = d.ld[sj];
+            const double2* F = Fb + d.front_off[sj];
+            __syncthreads();
+            for (int idx = tid; idx < npj * npj; idx += nth) {
+                const int i = idx % npj, t = idx / npj;
+                sA[t * 33 + i] = (t >= i) ? F[(size_t)i + (size_t)t * ld] : make_double2(0.0, 0.0);
+            }
+            for (int idx = tid; idx < npj * k; idx += nth) sY[idx] = __ldcg(Xb + (size_t)c0j * k + idx);
+            __syncthreads();
+            for (int idx = tid; idx < npj * k; idx += nth) {
+                const int i = idx / k, c = idx % k;
+                double2 acc = make_double2(0.0, 0.0);
+                for (int t = i; t < npj; ++t) cfma2(acc, sA[t * 33 + i], sY[t * k + c]);
+                Xb[(size_t)c0j * k + idx] = acc;
+            }
+        }
+        cluster_sync_all();
+        for (int i = rank; i < j; i += CHAIN_C) {  // block column j of U applied to the owned links below it
+            const int s = cf[i];
+            const int np = d.np[s], ld = d.ld[s], c0 = d.sn_ptr[s];
+            const double2* F = Fb + d.front_off[s];
+            const int xoff = c0j - (c0 + np);  // link j's pivot columns inside link i's update columns
+            chain_block_update(Xb, c0, F + (size_t)(np + xoff) * ld, 1, ld, np, npj, Xb, c0j, nullptr, k, sA, sX);
+        }
+    }
+}
+
+// forward: pivot rows of a link = right-hand side + what the links below left in its work rows; update rows live in W
+__global__ void __launch_bounds__(256) lu_forward_chain_cluster_kernel(LuDev d, const int2* __restrict__ items, const int* __restrict__ chain_fronts,
+                                                                       const double2* __restrict__ fronts, const int* __restrict__ piv, double2* Xp,
+                                                                       double2* W, int k) {
+    extern __shared__ double2 csm[];
+    double2* sA = csm;
+    double2* sX = sA + 32 * 33;
+    double2* sY = sX + 32 * k;
+    const int2 it = items[blockIdx.x / CHAIN_C];
+    const int rank = (int)cluster_cta_rank();
+    const int b = blockIdx.y, m = it.y, tid = threadIdx.x, nth = blockDim.x;
+    const int* cf = chain_fronts + it.x;
+    double2* Xb = Xp + (size_t)b * d.n * k;
+    double2* Wb = W + (size_t)b * d.w_total * k;
+    const double2* Fb = fronts + (size_t)b * d.front_total;
+    const int top = cf[m - 1];
+    const int nE = d.nf[top] - d.np[top];
+    for (int q = 0; q < m; ++q) {
+        const int s = cf[q];
+        const int np = d.np[s], ncb = d.nf[s] - np, ld = d.ld[s], c0 = d.sn_ptr[s];
+        const double2* F = Fb + d.front_off[s];
+        if (q % CHAIN_C == rank) {  // y1 = inv(L11) P (b1 + work rows)
+            const int* pv = piv + (size_t)b * d.n + c0;
+            const double2* Ws = Wb + (size_t)d.w_off[s] * k;
+            __syncthreads();
+            for (int idx = tid; idx < np * k; idx += nth) {
+                const double2 a = __ldcg(Xb + (size_t)c0 * k + idx), w = __ldcg(Ws + idx);
+                sY[idx] = make_double2(a.x + w.x, a.y + w.y);
+            }
+            for (int idx = tid; idx < np * np; idx += nth) {
+                const int i = idx % np, t = idx / np;
+                sA[t * 33 + i] = (t < i) ? F[(size_t)i + (size_t)t * ld] : make_double2(i == t ? 1.0 : 0.0, 0.0);
+            }
+            __syncthreads();
+            for (int idx = tid; idx < np * k; idx += nth) sX[idx] = sY[pv[idx / k] * k + idx % k];
+            __syncthreads();
+            for (int idx = tid; idx < np * k; idx += nth) {
+                const int i = idx / k, c = idx % k;
+                double2 acc = make_double2(0.0, 0.0);
+                for (int t = 0; t <= i; ++t) cfma2(acc, sA[t * 33 + i], sX[t * k + c]);
+                Xb[(size_t)c0 * k + idx] = acc;
+            }
+        }
+        cluster_sync_all();
+        // block column q of L applied to the rows below: the pivot rows of the later links (owner = link mod C) ...
+        const size_t w0 = (size_t)d.w_off[s] + np;  // first update row of this link in the work rows
+        for (int i = q + 1; i < m; ++i) {
+            if (i % CHAIN_C != rank) continue;
+            const int si = cf[i];
+            const int xoff = d.sn_ptr[si] - (c0 + np);
+            chain_block_update(Wb + w0 * k, xoff, F + (size_t)(np + xoff), 1, ld, d.np[si], np, Xb, c0, nullptr, k, sA, sX);
+        }
+        // ... and the rows of the ancestors above the chain, 32 at a time, dealt round-robin
+        for (int x = ncb - nE, blk = 0; x < ncb; x += 32, ++blk) {
+            if ((blk + q) % CHAIN_C != rank) continue;
+            chain_block_update(Wb + w0 * k, x, F + (size_t)(np + x), 1, ld, min(32, ncb - x), np, Xb, c0, nullptr, k, sA, sX);
+        }
+    }
+}
+
 // S[j] += sum_b wgt[b*mg + j] * X[b]   (contour moments, method_contour_common.jl:86-90), elementwise n*k
 __global__ void contour_accumulate_kernel(size_t nk, int nb, int mg, const double2* __restrict__ X, size_t x_stride,
                                                                  const double2* __restrict__ wgt, double2* __restrict__ S) {
@@ -1005,13 +1180,22 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
     }
     // chains of in-place fronts: the tail links (2..m) are walked by one CTA per shift in the solves
     std::vector<char> in_tail(ns, 0);
-    std::vector<int32_t> chain_fronts, sfr_items;
+    std::vector<int32_t> chain_fronts, sfr_items, sfr_tail;
+    std::vector<int4> fu_tail;
     std::vector<std::vector<int2>> fc_of_level(S.nlevels), bc_of_level(S.nlevels);
     // measured on gun (profiles/): a single CTA per shift cannot stream a big chain's factors fast enough (16.0 -> 25.3 ms for
     // 16 nodes), so the chain walk is opt-in (NEPB_LU_CHAINS=1) until it is double-buffered / cluster-wide
-    static const bool use_chains = getenv("NEPB_LU_CHAINS") && atoi(getenv("NEPB_LU_CHAINS")) != 0;
+    // round 2: the chain tails are solved by one thread-block cluster per (chain, shift) (lu_*_chain_cluster_kernel); chains with
+    // fewer than 8 tail links keep the per-level kernels.  NEPB_LU_CHAINS=0 switches the chain kernels off.
+    static const bool use_chains = !(getenv("NEPB_LU_CHAINS") && atoi(getenv("NEPB_LU_CHAINS")) == 0);
     for (int s = 0; s < ns && use_chains; ++s) {
         if (!S.in_place_child[s] || S.has_in_place_child[s]) continue;  // not the first link of a chain
+        int cnt = 0;
+        for (int cur = s; S.in_place_child[cur]; cur = S.sn_parent[cur]) ++cnt;
+        // measured on gun (profiles/r2_chain_solves.txt): a cluster launch costs ~10 us per link plus the rows above the chain, and a
+        // short chain inside a level that has other fronts only adds a launch to that level
+        static const int min_links = getenv("NEPB_LU_CHAIN_MIN") ? atoi(getenv("NEPB_LU_CHAIN_MIN")) : 8;
+        if (cnt < min_links) continue;
         const int first = (int)chain_fronts.size();
         int cur = s;
         while (S.in_place_child[cur]) {
@@ -1019,9 +1203,15 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
             chain_fronts.push_back(cur);
             in_tail[cur] = 1;
         }
-        const int cnt = (int)chain_fronts.size() - first;
-        fc_of_level[S.level[chain_fronts[first]]].push_back(make_int2(first, cnt));
+        // both directions are launched at the level of the LAST link: the forward chain needs the panels of all its links (the
+        // pipelined factor + forward sequence enqueues level l of the forward solve once the panels of level l are final)
+        fc_of_level[S.level[chain_fronts[first + cnt - 1]]].push_back(make_int2(first, cnt));
         bc_of_level[S.level[chain_fronts[first + cnt - 1]]].push_back(make_int2(first, cnt));
+        if (getenv("NEPB_LU_DEBUG")) {
+            const int top = chain_fronts[first + cnt - 1];
+            fprintf(stderr, "[lu] chain: first link front %d (nf %d, level %d), %d tail links up to level %d, %d rows above the chain\n", s, nf[s],
+                    S.level[s], cnt, S.level[top], nf[top] - np[top]);
+        }
     }
     std::vector<int2> fc_items, bc_items;
     int max_level_slots = 0;
@@ -1089,9 +1279,11 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
             for (int j0 = 0; j0 < ncb; j0 += SCHUR_T * SCHUR_GROUP)
                 for (int i0 = 0; i0 < ncb; i0 += SCHUR_T)
                     sp_items.push_back(make_int4(s, i0, j0, std::min(SCHUR_GROUP, (ncb - j0 + SCHUR_T - 1) / SCHUR_T)));
-            if (!in_tail[s]) sfr_items.push_back(s);
+            (in_tail[s] ? sfr_tail : sfr_items).push_back(s);
+            if (ncb > SOLVE_BIG)
+                for (int r0 = 0; r0 < ncb; r0 += SOLVE_CHUNK)
+                    (in_tail[s] ? fu_tail : fu_items).push_back(make_int4(s, r0, std::min(ncb, r0 + SOLVE_CHUNK), 0));
             if (ncb > SOLVE_BIG && !in_tail[s]) {
-                for (int r0 = 0; r0 < ncb; r0 += SOLVE_CHUNK) fu_items.push_back(make_int4(s, r0, std::min(ncb, r0 + SOLVE_CHUNK), 0));
                 // backward partial products over the rows of the ancestors above the parent; levels alternate between two
                 // slot buffers because these items run while the level above still reads its own slots
                 bw_slot[s] = slots;
@@ -1099,8 +1291,16 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
             }
         }
         max_level_slots = std::max(max_level_slots, slots);
+        // chain tails go behind the other fronts of the level: the per-level forward kernels of the pipelined factor + solve
+        // sequence take all of them, everything else stops before the tails (the chain kernels own those)
         L.fu_count = (int)fu_items.size() - L.fu_begin;
         L.sfr_count = (int)sfr_items.size() - L.sfr_begin;
+        fu_items.insert(fu_items.end(), fu_tail.begin(), fu_tail.end());
+        sfr_items.insert(sfr_items.end(), sfr_tail.begin(), sfr_tail.end());
+        L.fu_count_all = (int)fu_items.size() - L.fu_begin;
+        L.sfr_count_all = (int)sfr_items.size() - L.sfr_begin;
+        fu_tail.clear();
+        sfr_tail.clear();
         L.bp_count = (int)bp_items.size() - L.bp_begin;
         L.max_np = 1;
         for (int s2 : fl) L.max_np = std::max(L.max_np, (int)np[s2]);
@@ -1216,6 +1416,8 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
     cudaFuncSetAttribute(lu_backward_chain_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
     cudaFuncSetAttribute(lu_backward_partial_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     NEPB_SOLVE_ATTR(1) NEPB_SOLVE_ATTR(4) NEPB_SOLVE_ATTR(8) NEPB_SOLVE_ATTR(10) NEPB_SOLVE_ATTR(16)
+    cudaFuncSetAttribute(lu_forward_chain_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lu_backward_chain_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 #undef NEPB_SOLVE_ATTR
     *out = sd;
     return NEPB_OK;
@@ -1371,22 +1573,56 @@ struct SolveCtx {
     const int* piv;
     double2 *Xp, *W, *part;
     size_t smem;
+    bool chain_fwd = true;  // forward chain tails by the cluster kernel (false: per level, beside the factorisation)
 };
+
+static inline size_t chain_smem_bytes(int k) { return ((size_t)32 * 33 + (size_t)2 * 32 * k) * 16; }
+static const int2*& fc_ptr(LuSymbolicDev* sd, const LuLevel& L) {
+    static thread_local const int2* p;
+    p = sd->fc_items.p + L.fc_begin;
+    return p;
+}
+static const int2*& bc_ptr(LuSymbolicDev* sd, const LuLevel& L) {
+    static thread_local const int2* p;
+    p = sd->bc_items.p + L.bc_begin;
+    return p;
+}
+// one cluster of CHAIN_C CTAs per (chain, shift)
+static void launch_chain_cluster(const void* kernel, int nchains, int nb, int k, void** args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nchains * CHAIN_C), (unsigned)nb, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = chain_smem_bytes(k);
+    cfg.stream = stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CHAIN_C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelExC(&cfg, kernel, args);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
 
 template <int CK>
 static void solve_forward_level(const SolveCtx& c, int l) {
     LuSymbolicDev* sd = c.sd;
     const auto& L = sd->lv[l];
     const size_t sml = solve_smem_bytes(L.max_np, c.k);
-    if (L.sfr_count)
-        NEPB_LAUNCH((lu_forward_kernel<CK>), dim3(L.sfr_count, c.nb), 256, sml, sd->dev, sd->sfr_items.p + L.sfr_begin, c.F, c.piv, c.Xp, c.W, c.k,
+    // per-level kernels: without the chain tails when the chain kernel takes them (single solves), with them when the forward
+    // substitution runs beside the factorisation (level l as soon as its panels are final)
+    const int nfr = c.chain_fwd ? L.sfr_count : L.sfr_count_all, nfu = c.chain_fwd ? L.fu_count : L.fu_count_all;
+    if (nfr)
+        NEPB_LAUNCH((lu_forward_kernel<CK>), dim3(nfr, c.nb), 256, sml, sd->dev, sd->sfr_items.p + L.sfr_begin, c.F, c.piv, c.Xp, c.W, c.k,
                     L.max_np);
-    if (L.fu_count)
-        NEPB_LAUNCH((lu_forward_update_kernel<CK>), dim3(L.fu_count, c.nb), 128, sml, sd->dev, sd->fu_items.p + L.fu_begin, c.F,
+    if (nfu)
+        NEPB_LAUNCH((lu_forward_update_kernel<CK>), dim3(nfu, c.nb), 128, sml, sd->dev, sd->fu_items.p + L.fu_begin, c.F,
                     (const double2*)c.Xp, c.W, c.k, L.max_np);
-    if (L.fc_count)
-        NEPB_LAUNCH((lu_forward_chain_kernel<CK>), dim3(L.fc_count, c.nb), 256, c.smem, sd->dev, sd->fc_items.p + L.fc_begin, sd->chain_fronts.p,
-                    c.F, c.piv, c.Xp, c.W, c.k, sd->S.max_np);
+    if (L.fc_count && c.chain_fwd) {
+        void* args[] = {(void*)&sd->dev, (void*)&fc_ptr(sd, L), (void*)&sd->chain_fronts.p, (void*)&c.F, (void*)&c.piv, (void*)&c.Xp, (void*)&c.W, (void*)&c.k};
+        launch_chain_cluster((const void*)lu_forward_chain_cluster_kernel, L.fc_count, c.nb, c.k, args);
+    }
 }
 
 // partial products of level l over the solution rows of levels >= l + 2 (everything above the parents)
@@ -1404,9 +1640,10 @@ static void solve_backward_level(const SolveCtx& c, int l) {
     LuSymbolicDev* sd = c.sd;
     const auto& L = sd->lv[l];
     const size_t sml = solve_smem_bytes(L.max_np, c.k);
-    if (L.bc_count)
-        NEPB_LAUNCH((lu_backward_chain_kernel<CK>), dim3(L.bc_count, c.nb), 256, c.smem, sd->dev, sd->bc_items.p + L.bc_begin, sd->chain_fronts.p,
-                    c.F, c.Xp, sd->S.max_np, c.k);
+    if (L.bc_count) {
+        void* args[] = {(void*)&sd->dev, (void*)&bc_ptr(sd, L), (void*)&sd->chain_fronts.p, (void*)&c.F, (void*)&c.Xp, (void*)&c.k};
+        launch_chain_cluster((const void*)lu_backward_chain_cluster_kernel, L.bc_count, c.nb, c.k, args);
+    }
     if (L.sfr_count)
         NEPB_LAUNCH((lu_backward_kernel<CK>), dim3(L.sfr_count, c.nb), 256, sml, sd->dev, sd->sfr_items.p + L.sfr_begin, c.F, c.Xp,
                     (const double2*)c.part, sd->part_slots, L.max_np, c.k);
@@ -1492,6 +1729,7 @@ int lu_factor_solve_pipelined(nepb_lu* lu, int k, const double2* Bdev, size_t rh
     int rc = solve_ctx(lu, 0, lu->nb, k, &c);
     if (rc) return rc;
     const int n = c.sd->S.n, nlev = c.sd->S.nlevels, nb = lu->nb;
+    c.chain_fwd = false;
     cudaStream_t s0 = stream();
     dim3 pg((unsigned)(((size_t)n * k + 255) / 256), nb);
     NEPB_CUDA(cudaEventRecord(ev[0], s0));  // fork: the side stream starts after everything already queued on s0

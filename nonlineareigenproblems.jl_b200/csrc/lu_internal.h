@@ -63,9 +63,9 @@ struct LuLevel {
     int pn_begin = 0, pn_count = 0;
     int sc_begin = 0, sc_count = 0;
     int sp_begin = 0, sp_count = 0;  // pipelined schur items
-    int fu_begin = 0, fu_count = 0;  // forward update items (big fronts)
+    int fu_begin = 0, fu_count = 0, fu_count_all = 0;  // forward update items (big fronts); _all: including chain tails
     int bp_begin = 0, bp_count = 0;  // backward partial-product items (big fronts)
-    int sfr_begin = 0, sfr_count = 0;  // fronts handled per level in the solves (chain tails excluded)
+    int sfr_begin = 0, sfr_count = 0, sfr_count_all = 0;  // fronts handled per level in the solves (chain tails excluded / included)
     int fc_begin = 0, fc_count = 0;    // chains whose tail starts at this level (forward)
     int bc_begin = 0, bc_count = 0;    // chains whose tail ends at this level (backward)
 };

@@ -514,6 +514,7 @@ __global__ void __launch_bounds__(256) spmm_tma_kernel(int kt, int ldv, int ldz,
     constexpr int UN = CPT >= 3 ? 2 : 4;
     int base = start;
     if (pair) {
+#pragma unroll 2
         for (; base + 2 <= end; base += 2) {
             const int la = (int)sL[base], lb = (int)sL[base + 1];
             double va[VW], vb[VW];
