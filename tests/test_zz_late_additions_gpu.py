@@ -130,7 +130,13 @@ def test_tiled_spmm_tma_bulk_variant():
     lam = 0.3 + 0.2j
     for k in (5, 8, 12):
         V = rng.standard_normal((dnep.n, k)) + 1j * rng.standard_normal((dnep.n, k))
-        Z0 = dnep.compute_MM(lam * np.eye(k), V)
+        os.environ["NEPB_SPMM_TMA"] = "0"  # the round-1 cp.async tiled kernel: same summation order as its bulk-copy variant
+        try:
+            Z0 = dnep.compute_MM(lam * np.eye(k), V)
+        finally:
+            del os.environ["NEPB_SPMM_TMA"]
+        Zdef = dnep.compute_MM(lam * np.eye(k), V)  # the default (round 2) TMA-staged kernel: two accumulator sets, other order
+        assert np.linalg.norm(Zdef - Z0) <= 1e-14 * np.linalg.norm(Z0)
         os.environ["NEPB_SPMM_BULK"] = "1"
         try:
             Z1 = dnep.compute_MM(lam * np.eye(k), V)
