@@ -173,6 +173,7 @@ struct nepb_contour {
     int batch = 0, k = 0, mg = 0;
     std::vector<ContourGroup*> groups;
     DevBuf<double> vh, s, stage;
+    DevBuf<const double*> d_parts;  // device copy of the group accumulator pointers
     std::vector<int> node_flags;
     int64_t nodes_done = 0;
     ~nepb_contour() {
@@ -371,7 +372,7 @@ static int contour_integrate_groups(nepb_contour* c, int nnodes, const double* c
     // S = sum of the group accumulators, on the main stream (all group streams are idle: lu_fetch_info synchronised them)
     std::vector<const double*> parts;
     for (auto* G : c->groups) parts.push_back(G->s.p);
-    static DevBuf<const double*> d_parts;
+    DevBuf<const double*>& d_parts = c->d_parts;  // per handle (and therefore per device)
     NEPB_CUDA(d_parts.reserve(parts.size()));
     NEPB_CUDA(cudaMemcpyAsync(d_parts.p, parts.data(), sizeof(double*) * parts.size(), cudaMemcpyHostToDevice, main_stream()));
     const size_t cnt = 2 * nk * c->mg;

@@ -962,11 +962,13 @@ static int launch_tiled_vw(const nepb_spmf* h, const nepb_spmf::TileSet& T, int 
     const bool bulk = getenv("NEPB_SPMM_BULK") && atoi(getenv("NEPB_SPMM_BULK")) != 0;  // read per call: tests toggle it
 #define NEPB_TILED_B(CPT_, BULK_)                                                                                                     \
     do {                                                                                                                              \
-        static size_t attr_done = 0;                                                                                                  \
-        if (smem > 48 * 1024 && smem > attr_done) {                                                                                   \
+        static size_t attr_done[16] = {0}; /* per device */                                                                           \
+        int dev_ = 0;                                                                                                                 \
+        cudaGetDevice(&dev_);                                                                                                         \
+        if (smem > 48 * 1024 && smem > attr_done[dev_ & 15]) {                                                                        \
             NEPB_CUDA(cudaFuncSetAttribute(spmm_tiled_kernel<VW, CA, DIAG, CPT_, BULK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            (int)smem));                                                                               \
-            attr_done = smem;                                                                                                         \
+            attr_done[dev_ & 15] = smem;                                                                                              \
         }                                                                                                                             \
         NEPB_LAUNCH((spmm_tiled_kernel<VW, CA, DIAG, CPT_, BULK_>), (unsigned)T.ntiles, threads, smem, kt, kinv, ldv, ldz, T.max_cols, \
                     T.max_nnz, T.tiles.p, T.cols.p, h->d_rowptr.p, T.lidx.p, h->d_vals.p, V, Z, cp, cdiag, h->p);                     \

@@ -189,6 +189,7 @@ end
 struct B200BackslashLinSolverCreator <: LinSolverCreator end                     # LinSolverCreators.jl:21-37: factorise per solve
 struct B200BackslashLinSolver <: LinSolver; nep::B200SPMF; λ::CF; end
 create_linsolver(::B200BackslashLinSolverCreator, nep::B200SPMF, λ) = B200BackslashLinSolver(nep, CF(λ))
+# `solver.A \ x` on a sparse matrix is `lu(A) \ x` with UMFPACK's default of two refinement steps (LinSolvers.jl:157-159)
 lin_solve(s::B200BackslashLinSolver, b::AbstractVecOrMat; tol=0) = lin_solve(B200LinSolver(s.nep, s.λ, 2), b)
 
 # ------------------------------------------------------------------------------------------------
@@ -199,7 +200,8 @@ lin_solve(s::B200BackslashLinSolver, b::AbstractVecOrMat; tol=0) = lin_solve(B20
 abstract type B200Trapezoidal <: MatrixIntegrator end
 
 """S[:,:,j] = Σ_i w[i,j] M(λ_i)⁻¹ Vh for this rank's nodes; `reduce=true` sums over the NCCL communicator."""
-function b200_contour_moments(nep::B200SPMF, λv::Vector{CF}, W::Matrix{CF}, Vh::Matrix{CF}; batch::Integer=32, reduce::Bool=false)
+function b200_contour_moments(nep::B200SPMF, λv::Vector{CF}, W::Matrix{CF}, Vh::Matrix{CF}; batch::Integer=32, reduce::Bool=false,
+                              root_only::Bool=false)   # root_only: only rank 0 copies the summed moments back (the others get garbage in S)
     n, k = size(Vh); N, mg = size(W)
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
     chk(ccall(sym(:nepb_contour_create), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Ptr{Cvoid}}), nep.h, k, mg, min(batch, max(N, 1)), ctx))
@@ -209,11 +211,14 @@ function b200_contour_moments(nep::B200SPMF, λv::Vector{CF}, W::Matrix{CF}, Vh:
     S = Array{CF,3}(undef, n, k, mg); flags = zeros(Cint, max(N, 1))
     try
         chk(ccall(sym(:nepb_contour_integrate), Cint, (Ptr{Cvoid}, Cint, Ptr{CF}, Ptr{CF}, Ptr{CF}, Int64, Cint, Ptr{CF}, Ptr{Cint}),
-                  ctx[], N, coef, Wt, Vh, n, reduce ? 1 : 0, S, flags))
+                  ctx[], N, coef, Wt, Vh, n, reduce ? (root_only ? 2 : 1) : 0, S, flags))
     finally
         ccall(sym(:nepb_contour_destroy), Cint, (Ptr{Cvoid},), ctx[])
     end
-    any(flags .& 2 .!= 0) && throw(LinearAlgebra.SingularException(0))   # an eigenvalue lies on the contour
+    # bit0 zero pivot, bit1 non-finite pivot, bit2 lifted pivots (after the library's static-pivoting fallback, bit3): the
+    # reference would get an accurate UMFPACK solve or a SingularException at such a node, never a silently perturbed one
+    any(flags .& 7 .!= 0) && throw(LinearAlgebra.SingularException(0))
+    any(flags .& 16 .!= 0) && @warn "quadrature nodes with pivots below 1e-8 max|M_ij|: an eigenvalue lies very close to the contour"
     return S
 end
 
@@ -228,15 +233,18 @@ function contour_beyn(::Type{T}, nep::B200SPMF, ::Type{B200Trapezoidal}; σ::Num
     W = hcat(gp .* h, gp .* g .* h)                               # temp*G[i,j]*h; the /(2πi) is applied by contour_beyn itself
     mine = (rank+1):world:N
     S = b200_contour_moments(nep, CF.(g[mine] .+ σ), Matrix{CF}(W[mine, :]), Vhm; batch=batch, reduce=world > 1)
-    # hand the finished integral to the reference's own extraction code (SVD, rank test, eigen, filters: :110-184)
-    precomputed_integral[] = S
-    return NonlinearEigenproblems.NEPSolver.contour_beyn(T, nep, PrecomputedIntegral; σ=σ, radius=radius, N=N, neigs=neigs, k=k, kwargs...)
+    # hand the finished integral to the reference's own extraction code (SVD, rank test, eigen, filters: :110-184).  The
+    # integrator is selected by TYPE in the reference (method_contour_common.jl:18-45), so it cannot carry the array itself;
+    # task-local storage keeps concurrent contour_beyn calls (one per Task / worker) apart.
+    return task_local_storage(:nepb200_precomputed_integral, S) do
+        NonlinearEigenproblems.NEPSolver.contour_beyn(T, nep, PrecomputedIntegral; σ=σ, radius=radius, N=N, neigs=neigs, k=k, kwargs...)
+    end
 end
 contour_beyn(nep::B200SPMF; params...) = contour_beyn(CF, nep, B200Trapezoidal; params...)
 # integrator that returns an integral computed beforehand (lets the unmodified reference code do the post-processing)
 abstract type PrecomputedIntegral <: MatrixIntegrator end
-const precomputed_integral = Ref{Array{CF,3}}()
-integrate_interval(::Type{PrecomputedIntegral}, ::Type{T}, f, gv, a, b, N, logger) where {T<:Number} = precomputed_integral[]
+integrate_interval(::Type{PrecomputedIntegral}, ::Type{T}, f, gv, a, b, N, logger) where {T<:Number} =
+    task_local_storage(:nepb200_precomputed_integral)::Array{CF,3}
 
 # ------------------------------------------------------------------------------------------------
 # multi-GPU plumbing: one Julia worker per GPU (`julia -p 8`), NCCL id shipped with Distributed

@@ -195,3 +195,51 @@ def test_ilan_device_matches_oracle():
             assert np.linalg.norm(o.compute_Mlincomb(onep, l, w)) / np.linalg.norm(w) < 1e-6
     with pytest.raises(nepb200.NoConvergenceException):
         nepb200.ilan(dnep, neigs=2, maxit=3, tol=np.finfo(float).eps * 100, check_error_every=np.inf, v=np.ones(n))
+
+
+def test_contour_c3_at_the_stated_size():
+    """BASELINE config C3 at its full size: gun, contour_beyn sigma = 150^2, radius = 500, N = 128 nodes, k = 20 probe columns.
+    The CPU oracle needs ~2 s per node, so the full integral is checked through what does not depend on the size --
+      * sharding: the 8 round-robin shares of the nodes (what each of 8 GPUs integrates) add up to the 128-node moments (1e-12),
+      * a 6-node sample of exactly these nodes / weights / probe against SuperLU solves at k = 20 (1e-10),
+      * extraction: exactly one eigenvalue inside, equal to the reference's 22345.116783765 + 0.644998598im (test/gun_native.jl:9),
+        with relative residual below 1e-10 -- and batch size / graph replay do not change a bit of the moments."""
+    import scipy.sparse.linalg as sla
+    onep, dnep = gun_pair()
+    n, N, k = dnep.n, 128, 20
+    Vh = msws_probe(n, k)
+    sigma, radius = 150.0 ** 2, 500.0
+    lam, V, A0, A1, info = nepb200.contour_beyn(dnep, Vh, sigma=sigma, radius=radius, N=N, neigs=5, k=k, batch=128, return_moments=True)
+    assert len(lam) == 1 and info["p"] == 1
+    assert abs(lam[0] - (22345.116783765 + 0.644998598j)) < 1e-6
+    Mo = sp.csc_matrix(o.compute_Mder(onep, lam[0]))
+    assert np.linalg.norm(Mo @ V[:, 0]) / (abs(Mo).sum(axis=0).max() * np.linalg.norm(V[:, 0])) < 1e-10
+    h = 2 * np.pi / N
+    t = h * np.arange(N)
+    g_ = radius * (np.cos(t) + 1j * np.sin(t))
+    gp = radius * (-np.sin(t) + 1j * np.cos(t))
+    W = np.stack([gp * h / (2j * np.pi), gp * g_ * h / (2j * np.pi)], axis=1)
+    integ = nepb200.ContourIntegrator(dnep, k, 2, 16)
+    S = np.zeros((n, k, 2), dtype=complex)
+    for r in range(8):
+        part, flags = integ.integrate(g_[r::8] + sigma, W[r::8], Vh)
+        assert not np.any(flags)
+        S += part
+    assert np.linalg.norm(S[:, :, 0] - A0) / np.linalg.norm(A0) < 1e-12
+    assert np.linalg.norm(S[:, :, 1] - A1) / np.linalg.norm(A1) < 1e-12
+    # the same 128 nodes in one batch, twice: bitwise reproducible
+    integ2 = nepb200.ContourIntegrator(dnep, k, 2, 128)
+    Sa, _ = integ2.integrate(g_ + sigma, W, Vh)
+    Sb, _ = integ2.integrate(g_ + sigma, W, Vh)
+    assert np.array_equal(Sa, Sb)
+    assert np.linalg.norm(Sa[:, :, 0] - A0) / np.linalg.norm(A0) < 1e-12
+    idx = np.array([0, 17, 31, 64, 99, 127])
+    Ssub, _ = integ.integrate(g_[idx] + sigma, W[idx], Vh)
+    ref = np.zeros_like(Ssub)
+    for i in idx:
+        X = sla.splu(sp.csc_matrix(o.compute_Mder(onep, g_[i] + sigma), dtype=complex)).solve(Vh.astype(complex))
+        ref[:, :, 0] += W[i, 0] * X
+        ref[:, :, 1] += W[i, 1] * X
+    assert np.linalg.norm(Ssub - ref) / np.linalg.norm(ref) < 1e-10
+    integ.close()
+    integ2.close()
