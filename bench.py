@@ -30,6 +30,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NumPy's BLAS worker threads keep spinning for tens of milliseconds after a call (the parity norms below) and then compete with
+# the library's host-copy threads for the cores: the host-buffer timings of the next call went from 1.2 ms to 24 ms
+# (gpurun_out/r2_hostcopy3.log).  The harness itself needs no threaded BLAS.
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+os.environ.setdefault("MKL_NUM_THREADS", "1")
 
 import numpy as np  # noqa: E402
 
@@ -244,10 +249,13 @@ def bench_spmm(args, ks=(1, 8, 20)):
         err = float(np.linalg.norm(Zb.download() - Zref) / np.linalg.norm(Zref))
         Zh = np.empty((n, k), dtype=np.complex128, order="F")  # the caller's result array, reused (no fresh pages per call)
         dnep.apply(_lib.COEF_SCALAR, V, coef, k, out=Zh)
-        t0 = time.perf_counter()
-        for _ in range(3):
+        tes = []
+        for _ in range(5):
+            t0 = time.perf_counter()
             dnep.apply(_lib.COEF_SCALAR, V, coef, k, out=Zh)
-        te = (time.perf_counter() - t0) / 3 * 1e3
+            tes.append((time.perf_counter() - t0) * 1e3)
+        te = float(np.median(tes))
+        log("[bench]   host-buffer calls k=%d: %s ms" % (k, " ".join("%.2f" % x for x in tes)))
         err = max(err, float(np.linalg.norm(Zh - Zref) / np.linalg.norm(Zref)))
         out[k] = {"k": k, "ms": t, "gbs": nbytes / t / 1e6, "bytes": int(nbytes), "frac": nbytes / t / 1e6 / peak,
                   "launches": int(launches), "e2e_ms": te, "e2e_gbs": nbytes / te / 1e6, "parity_relerr": err}
