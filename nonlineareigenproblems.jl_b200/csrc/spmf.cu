@@ -761,6 +761,165 @@ __global__ void __launch_bounds__(256) panel_gemm_kernel(int n, int k, int w, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// GENERAL mode, round 2.  Stage 1: X(n x w) = V(n x k) * Cs(k x w), w = p*q small.  Bandwidth bound on V: 8 lanes per row
+// (a warp instruction reads four rows with 128 contiguous bytes each), lane g owns k-indices g, g + 8, ..; the WT outputs of a
+// pass are reduced over the 8 lanes with 3 shuffle steps and written as one contiguous piece per row.  Cs sits in shared
+// memory (k*w*16 bytes).  Round 1's 32 x 32 shared-memory tile kernel took 219 us where 60 us is the HBM time (C4, k = 20).
+// ---------------------------------------------------------------------------------------------
+template <int WT>
+__global__ void __launch_bounds__(256) panel_rows_kernel(int n, int k, int w, const double2* __restrict__ V, int ldv,
+                                                         const double2* __restrict__ Cs, double2* __restrict__ X) {
+    // 4 lanes per row (lane g owns the k-indices g, g + 4, ..), 4 rows per lane: a coefficient Cs[kk][c] read from shared memory
+    // serves 4 rows, and the reduction over the lanes of a row needs 2 shuffle steps.  (First version: 8 lanes per row, one row per
+    // lane -- the coefficient reads alone kept the shared-memory pipe 83-90 % busy, DRAM at 20 %.)  Pitch w + 1: the 8 lanes of
+    // a 128-bit shared-memory phase read 4 different rows of Cs, conflict-free with the odd pitch.
+    extern __shared__ double2 sCs[];  // [k][w + 1]
+    const int pw = w + 1;
+    for (int idx = threadIdx.x; idx < k * w; idx += 256) sCs[(idx / w) * pw + idx % w] = Cs[idx];
+    __syncthreads();
+    constexpr int RPL = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane & 3, rg = lane >> 2;
+    const int row_base = blockIdx.x * (8 * 8 * RPL) + warp * (8 * RPL) + rg;  // rows row_base + 8 u, u < RPL
+    for (int w0 = 0; w0 < w; w0 += WT) {
+        double2 acc[RPL][WT];
+#pragma unroll
+        for (int u = 0; u < RPL; ++u)
+#pragma unroll
+            for (int c = 0; c < WT; ++c) acc[u][c] = make_double2(0.0, 0.0);
+        for (int kk = g; kk < k; kk += 4) {
+            double2 v[RPL], cc[WT];
+#pragma unroll
+            for (int u = 0; u < RPL; ++u) {
+                const int r = row_base + 8 * u;
+                v[u] = r < n ? V[(size_t)r * ldv + kk] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int c = 0; c < WT; ++c) cc[c] = (w0 + c < w) ? sCs[kk * pw + w0 + c] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < RPL; ++u)
+#pragma unroll
+                for (int c = 0; c < WT; ++c) cfma(acc[u][c], v[u], cc[c]);
+        }
+#pragma unroll
+        for (int u = 0; u < RPL; ++u)
+#pragma unroll
+            for (int c = 0; c < WT; ++c) {
+                acc[u][c].x += __shfl_xor_sync(0xffffffffu, acc[u][c].x, 1);
+                acc[u][c].y += __shfl_xor_sync(0xffffffffu, acc[u][c].y, 1);
+                acc[u][c].x += __shfl_xor_sync(0xffffffffu, acc[u][c].x, 2);
+                acc[u][c].y += __shfl_xor_sync(0xffffffffu, acc[u][c].y, 2);
+            }
+#pragma unroll
+        for (int u = 0; u < RPL; ++u) {
+            const int r = row_base + 8 * u;
+            if (r < n) {
+#pragma unroll
+                for (int c = 0; c < WT; ++c)
+                    if ((c & 3) == g && w0 + c < w) X[(size_t)r * w + w0 + c] = acc[u][c];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GENERAL mode, stage 2 (round 2): Z[row, c] = sum_nz sum_i a_i(nz) X[col(nz)][c][i] with the rows of X (p*q complex values,
+// contiguous) staged per 16-row tile by TMA bulk copies of column runs, like spmm_tma_kernel; real term values, p <= 4.
+// Lane layout per row: 4 lanes = the 4 terms (lane i multiplies with a_i: the 32 bytes of term values of a nonzero are read as
+// four different 8-byte pieces, nothing is broadcast), times QS column slots (1 for q = 1, else 2).  The term sums are
+// reduced over the 4 lanes with 2 shuffle steps at the end of the row.
+// ---------------------------------------------------------------------------------------------
+template <int QS, int CPT>
+__global__ void __launch_bounds__(128) spmm_stacked_tma_kernel(int q, int p, int ldz, int max_cols, int max_nnz, int tile_rows,
+                                                               const int4* __restrict__ tiles, const int2* __restrict__ runs,
+                                                               const int* __restrict__ rowptr, const uint16_t* __restrict__ lidx,
+                                                               const double* __restrict__ vals, const double2* __restrict__ X,
+                                                               double2* __restrict__ Z) {
+    constexpr int LPR = 4 * QS;  // lanes per row
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int P = p * q;  // complex values per row of X
+    const TmaSmem L = tma_smem_layout(max_cols, max_nnz, P, 4, true, tile_rows);
+    const double2* sX = (const double2*)(smem_raw + L.sV);
+    int* sRp = (int*)(smem_raw + L.sRp);
+    const int4 t0 = tiles[2 * blockIdx.x], t1 = tiles[2 * blockIdx.x + 1];
+    const int row0 = t0.x, nrows = t0.y, ncols = t0.w, nz0 = t1.x, nnz = t1.y, run0 = t1.z, nruns = t1.w;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(smem_raw + L.bar);
+    const size_t a_byte = (size_t)nz0 * p * 8, l_byte = (size_t)nz0 * 2;  // p doubles per nonzero (real values)
+    const unsigned a_skip = (unsigned)(a_byte & 15), l_skip = (unsigned)(l_byte & 15);
+    const unsigned a_len = ((unsigned)nnz * p * 8 + a_skip + 15) & ~15u, l_len = ((unsigned)nnz * 2 + l_skip + 15) & ~15u;
+    const double* sA = (const double*)(smem_raw + L.sA + a_skip);
+    const uint16_t* sL = (const uint16_t*)(smem_raw + L.sL + l_skip);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned total = (unsigned)ncols * P * 16 + a_len + l_len;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(total) : "memory");
+        bulk_g2s((unsigned)__cvta_generic_to_shared(smem_raw + L.sA), (const unsigned char*)vals + (a_byte - a_skip), a_len, bar_s);
+        bulk_g2s((unsigned)__cvta_generic_to_shared(smem_raw + L.sL), (const unsigned char*)lidx + (l_byte - l_skip), l_len, bar_s);
+    }
+    for (int r = tid; r < nruns; r += nth) {
+        const int2 rn = runs[run0 + r];
+        const int dst_row = rn.y & 0xffff, len = rn.y >> 16;
+        bulk_g2s((unsigned)__cvta_generic_to_shared(sX + (size_t)dst_row * P), X + (size_t)rn.x * P, (unsigned)len * P * 16, bar_s);
+    }
+    if (tid <= nrows) sRp[tid] = rowptr[row0 + tid] - nz0;
+    {
+        unsigned done = 0, spins = 0;
+        while (!done) {
+            if (++spins > (1u << 26)) asm volatile("trap;");
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done)
+                         : "r"(bar_s), "r"(0)
+                         : "memory");
+        }
+    }
+    __syncthreads();
+    const int i = tid & 3;                   // term
+    const int cs = (tid % LPR) >> 2;         // column slot
+    const int r = tid / LPR;                 // row within the tile
+    int start = 0, end = 0;
+    if (r < nrows) {
+        start = sRp[r];
+        end = sRp[r + 1];
+    }
+    double2 acc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[j] = make_double2(0.0, 0.0);
+    const bool term_ok = i < p;
+#pragma unroll 2
+    for (int idx = start; idx < end; ++idx) {
+        const double a = term_ok ? sA[(size_t)idx * p + i] : 0.0;   // p doubles per nonzero (vw = p, real values)
+        const double2* xr = sX + (size_t)sL[idx] * P + (term_ok ? i : 0);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int c = cs + j * QS;
+            if (c < q) {
+                const double2 x = xr[c * p];
+                acc[j].x = fma(a, x.x, acc[j].x);
+                acc[j].y = fma(a, x.y, acc[j].y);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, 1);
+        acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, 1);
+        acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, 2);
+        acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, 2);
+    }
+    if (r < nrows && i == 0) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int c = cs + j * QS;
+            if (c < q) Z[(size_t)(row0 + r) * ldz + c] = acc[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Mder values: out[e] (CSC order) = sum_i c_i * vals[csr_of_csc[e]][i]
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mder_kernel(int64_t nnz, int p, int ca, const int* __restrict__ csr_of_csc,
@@ -1215,9 +1374,54 @@ int spmf_apply_device_ld(const nepb_spmf* h, int mode, int k, int q, const doubl
     NEPB_CUDA(cudaMemcpyAsync(h->d_coef.p, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice, stream()));
     NEPB_CUDA(cudaStreamSynchronize(stream()));  // cs is a local buffer
     NEPB_CUDA(h->d_tmp_x.reserve((size_t)2 * h->n * w));
-    NEPB_LAUNCH(panel_gemm_kernel, (int)((h->n + PANEL_R - 1) / PANEL_R), 256, 0, (int)h->n, k, w, dV, ldv,
-                (const double2*)h->d_coef.p, (double2*)h->d_tmp_x.p);
+    static const bool v1 = getenv("NEPB_GENERAL_V1") && atoi(getenv("NEPB_GENERAL_V1")) != 0;
+    // stage 1: row-streaming panel product when the coefficient block fits shared memory
+    if (!v1 && (size_t)k * (w + 1) * 16 <= 96 * 1024) {
+        const size_t smem = (size_t)k * (w + 1) * 16;
+        static size_t attr_done[16] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (smem > 48 * 1024 && smem > attr_done[dev & 15]) {
+            NEPB_CUDA(cudaFuncSetAttribute(panel_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            NEPB_CUDA(cudaFuncSetAttribute(panel_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_done[dev & 15] = 96 * 1024;
+        }
+        const unsigned grid = (unsigned)((h->n + 255) / 256);
+        if (w <= 4)
+            NEPB_LAUNCH(panel_rows_kernel<4>, grid, 256, smem, (int)h->n, k, w, dV, ldv, (const double2*)h->d_coef.p, (double2*)h->d_tmp_x.p);
+        else
+            NEPB_LAUNCH(panel_rows_kernel<8>, grid, 256, smem, (int)h->n, k, w, dV, ldv, (const double2*)h->d_coef.p, (double2*)h->d_tmp_x.p);
+    } else {
+        NEPB_LAUNCH(panel_gemm_kernel, (int)((h->n + PANEL_R - 1) / PANEL_R), 256, 0, (int)h->n, k, w, dV, ldv,
+                    (const double2*)h->d_coef.p, (double2*)h->d_tmp_x.p);
+    }
     NEPB_LAUNCH_CHECK();
+    // stage 2: TMA-staged stacked gather for real term values with p <= 4 and up to 32 output columns
+    if (!v1 && !h->is_complex && p <= 4 && h->vw == p && q <= 32 && spmf_build_tiles(h, 1) == 1) {
+        const nepb_spmf::TileSet& T = h->tiling[1];
+        const TmaSmem L = tma_smem_layout(T.max_cols, T.max_nnz, w, 4, true, 16);
+        if (L.total <= 200 * 1024) {
+#define NEPB_STK(QS_, CPT_)                                                                                                          \
+    do {                                                                                                                             \
+        static size_t attr_done2[16] = {0};                                                                                          \
+        int dev2 = 0;                                                                                                                \
+        cudaGetDevice(&dev2);                                                                                                        \
+        if (L.total > 48 * 1024 && L.total > attr_done2[dev2 & 15]) {                                                                \
+            NEPB_CUDA(cudaFuncSetAttribute(spmm_stacked_tma_kernel<QS_, CPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
+            attr_done2[dev2 & 15] = L.total;                                                                                         \
+        }                                                                                                                            \
+        NEPB_LAUNCH((spmm_stacked_tma_kernel<QS_, CPT_>), (unsigned)T.ntiles, 16 * 4 * QS_, L.total, q, p, ldz, T.max_cols, T.max_nnz, 16, \
+                    T.tiles.p, T.runs.p, h->d_rowptr.p, T.lidx.p, h->d_vals.p, (const double2*)h->d_tmp_x.p, dZ);                     \
+    } while (0)
+            if (q == 1) NEPB_STK(1, 1);
+            else if (q <= 8) NEPB_STK(2, 4);
+            else if (q <= 16) NEPB_STK(2, 8);
+            else NEPB_STK(2, 16);
+#undef NEPB_STK
+            NEPB_LAUNCH_CHECK();
+            return NEPB_OK;
+        }
+    }
     return launch_stacked(h, q, (const double2*)h->d_tmp_x.p, dZ, ldz);
 }
 
