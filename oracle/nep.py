@@ -498,3 +498,78 @@ def nep_gallery(name, *params):
         n = A0.shape[0]
         return SPMF_NEP([-sp.identity(n, format="csc"), A0, A1], [f_pow(2), f_one, f_exp(-1.0)])
     raise ValueError("%s not supported" % name)
+
+
+# --------------------------------------------------------------------------------------------
+# deflation (src/nep_deflation.jl), MM formulation: DeflatedNEPMM (:17-21), compute_MM (:183-197), compute_Mlincomb through
+# compute_Mlincomb_from_MM (:199-201), compute_Mder column by column through compute_MM (compute_Mder_from_MM, NEPCore.jl).
+# The product mirrors the *Generic* formulation (binomial expansion); the reference's own test "Deflation modes" (test/deflation.jl:
+# 46-92) asserts that the two formulations agree -- that assertion is what the parity tests re-use.
+# --------------------------------------------------------------------------------------------
+class DeflatedNEPMM:
+    def __init__(self, orgnep, S0, V0):
+        self.orgnep = orgnep
+        self.S0 = np.atleast_2d(np.asarray(S0, dtype=np.complex128))
+        self.V0 = np.asarray(V0, dtype=np.complex128).reshape(orgnep.n, -1)
+        self.n = orgnep.n + self.V0.shape[1]
+
+
+def deflated_compute_MM(dnep, S, V):
+    """nep_deflation.jl:183-197."""
+    S = np.atleast_2d(np.asarray(S, dtype=np.complex128))
+    V = np.asarray(V, dtype=np.complex128)
+    n0, p0, p = dnep.orgnep.n, dnep.S0.shape[0], S.shape[0]
+    V1, V2 = V[:n0, :], V[n0:, :]
+    Stilde = np.block([[dnep.S0, V2], [np.zeros((p, p0), dtype=np.complex128), S]])
+    Vtilde = np.concatenate([dnep.V0, V1], axis=1)
+    R = compute_MM(dnep.orgnep, Stilde, Vtilde)
+    return np.concatenate([R[:n0, p0:], dnep.V0.conj().T @ V1], axis=0)
+
+
+def deflated_compute_Mlincomb(dnep, lam, V, a=None):
+    """compute_Mlincomb_from_MM (NEPCore.jl:212-228) on the deflated problem."""
+    V = np.array(V, dtype=np.complex128, copy=True)
+    V = V.reshape(dnep.n, -1, order="F") if V.ndim == 1 else V
+    k = V.shape[1]
+    a = np.ones(k, dtype=np.complex128) if a is None else np.array(a, dtype=np.complex128, copy=True)
+    zero = a == 0
+    V[:, zero] = 0
+    a[zero] = 1
+    S = np.diag(np.full(k, lam, dtype=np.complex128)) + np.diag((a[1:] / a[:-1]) * np.arange(1, k), -1)
+    return a[0] * deflated_compute_MM(dnep, S, V)[:, 0]
+
+
+def deflated_compute_Mder(dnep, lam, der=0):
+    """compute_Mder_from_MM: column j of M^(der)(lam) = der-th derivative applied to e_j, through a Jordan block of size der + 1."""
+    n = dnep.n
+    M = np.zeros((n, n), dtype=np.complex128)
+    S = np.diag(np.full(der + 1, lam, dtype=np.complex128)) + np.diag(np.ones(der), 1)
+    fact = float(np.prod(np.arange(1, der + 1))) if der else 1.0
+    for j in range(n):
+        V = np.zeros((n, der + 1), dtype=np.complex128)
+        V[j, 0] = 1.0
+        M[:, j] = deflated_compute_MM(dnep, S, V)[:, der] * fact
+    return M
+
+
+def normalize_schur_pair(S, V):
+    """nep_deflation.jl:278-287."""
+    QQ, RR = np.linalg.qr(V)
+    return RR @ S @ np.linalg.inv(RR), QQ
+
+
+def deflate_eigpair(nep, lam, v):
+    """nep_deflation.jl:369-398 (mode :MM)."""
+    v = np.asarray(v, dtype=np.complex128)
+    if isinstance(nep, DeflatedNEPMM):
+        n, p0 = nep.orgnep.n, nep.V0.shape[1]
+        V1 = np.zeros((n, p0 + 1), dtype=np.complex128)
+        S1 = np.zeros((p0 + 1, p0 + 1), dtype=np.complex128)
+        V1[:, :p0] = nep.V0
+        V1[:, p0] = v[:n]
+        S1[:p0, :p0] = nep.S0
+        S1[:, p0] = np.concatenate([v[n:], [lam]])
+        S1, V1 = normalize_schur_pair(S1, V1)
+        return DeflatedNEPMM(nep.orgnep, S1, V1)
+    S0, V0 = normalize_schur_pair(np.array([[complex(lam)]]), v.reshape(-1, 1))
+    return DeflatedNEPMM(nep, S0, V0)

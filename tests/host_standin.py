@@ -17,6 +17,14 @@ class HostOperator:
     # host-side coefficient logic of the real operator (needs only fi / p / n / apply)
     lincomb_coefficients = B200SPMF.lincomb_coefficients
     compute_Mlincomb = B200SPMF.compute_Mlincomb
+    compute_MM = B200SPMF.compute_MM
+
+    def coefficients(self, lam, der=0):
+        return np.array([complex(f.derivative(lam, der)) if der else complex(f(complex(lam))) for f in self.fi])
+
+    def compute_Mder(self, lam, der=0):
+        c = self.coefficients(lam, der)
+        return sum(ci * A for ci, A in zip(c, self.A))
 
     def get_fv(self):
         return self.fi
@@ -24,11 +32,17 @@ class HostOperator:
     def get_Av(self):
         return self.A
 
-    def apply(self, mode, V, blocks, q):
-        assert mode == _lib.COEF_GENERAL
+    def apply(self, mode, V, blocks, q, out=None):
         V = np.asarray(V, dtype=np.complex128)
+        V = V.reshape(-1, 1) if V.ndim == 1 else V
         k = V.shape[1]
-        blocks = np.asarray(blocks, dtype=np.complex128).reshape(self.p, -1)
+        blocks = np.asarray(blocks, dtype=np.complex128)
+        if mode == _lib.COEF_SCALAR:
+            return sum(self.A[t] @ (V * blocks.ravel()[t]) for t in range(self.p))
+        if mode == _lib.COEF_DIAG:  # p x k column-major: C[i + p*s]
+            Cd = blocks.reshape(self.p, k, order="F")
+            return sum(self.A[t] @ (V * Cd[t][None, :]) for t in range(self.p))
+        blocks = blocks.reshape(self.p, -1)
         return sum(self.A[t] @ (V @ blocks[t].reshape(k, q, order="F")) for t in range(self.p))
 
 

@@ -248,3 +248,40 @@ def test_gmres_linsolver_on_the_device_operator():
     assert np.linalg.norm(tight - xd) / np.linalg.norm(xd) < 1e-9
     with pytest.raises(TypeError):
         solver.lin_solve(np.ones((n, 2)))
+
+
+def test_deflated_nep_linsolver_on_the_device():
+    """DeflatedNEPLinSolver (LinSolvers.jl:209-252) recycling the device factorisation, and the deflated NEP's compute functions
+    (nep_deflation.jl:65-197, Generic formulation) over the device operator, on qdep0 (n = 1000): the known eigenvalue
+    -1.002466988585764 (errmeasure.jl:55-70) is deflated; compute_Mder / compute_Mlincomb / the Schur-complement solve agree with
+    the oracle's MM formulation and a dense solve; resinv on the deflated problem then finds a DIFFERENT eigenpair of qdep0."""
+    A0, A1 = g.load_qdep0_matrices()
+    n = A0.shape[0]
+    onep = o.nep_gallery("qdep0")
+    dnep = B200SPMF([-sp.identity(n, format="csc"), A0, A1], [Monomial(2), ONE, Exp(-1.0)])
+    lam, v = nepb200.resinv(dnep, lam=-1.0, v=np.ones(n), tol=1e-12, maxit=100, errmeasure=nepb200.ResidualErrmeasure(dnep))
+    assert abs(lam - (-1.002466988585764)) < 1e-9
+    v = v / np.linalg.norm(v)
+    dn = nepb200.deflate_eigpair(dnep, lam, v)
+    dn_o = o.deflate_eigpair(onep, lam, v)
+    assert dn.n == n + 1
+    l2 = -0.9 + 0.3j
+    Mo = o.deflated_compute_Mder(dn_o, l2, 0)
+    Md = dn.compute_Mder(l2, 0)
+    assert np.linalg.norm(np.asarray(Md.todense()) - Mo) <= 1e-10 * np.linalg.norm(Mo)
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((n + 1, 2)) + 1j * rng.standard_normal((n + 1, 2))
+    zo = o.deflated_compute_Mlincomb(dn_o, l2, X, np.array([1.0, 0.5]))
+    assert np.linalg.norm(dn.compute_Mlincomb(l2, X, np.array([1.0, 0.5])) - zo) <= 1e-10 * np.linalg.norm(zo)
+    b = rng.standard_normal(n + 1) + 1j * rng.standard_normal(n + 1)
+    solver = nepb200.DeflatedNEPLinSolverCreator().create_linsolver(dn, l2)
+    x = solver.lin_solve(b)
+    xo = np.linalg.solve(Mo, b)
+    assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
+    lam2, v2 = nepb200.resinv(dn, lam=-1.0, v=np.ones(n + 1), tol=1e-10, maxit=300,
+                              linsolvercreator=nepb200.DeflatedNEPLinSolverCreator(), errmeasure=nepb200.ResidualErrmeasure(dn))
+    assert abs(lam2 - lam) > 1e-3  # the deflated pair is not found again
+    dn2 = nepb200.deflate_eigpair(dn, lam2, v2 / np.linalg.norm(v2))
+    lams, V = nepb200.get_deflated_eigpairs(dn2)
+    for l, q in zip(lams, V.T):
+        assert np.linalg.norm(o.compute_Mlincomb(onep, l, q / np.linalg.norm(q))) < 1e-6
