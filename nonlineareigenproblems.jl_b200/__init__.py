@@ -20,7 +20,8 @@ from .solvers import (contour_block_SS, block_ss_quadrature, block_ss_extract, c
                       LostOrthogonalityException)
 from .dense import (dgks, block_gemm, copy_cols, colnorms, solve_block, mlincomb_block, residual_errors,  # noqa: F401
                     tiar_device, iar_device, iar_chebyshev_device)
-from .nleigs import nleigs, nleigs_backslash, backslash_coefficients, DeviceLinSolverCache  # noqa: F401
+from .nleigs import (nleigs, nleigs_backslash, backslash_coefficients, DeviceLinSolverCache, nleigs_lowrank,  # noqa: F401
+                     lowrank_backslash, LowRankStructure)
 from .deflation import (DeflatedGenericNEP, deflate_eigpair, get_deflated_eigpairs, normalize_schur_pair,  # noqa: F401
                         DeflatedNEPLinSolver, DeflatedNEPLinSolverCreator)
 from . import rk_helper  # noqa: F401

@@ -329,3 +329,227 @@ def nleigs(nep: B200SPMF, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf
     for s in cache.solvers.values():
         _release(s)
     return lam[conv], X[:, conv], res[conv], details
+
+
+# ---------------------------------------------------------------------------------------------
+# low-rank branch: SumNEP(PEP, LowRankFactorizedNEP) as in the reference's gun variants R1 / R2 / S
+# ---------------------------------------------------------------------------------------------
+class LowRankStructure:
+    """What get_rk_nep attaches for `SumNEP(PEP, LowRankFactorizedNEP)` (rk_helper/rk_nep.jl:127-152): polynomial degree p, the
+    L factors of the q nonlinear terms side by side (n x r), UU = hcat(U...) and the term every column belongs to."""
+
+    def __init__(self, p, L, U):
+        import scipy.sparse as sp
+        self.p, self.q = int(p), len(L)
+        self.L = [sp.csr_matrix(x) for x in L]
+        self.Lcat = sp.hstack(self.L).tocsr()
+        self.UUt = sp.hstack([sp.csr_matrix(u) for u in U]).conj().T.tocsr()  # r x n
+        self.r = self.Lcat.shape[1]
+        self.iL = np.concatenate([np.full(x.shape[1], i) for i, x in enumerate(self.L)])
+
+    @classmethod
+    def from_terms(cls, p, nonlinear_matrices):
+        LU = [rk.low_rank_lu_factors(A) for A in nonlinear_matrices]
+        return cls(p, [x[0] for x in LU], [x[1] for x in LU])
+
+
+def lowrank_backslash(nep: B200SPMF, P: LowRankStructure, solve, wc, sigma, k, beta, N, xi, sgdd):
+    """`backslash` of method_nleigs.jl:399-518 with `P.is_low_rank`: after the p-th block the blocks of the continuation vector
+    have r entries (sum of the ranks) instead of n, so everything but the first p blocks is tiny and stays on the host; the
+    device does what is O(nnz) or worse -- the products with all A_i at once (`P.BBCC * block` weighted by a column of sgdd =
+    ONE fused SpMM in SCALAR mode with C_i = sgdd[i, .]) and the shifted solve.  0-based indices as in the oracle."""
+    n, p, r = nep.n, P.p, P.r
+    shift = sigma[k]
+    wc = np.asarray(wc, dtype=np.complex128)
+
+    def stacked(block, col):  # sum_i sgdd[i, col] A_i block
+        return nep.apply(_lib.COEF_SCALAR, block.reshape(n, 1), np.ascontiguousarray(sgdd[:, col]), 1)[:, 0]
+
+    Bw = np.zeros_like(wc)
+    Bw[:n] = -stacked(wc[(p - 1) * n:p * n], p) / beta[p]  # first block (:408-416)
+    i0b, i0e = 0, n
+    for ii in range(1, N + 1):  # other blocks (:418-435)
+        i1b, i1e = i0e, i0e + (n if ii < p else r)
+        if ii != p:
+            Bw[i1b:i1e] = wc[i0b:i0e] + beta[ii] / xi[ii - 1] * wc[i1b:i1e]
+        else:
+            Bw[i1b:i1e] = P.UUt @ wc[i0b:i0e] + beta[ii] / xi[ii - 1] * wc[i1b:i1e]
+        i0b, i0e = i1b, i1e
+    z = Bw.copy()  # z0 (:437-489)
+    i1b, i1e = n, (2 * n if p > 1 else n + r)
+    z[i1b:i1e] = z[i1b:i1e] / (beta[1] * (1 - shift / xi[0]))
+    for ii in range(1, N + 1):
+        i2b, i2e = i1e, i1e + (n if ii < p - 1 else r)
+        if ii < p:
+            z[:n] -= stacked(z[i1b:i1e], ii)
+        elif ii > p:
+            z[:n] -= P.Lcat @ (z[i1b:i1e] * sgdd[p + 1:, ii][P.iL])  # the LL / iLr loops (:463-470)
+        if ii < N:
+            mu = shift - sigma[ii]
+            nu = beta[ii + 1] * (1 - shift / xi[ii])
+            if ii != p - 1:
+                z[i2b:i2e] = z[i2b:i2e] / nu + mu / nu * z[i1b:i1e]
+            else:
+                z[i2b:i2e] = z[i2b:i2e] / nu + mu / nu * (P.UUt @ z[i1b:i1e])
+        i1b, i1e = i2b, i2e
+    w = np.zeros_like(wc)  # solve and substitutions (:491-515)
+    w[:n] = solve(shift, z[:n] / beta[0])
+    i0b, i0e = 0, n
+    for ii in range(1, N + 1):
+        i1b, i1e = i0e, i0e + (n if ii < p else r)
+        mu = shift - sigma[ii - 1]
+        nu = beta[ii] * (1 - shift / xi[ii - 1])
+        if ii != p:
+            w[i1b:i1e] = mu / nu * w[i0b:i0e] + Bw[i1b:i1e] / nu
+        else:
+            w[i1b:i1e] = mu / nu * (P.UUt @ w[i0b:i0e]) + Bw[i1b:i1e] / nu
+        i0b, i0e = i1b, i1e
+    return w
+
+
+def nleigs_lowrank(nep: B200SPMF, lowrank: LowRankStructure, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf,), maxdgr=100,
+                   minit=20, maxit=200, tol=1e-10, tollin=None, v=None, errmeasure=None, isfunm=True, static=False, leja=1, nodes=(),
+                   reusefact=1, check_error_every=5, umfpack_refinements=0, linsolvercache=None):
+    """nleigs (method_nleigs.jl:60-377) for `SumNEP(PEP, LowRankFactorizedNEP)`: `nep` is the device operator with the terms in
+    the order (PEP coefficients 0..p, nonlinear terms), `lowrank` their low-rank structure.  The rational Krylov vectors have
+    p n + (N - p + 1) r entries (gun: 9956 + 84 per extra block instead of 9956 per block), so the basis, DGKS and the small
+    recurrences live on the host; the device does the products with all A_i and the cached shifted solves.
+    Returns (lam, X, res, details)."""
+    from .solvers import dgks_host
+    import scipy.linalg as sla
+    P = lowrank
+    Sigma = np.asarray(Sigma, dtype=np.complex128)
+    Xi = np.asarray(Xi, dtype=np.float64)
+    n, p_poly, r = nep.n, P.p, P.r
+    tollin = max(tol / 10, 100 * np.finfo(float).eps) if tollin is None else tollin
+    v = np.random.default_rng(0).standard_normal(n) if v is None else v
+    v = np.asarray(v, dtype=np.complex128)
+    errmeasure = errmeasure or ResidualErrmeasure(nep)
+    host_err = callable(errmeasure) and not hasattr(errmeasure, "estimate_error")
+    nodes = np.asarray(nodes, dtype=np.complex128)
+    if leja == 0:  # nodes, poles, scalings (:120-146)
+        if len(nodes) == 0:
+            raise ValueError("Interpolation nodes must be provided via 'nodes' when no Leja-Bagby points ('leja' == 0) are used.")
+        gamma, _ = rk.discretizepolygon(Sigma)
+        max_count = maxit + maxdgr + 2 if static else max(maxit, maxdgr) + 2
+        sigma = np.tile(nodes, -(-max_count // len(nodes)))
+        _, xi, beta = rk.lejabagby(sigma[:maxdgr + 2], Xi, gamma, maxdgr + 2, True, p_poly)
+    elif leja == 1:
+        if len(nodes) == 0:
+            gamma, nodes = rk.discretizepolygon(Sigma, True)
+        else:
+            gamma, _ = rk.discretizepolygon(Sigma)
+        nodes = np.tile(nodes, -(-(maxit + 1) // len(nodes)))
+        sigma, xi, beta = rk.lejabagby(gamma, Xi, gamma, maxdgr + 2, False, p_poly)
+    else:
+        gamma, _ = rk.discretizepolygon(Sigma)
+        max_count = maxit + maxdgr + 2 if static else max(maxit, maxdgr) + 2
+        sigma, xi, beta = rk.lejabagby(gamma, Xi, gamma, max_count, False, p_poly)
+    sigma = np.array(sigma, dtype=np.complex128)
+    xi = np.array(xi, dtype=np.float64)
+    xi[maxdgr + 1] = np.nan
+    head = slice(0, maxdgr + 2)
+    sgdd = rk.scgendivdiffs(sigma[head], xi[head], beta[head], maxdgr, isfunm, nep.get_fv())
+    nrmD = [float(np.abs(sgdd[:, 0]).max())]
+    if not np.isfinite(nrmD[0]):
+        raise ValueError("The generalized divided differences must be finite.")
+    kmax = maxit + maxdgr if static else maxit
+    cache = linsolvercache or DeviceLinSolverCache(nep, umfpack_refinements)  # (`linsolvercache`: tests inject a host stand-in)
+
+    def solve(shift, y, add_to_cache):
+        s = cache.get(shift, add_to_cache)
+        x = s.lin_solve(y)
+        if cache.solvers.get(complex(shift)) is not s:
+            _release(s)
+        return x
+
+    launches0 = lib.nepb_launch_count()
+    v = solve(sigma[0], v / np.linalg.norm(v), reusefact == 2)
+    V = np.zeros((p_poly * n + (kmax + 2) * r + n, kmax + 1), dtype=np.complex128)
+    V[:n, 0] = v / np.linalg.norm(v)
+    H = np.zeros((kmax + 1, kmax), dtype=np.complex128)
+    K = np.zeros((kmax + 1, kmax), dtype=np.complex128)
+    expand, kconv = True, np.iinfo(np.int64).max // 2
+    kn, l, N, nbconv, nblamin = n, 0, 0, 0, 0
+    lam = np.zeros(0, dtype=np.complex128)
+    X = np.zeros((n, 0), dtype=np.complex128)
+    res = np.zeros(0)
+    conv = np.zeros(0, dtype=bool)
+    nfact = 0
+    k = 1
+    while k <= kmax:
+        if expand:
+            kn += n if k < p_poly else r  # (:205-211)
+            N += 1
+            nrmD.append(float(np.abs(sgdd[:, k]).max()))
+            if not np.isfinite(nrmD[k]):
+                raise ValueError("The generalized divided differences must be finite.")
+            if n > 1 and k >= 5 and k < kconv:
+                if sum(nrmD[k - 4:k + 1]) < 5 * tollin:
+                    kconv = k - 1
+                    if static:
+                        kmax = maxit + kconv
+                    expand = False
+                    if leja == 1:
+                        if len(sigma) < kmax + 1:
+                            sigma = np.concatenate([sigma, np.zeros(kmax + 1 - len(sigma), dtype=np.complex128)])
+                        sigma[k:kmax + 1] = nodes[:kmax - k + 1]
+                    xi, beta, nrmD = xi[:k], beta[:k], nrmD[:k]
+                    if static:
+                        kn -= n if k < p_poly else r
+                    N -= 1
+                elif k == maxdgr + 1:
+                    kconv = k
+                    expand = False
+                    if leja == 1:
+                        if len(sigma) < kmax + 1:
+                            sigma = np.concatenate([sigma, np.zeros(kmax + 1 - len(sigma), dtype=np.complex128)])
+                        sigma[k:kmax + 1] = nodes[:kmax - k + 1]
+                    N -= 1
+                    warnings.warn("NLEIGS: Linearization not converged after %d iterations" % maxdgr)
+        l = k - N if static else k
+        if not static or (static and not expand):
+            if kn > V.shape[0] or l + 1 > V.shape[1]:
+                W = np.zeros((max(kn, V.shape[0]), max(l + 1, V.shape[1])), dtype=np.complex128)
+                W[:V.shape[0], :V.shape[1]] = V
+                V = W
+            t = np.zeros(l, dtype=np.complex128)
+            t[l - 1] = 1
+            add_to_cache = ((not expand or k > kconv) and reusefact == 1) or reusefact == 2
+            w = lowrank_backslash(nep, P, lambda s, y: solve(s, y, add_to_cache), V[:kn, l - 1].copy(), sigma, k, beta, N, xi, sgdd)
+            h = np.zeros(l, dtype=np.complex128)
+            H[l, l - 1] = dgks_host(V[:kn, :l], w, h)
+            H[:l, l - 1] = h
+            K[:l, l - 1] = h * sigma[k] + t
+            K[l, l - 1] = H[l, l - 1] * sigma[k]
+            V[:kn, l] = w
+        check = ((not expand and k >= N + minit and (k - (N + minit)) % check_error_every == 0) or
+                 (k >= kconv + minit and (k - (kconv + minit)) % check_error_every == 0) or k == kmax)
+        if check:
+            lambda_, S = sla.eig(K[:l, :l], H[:l, :l])
+            lamin = rk.in_sigma(lambda_, Sigma, tol)
+            ilam = np.nonzero(lamin)[0]
+            lam = lambda_[ilam]
+            nblamin = int(np.sum(lamin))
+            for i in ilam:
+                S[:, i] = S[:, i] / np.linalg.norm(H[:l + 1, :l] @ S[:, i])
+            X = V[:n, :l + 1] @ (H[:l + 1, :l] @ S[:, ilam])
+            X = X / np.linalg.norm(X, axis=0)[None, :] if X.shape[1] else X
+            if len(lam) == 0:
+                res = np.zeros(0)
+            elif host_err:
+                res = np.array([errmeasure(lam[i], X[:, i]) for i in range(len(lam))], dtype=float)
+            else:
+                res = np.asarray(errmeasure.estimate_errors(lam, X) if hasattr(errmeasure, "estimate_errors")
+                                 else [errmeasure.estimate_error(lam[i], X[:, i]) for i in range(len(lam))], dtype=float)
+            conv = np.abs(res) < tol
+            nbconv = int(np.sum(conv)) if len(conv) else 0
+        if ((not expand and k >= N + minit) or k >= kconv + minit) and nblamin == nbconv:
+            break
+        k += 1
+    details = {"sigma": sigma[:min(k, len(sigma))], "xi": xi, "beta": beta, "nrmD": nrmD, "kconv": kconv, "iterations": min(k, kmax),
+               "factorizations": len(cache.solvers), "N": N, "l": l, "rows": kn, "gpu_launches": int(lib.nepb_launch_count() - launches0),
+               "lam_all": lam, "res_all": res}
+    for s in cache.solvers.values():
+        _release(s)
+    return lam[conv], X[:, conv], res[conv], details

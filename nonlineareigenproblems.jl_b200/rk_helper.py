@@ -210,3 +210,24 @@ def rk_structure(nep, source=None):
     if src is None and all(isinstance(f, Monomial) and f.d == i and f.c == 1.0 for i, f in enumerate(nep.get_fv())):
         return nterms - 1, 0  # an operator built directly from monomials is a PEP
     return -1, nterms
+
+
+def low_rank_lu_factors(A):
+    """low_rank_lu_factors + compactlu (rk_helper/rk_nep.jl:66-95): LU of the bounding box of the nonzeros of A with the trivial
+    columns dropped, embedded back: A = L @ U.T with L (n x r), U (n x r) sparse.  As in the reference the row permutation of the
+    dense LU is not carried along, so a factorisation that needs row exchanges is rejected."""
+    import scipy.linalg as sl
+    import scipy.sparse as sp
+    A = sp.coo_matrix(A)
+    n = A.shape[0]
+    r0, r1, c0, c1 = A.row.min(), A.row.max(), A.col.min(), A.col.max()
+    B = A.tocsr()[r0:r1 + 1, c0:c1 + 1].toarray()
+    Pm, Lf, Uf = sl.lu(B)
+    if not np.allclose(Pm, np.eye(len(B))):
+        raise ValueError("low-rank LU factors with row exchanges are not supported (rk_nep.jl:80-88)")
+    sel = np.array([(np.count_nonzero(Lf[i:, i]) > 1) or (np.count_nonzero(Uf[i, i:]) > 0) for i in range(len(B))])
+    L = sp.lil_matrix((n, int(sel.sum())))
+    L[r0:r1 + 1, :] = Lf[:, sel]
+    U = sp.lil_matrix((A.shape[1], int(sel.sum())))
+    U[c0:c1 + 1, :] = Uf[sel, :].T
+    return sp.csr_matrix(L), sp.csr_matrix(U)

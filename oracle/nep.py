@@ -573,3 +573,39 @@ def deflate_eigpair(nep, lam, v):
         return DeflatedNEPMM(nep.orgnep, S1, V1)
     S0, V0 = normalize_schur_pair(np.array([[complex(lam)]]), v.reshape(-1, 1))
     return DeflatedNEPMM(nep, S0, V0)
+
+
+# --------------------------------------------------------------------------------------------
+# LowRankFactorizedNEP (src/low_rank_nep.jl:24-43) and the low-rank LU factors nleigs works with
+# (src/rk_helper/rk_nep.jl:43-98: LowRankMatrixAndFunction, low_rank_lu_factors, compactlu)
+# --------------------------------------------------------------------------------------------
+def low_rank_lu_factors(A):
+    """rk_nep.jl:66-89: LU of the bounding box of the nonzeros, trivial columns dropped; A = L U^T (the reference ignores the
+    row permutation of `lu`; as there, the factors are only valid when no row exchange happens -- asserted)."""
+    import scipy.linalg as L_
+    A = sp.coo_matrix(A)
+    n = A.shape[0]
+    r0, r1, c0, c1 = A.row.min(), A.row.max(), A.col.min(), A.col.max()
+    B = A.tocsr()[r0:r1 + 1, c0:c1 + 1].toarray()
+    Pm, Lf, Uf = L_.lu(B)
+    assert np.allclose(Pm, np.eye(len(B))), "low_rank_lu_factors: row exchanges are not supported (rk_nep.jl:80-88)"
+    m = len(B)
+    sel = np.array([(np.count_nonzero(Lf[i:, i]) > 1) or (np.count_nonzero(Uf[i, i:]) > 0) for i in range(m)])  # compactlu (:91-95)
+    Lca = sp.lil_matrix((n, int(sel.sum())))
+    Lca[r0:r1 + 1, :] = Lf[:, sel]
+    Uca = sp.lil_matrix((int(sel.sum()), A.shape[1]))
+    Uca[:, c0:c1 + 1] = Uf[sel, :]
+    return sp.csc_matrix(Lca), sp.csc_matrix(Uca.T)
+
+
+class LowRankFactorizedNEP(SPMF_NEP):
+    """An SPMF whose terms come with factors A_i = L_i U_i^T; r = sum of the ranks (low_rank_nep.jl:24-29).  All compute
+    functions are those of the underlying SPMF (:45-60)."""
+
+    def __init__(self, A, fi, L=None, U=None):
+        super().__init__(A, fi)
+        if L is None:
+            LU = [low_rank_lu_factors(a) for a in A]
+            L, U = [x[0] for x in LU], [x[1] for x in LU]
+        self.L, self.U = list(L), list(U)
+        self.r = int(sum(u.shape[1] for u in self.U))

@@ -262,15 +262,26 @@ def scgendivdiffs(sigma, xi, beta, maxdgr, isfunm, pff):
 
 
 class RKNEP:
-    """get_rk_nep (rk_helper/rk_nep.jl:101-153) without the low-rank branch: spmf flag, polynomial degree p, number of
-    nonlinear terms q."""
+    """get_rk_nep (rk_helper/rk_nep.jl:101-153): spmf flag, polynomial degree p, number of nonlinear terms q and, for a
+    PEP + LowRankFactorizedNEP sum, the low-rank data (L factors side by side, UU = hcat(U...), iL = term of every column)."""
 
     def __init__(self, nep):
         self.nep = nep
+        self.n = nep.n
         self.spmf = isinstance(nep, (o.SPMF_NEP, o.PEP, o.DEP, o.SumNEP, o.DerSPMF))
         self.p, self.q = 0, 0
+        self.is_low_rank, self.r = False, 0
         self.Av = o.get_Av(nep) if self.spmf else []
         if not self.spmf:
+            return
+        if (isinstance(nep, o.SumNEP) and isinstance(nep.nep1, o.PEP) and isinstance(nep.nep2, o.LowRankFactorizedNEP)
+                and len(o.get_Av(nep.nep2)) > 0):
+            self.p, self.q = len(o.get_Av(nep.nep1)) - 1, len(o.get_Av(nep.nep2))
+            self.is_low_rank, self.r = True, nep.nep2.r
+            self.L = nep.nep2.L
+            self.Lcat = sp.hstack(self.L).tocsr()          # n x r
+            self.UU = sp.hstack(nep.nep2.U).tocsc()        # n x r
+            self.iL = np.concatenate([np.full(L.shape[1], i) for i, L in enumerate(self.L)])
             return
         if isinstance(nep, o.PEP):
             self.p, self.q = len(self.Av) - 1, 0
@@ -301,12 +312,83 @@ class LinSolverCache:
 
 
 def _constructD(nb, P, sgdd):
-    """method_nleigs.jl:380-396 (full-rank branch)."""
+    """method_nleigs.jl:380-396."""
+    if P.is_low_rank and nb > P.p:
+        return sp.hstack([sgdd[P.p + 1 + ii, nb] * P.L[ii] for ii in range(P.q)]).tocsr()
     D = None
     for ii, A in enumerate(P.Av):
         T = sgdd[ii, nb] * A
         D = T if D is None else D + T
     return D
+
+
+def backslash_ref(wc, P, solve, computeD, sigma, k, D, beta, N, xi, sgdd):
+    """The complete `backslash` of method_nleigs.jl:399-518 including the low-rank branches (`P.is_low_rank`): after the p-th
+    block the blocks of the continuation vector have length r (sum of the ranks) instead of n, the step from block p to p + 1
+    goes through UU^T, and the nonlinear terms enter z0 through the L factors (:463-471).  0-based: sigma[k] = the reference's
+    sigma[k+1], beta[ii] = beta[ii+1], xi[ii-1] = xi[ii], D[ii] = D[ii+1], sgdd[:, ii] = sgdd[:, ii+1]."""
+    n, p, lr = P.n, P.p, P.is_low_rank
+    r = P.r if lr else 0
+    shift = sigma[k]
+    wc = np.asarray(wc, dtype=np.complex128)
+    use_D = (not P.spmf) or computeD
+    BBCC = None if use_D else sp.vstack(P.Av).tocsr()
+    UUt = P.UU.conj().T.tocsr() if lr else None
+    Bw = np.zeros_like(wc)
+    if lr:  # first block (:408-416)
+        blk = wc[(p - 1) * n:p * n]
+        if use_D:
+            Bw[:n] = -(D[p] @ blk) / beta[p]
+        else:
+            Bw[:n] = -((BBCC @ blk).reshape(-1, n).T * sgdd[:, p][None, :]).sum(axis=1) / beta[p]
+    i0b, i0e = 0, n
+    for ii in range(1, N + 1):  # other blocks (:418-435)
+        i1b = i0e
+        i1e = i0e + (n if (not lr or ii < p) else r)
+        if not lr or ii != p:
+            Bw[i1b:i1e] = wc[i0b:i0e] + beta[ii] / xi[ii - 1] * wc[i1b:i1e]
+        else:
+            Bw[i1b:i1e] = UUt @ wc[i0b:i0e] + beta[ii] / xi[ii - 1] * wc[i1b:i1e]
+        i0b, i0e = i1b, i1e
+    z = Bw.copy()  # construction of z0 (:437-489)
+    i1b = n
+    i1e = 2 * n if (not lr or p > 1) else n + r
+    nu = beta[1] * (1 - shift / xi[0])
+    z[i1b:i1e] = z[i1b:i1e] / nu
+    for ii in range(1, N + 1):
+        i2b = i1e
+        i2e = i1e + (n if (not lr or ii < p - 1) else r)
+        if use_D:
+            if not lr or ii != p:
+                z[:n] -= D[ii] @ z[i1b:i1e]
+        else:
+            if not lr or ii < p:
+                z[:n] -= ((BBCC @ z[i1b:i1e]).reshape(-1, n).T * sgdd[:, ii][None, :]).sum(axis=1)
+            elif ii > p:
+                dd = sgdd[p + 1:, ii]
+                z[:n] -= P.Lcat @ (z[i1b:i1e] * dd[P.iL])  # the LL / iLr loops of :463-470
+        if ii < N:
+            mu = shift - sigma[ii]
+            nu = beta[ii + 1] * (1 - shift / xi[ii])
+            if not lr or ii != p - 1:
+                z[i2b:i2e] = z[i2b:i2e] / nu + mu / nu * z[i1b:i1e]
+            else:
+                z[i2b:i2e] = z[i2b:i2e] / nu + mu / nu * (UUt @ z[i1b:i1e])
+        i1b, i1e = i2b, i2e
+    w = np.zeros_like(wc)  # solve and substitutions (:491-515)
+    w[:n] = solve(shift, z[:n] / beta[0])
+    i0b, i0e = 0, n
+    for ii in range(1, N + 1):
+        i1b = i0e
+        i1e = i0e + (n if (not lr or ii < p) else r)
+        mu = shift - sigma[ii - 1]
+        nu = beta[ii] * (1 - shift / xi[ii - 1])
+        if not lr or ii != p:
+            w[i1b:i1e] = mu / nu * w[i0b:i0e] + Bw[i1b:i1e] / nu
+        else:
+            w[i1b:i1e] = mu / nu * (UUt @ w[i0b:i0e]) + Bw[i1b:i1e] / nu
+        i0b, i0e = i1b, i1e
+    return w
 
 
 def backslash_generic(wc, n, Dlist, solve, sigma, k, beta, N, xi, add_to_cache):
@@ -429,7 +511,7 @@ def nleigs(nep, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf,), maxdgr
     k = 1
     while k <= kmax:
         if expand:
-            kn += n
+            kn += n if (not P.is_low_rank or k < P.p) else P.r  # (:205-211)
             if P.spmf and computeD:
                 D.append(_constructD(k, P, sgdd))
             N += 1
@@ -453,7 +535,7 @@ def nleigs(nep, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf,), maxdgr
                         D = D[:k]
                     xi, beta, nrmD = xi[:k], beta[:k], nrmD[:k]
                     if static:
-                        kn -= n
+                        kn -= n if (not P.is_low_rank or k < P.p) else P.r
                     N -= 1
                 elif k == maxdgr + 1:
                     kconv = k
@@ -472,7 +554,9 @@ def nleigs(nep, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf,), maxdgr
             t[l - 1] = 1
             wc = V[:kn, l - 1].copy()
             add_to_cache = ((not expand or k > kconv) and reusefact == 1) or reusefact == 2
-            if P.spmf and not computeD:
+            if P.is_low_rank:
+                w = backslash_ref(wc, P, lambda s, y: cache.solve(s, y, add_to_cache), computeD, sigma, k, D, beta, N, xi, sgdd)
+            elif P.spmf and not computeD:
                 if backslash is not None:
                     w = backslash(wc, sigma, k, beta, N, xi, sgdd, add_to_cache)
                 else:

@@ -206,3 +206,35 @@ def test_nleigs_gun_naive_reference_eigenvalue():
         gold = json.load(f)["naive"]
     assert det["kconv"] == gold["kconv"] and det["iterations"] == gold["iterations"]
     assert abs(lam[0] - complex(*gold["lam"][0])) < 1e-10 * abs(lam[0])
+
+
+def test_lowrank_branch_matches_the_reference_counts_and_the_fullrank_run():
+    """The low-rank branches of nleigs (method_nleigs.jl:380-518 with `P.is_low_rank`, rk_helper/rk_nep.jl:43-152) on
+    SumNEP(PEP([K, M]), LowRankFactorizedNEP([c1, c2])) as built in test/rk_helper/gun_test_utils.jl:36-43: the golden file holds
+    the oracle runs of the variants R1 / R2 / S, for which the reference asserts 21 eigenvalues each
+    (test/nleigs/nleigs_gun_variant_{r1,r2,s}.jl); the eigenvalues equal those of the full-rank runs.  Variant R1 is re-run here
+    (~20 s), and `backslash_ref` is checked against the full-rank `backslash` on a full-rank operator."""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    from make_nleigs_lowrank_golden import gun_lowrank_nep, run
+    low = json.load(open(os.path.join(here, "golden", "nleigs_gun_lowrank.json")))
+    full = json.load(open(os.path.join(here, "golden", "nleigs_gun.json")))
+    for var in ("R1", "R2", "S"):
+        assert low[var]["count"] == 21 and max(low[var]["res"]) < 1e-10
+    for var in ("R2", "S"):
+        a = np.array([complex(*x) for x in low[var]["lam"]])
+        b = np.array([complex(*x) for x in full[var]["lam"]])
+        assert max(np.min(np.abs(a - x)) / abs(x) for x in b) < 1e-7
+    nep, _ = gun_lowrank_nep()
+    P = onl.RKNEP(nep)
+    assert P.is_low_rank and (P.p, P.q, P.r) == (1, 2, 84)  # ranks 19 + 65 of W1, W2
+    for A, L, U in zip(o.get_Av(nep.nep2), nep.nep2.L, nep.nep2.U):
+        assert abs(L @ U.T - A).max() < 1e-14
+    r1 = run("R1")
+    assert r1["count"] == 21
+    a = np.array([complex(*x) for x in r1["lam"]])
+    b = np.array([complex(*x) for x in low["R1"]["lam"]])
+    assert np.max(np.abs(a - b) / np.abs(b)) < 1e-9
