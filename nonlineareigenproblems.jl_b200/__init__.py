@@ -11,7 +11,7 @@ The directory name contains a dot, so it is imported under the alias `nepb200` (
 from . import _lib  # noqa: F401  (raises ImportError when libnepb200.so is missing)
 from ._lib import NepbError, SingularException, device_count, LIB_PATH  # noqa: F401
 from .functions import ScalarFunction, Monomial, Exp, PowShift, Callable, ONE, IDENTITY  # noqa: F401
-from .neptypes import SPMF_NEP, PEP, DEP, SumNEP, B200SPMF, Block, B200ProjSPMF, create_proj_NEP  # noqa: F401
+from .neptypes import SPMF_NEP, PEP, DEP, SumNEP, LowRankFactorizedNEP, B200SPMF, Block, B200ProjSPMF, create_proj_NEP  # noqa: F401
 from .linsolve import (B200LU, B200FactorizeLinSolver, B200BackslashLinSolver, B200LinSolverCreator, matching,  # noqa: F401
                        B200BackslashLinSolverCreator, DefaultLinSolverCreator, LinSolverCache, LinSolver, LinSolverCreator,
                        symbolic_info, symbolic_get, analyse_pattern, GMRESLinSolver, GMRESLinSolverCreator, gmres)

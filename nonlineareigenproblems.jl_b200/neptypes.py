@@ -75,6 +75,27 @@ class SumNEP(SPMF_NEP):
         self.nep1, self.nep2 = nep1, nep2
 
 
+class LowRankFactorizedNEP(SPMF_NEP):
+    """SPMF whose terms carry factors A_i = L_i U_i^T, r = sum of the ranks (low_rank_nep.jl:24-43).  Built from the factors
+    (`LowRankFactorizedNEP(L, U, f)`) or from the matrices, whose factors nleigs then derives (rk_nep.jl:66-95).  All compute
+    functions are those of the SPMF (:45-60); only nleigs looks at the factors."""
+
+    def __init__(self, A, fi, L=None, U=None):
+        super().__init__(A, fi)
+        if L is None:
+            from .rk_helper import low_rank_lu_factors
+            LU = [low_rank_lu_factors(a) for a in A]
+            L, U = [x[0] for x in LU], [x[1] for x in LU]
+        self.L, self.U = list(L), list(U)
+        self.r = int(sum(u.shape[1] for u in self.U))
+
+    @classmethod
+    def from_factors(cls, L, U, fi):
+        L = [sp.csc_matrix(x) for x in L]
+        U = [sp.csc_matrix(x) for x in U]
+        return cls([sp.csc_matrix(l @ u.conj().T) for l, u in zip(L, U)], fi, L, U)
+
+
 # ---------------------------------------------------------------------------------------------
 # device-resident dense block (n x k ComplexF64, row-major in HBM)
 # ---------------------------------------------------------------------------------------------

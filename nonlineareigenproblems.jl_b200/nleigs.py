@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import lib, check, ptr
-from .neptypes import B200SPMF, Block
+from .neptypes import B200SPMF, Block, SumNEP, PEP, LowRankFactorizedNEP
 from .dense import block_gemm, solve_block
 from .linsolve import B200FactorizeLinSolver
 
@@ -154,6 +154,12 @@ def nleigs(nep: B200SPMF, Sigma=(-1.0 - 1j, -1 + 1j, 1 + 1j, 1 - 1j), Xi=(np.inf
     Ritz vectors and residuals of all candidates in one product each.  `errmeasure`: None = ResidualErrmeasure
     (the reference default), a device error measure, or a host callable (lam, x) -> float as in the reference's gun tests.
     Returns (lam, X, res, details)."""
+    src = getattr(nep, "source", None)
+    if (poly_degree is None and isinstance(src, SumNEP) and isinstance(src.nep1, PEP) and isinstance(src.nep2, LowRankFactorizedNEP)
+            and len(src.nep2.get_Av()) > 0):  # get_rk_nep's low-rank case (rk_helper/rk_nep.jl:127-152)
+        return nleigs_lowrank(nep, LowRankStructure(len(src.nep1.get_Av()) - 1, src.nep2.L, src.nep2.U), Sigma, Xi, maxdgr, minit,
+                              maxit, tol, tollin, v, errmeasure, isfunm, static, leja, nodes, reusefact, check_error_every,
+                              umfpack_refinements)
     Sigma = np.asarray(Sigma, dtype=np.complex128)
     Xi = np.asarray(Xi, dtype=np.float64)
     n = nep.n

@@ -162,3 +162,31 @@ def test_nleigs_stencil_pep_device_matches_oracle():
         assert np.min(np.abs(lo - x)) <= 1e-9 * max(1.0, abs(x))
     for i in range(len(ld)):
         assert np.linalg.norm(o.compute_Mlincomb(onep, ld[i], Xd[:, i])) / np.linalg.norm(Xd[:, i]) < 1e-9
+
+
+@pytest.mark.parametrize("variant", ["R1", "R2", "S"])
+def test_nleigs_gun_lowrank_device(variant):
+    """test/nleigs/nleigs_gun_variant_{r1,r2,s}.jl as the reference runs them: SumNEP(PEP([K, -M]), LowRankFactorizedNEP([W1, W2]))
+    (gun_test_utils.jl:36-43), so `nleigs` takes the low-rank branches of backslash (method_nleigs.jl:408-416,430,463-471,480,510).
+    21 eigenvalues each (the reference's literal), equal to the oracle's golden runs; products with the A_i and the shifted
+    solves on the device."""
+    K, M, W1, W2 = g.load_gun_matrices()
+    low = nepb200.LowRankFactorizedNEP([W1, W2], [PowShift(0.5, 0.0, 1j), PowShift(0.5, 108.8774 ** 2, 1j)])
+    dnep = B200SPMF.from_nep(nepb200.SumNEP(nepb200.PEP([K, -M]), low))
+    assert low.r == 84
+    Sigma, Xi, nodes = mg.gun_setup()
+    v = mg.gun_start_vector(dnep.n)
+    funres = mg.gun_residual(K, -M, W1, W2)
+    if variant == "R1":
+        lam, X, res, det = nepb200.nleigs(dnep, Sigma, Xi=Xi, maxit=100, v=v, leja=0, nodes=nodes, reusefact=2, errmeasure=funres)
+    elif variant == "R2":
+        lam, X, res, det = nepb200.nleigs(dnep, Sigma, Xi=Xi, minit=60, maxit=100, v=v, nodes=nodes, errmeasure=funres)
+    else:
+        lam, X, res, det = nepb200.nleigs(dnep, Sigma, Xi=Xi, minit=70, maxit=100, v=v, nodes=nodes, static=True, errmeasure=funres)
+    with open(os.path.join(os.path.dirname(__file__), "golden", "nleigs_gun_lowrank.json")) as f:
+        gold = json.load(f)[variant]
+    assert gold["count"] == 21 and len(lam) == 21
+    _match(lam, gold["lam"], 1e-8)
+    assert det["kconv"] == gold["kconv"] and det["N"] == gold["N"]
+    assert det["rows"] == dnep.n + det["N"] * 84 and det["gpu_launches"] > 0
+    assert np.all(res < 1e-10)
