@@ -363,6 +363,8 @@ def compute_Mlincomb(nep, lam, V, a=None, startder=None):
         V = np.concatenate([np.zeros((nep.n, startder), dtype=Vm.dtype), Vm], axis=1)
         return compute_Mlincomb(nep, lam, V, a)
     a = None if a is None else np.array(a, copy=True)
+    if hasattr(nep, "native_Mlincomb"):  # a NEP type with its own method, e.g. WEP_FD (Waveguide.jl:324-379, oracle/wep.py)
+        return nep.native_Mlincomb(lam, V, a)
     if isinstance(nep, SumNEP):
         # generic a handling (NEPCore.jl:113-125) then delegation (NEPTypes.jl:889-890)
         if a is not None and not np.all(a == 1):
