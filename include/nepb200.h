@@ -217,6 +217,31 @@ int nepb_comm_destroy(void);
 int nepb_comm_info(int* nranks, int* rank, int* nccl_version);
 int nepb_comm_allreduce_sum_dev(void* dev_ptr, int64_t count /* doubles */);
 
+/* ---- (f)3: WEP-native path -- the waveguide eigenvalue problem in its own format ------------------------------
+ * Replaces, for `WEP_FD` (src/gallery_extra/waveguide/Waveguide.jl:203-240), the matrix-free methods
+ *   compute_Mlincomb(nep::WEP_FD, lambda, V, a)      Waveguide.jl:324-379
+ *   *(M::SchurMatVec, v)                             Waveguide.jl:393-402
+ *   Pinv(nep, lambda, x)                             Waveguide.jl:160-163
+ * n = nx*nz + 2*nz; the interior unknowns are vec(X), X nz x nx (index z + nz*x), followed by the 2 nz boundary unknowns.
+ * K_scaled = K - mean(K) (nz x nx complex, column-major), bb = the reference's bb (nz complex).  Scalar functions stay
+ * on the host: the caller passes the Gegenbauer derivative table of sqrt_derivative (Waveguide.jl:574-616) as `coef`. */
+typedef struct nepb_wep nepb_wep;
+int nepb_wep_create(int nx, int nz, double hx, double hz, const double* K_scaled, const double* k_bar /* complex */,
+                    const double* bb, nepb_wep** out);
+int nepb_wep_destroy(nepb_wep* h);
+int nepb_wep_info(const nepb_wep* h, int* nx, int* nz, int64_t* n);
+/* Z[:, zcol] = sum_j a_j M^{(j)}(lambda) V[:, vcol0 + j], j = 0..na-1.  coef: 2 nz x na complex, ROW-major,
+ * coef[m, j] = a_j * (D[m, j] + (j == 0 ? d0 : 0)) with D as in Waveguide.jl:351-361. */
+int nepb_wep_mlincomb_block(const nepb_wep* h, const double* lambda, const nepb_block* V, int vcol0, int na, const double* a,
+                            const double* coef, nepb_block* Z, int zcol);
+/* y = [R(coef[0:nz] .* Rinv(x[0:nz])); R(coef[nz:2nz] .* Rinv(x[nz:2nz]))]; coef = 1 ./ [sM; sP] gives Pinv */
+int nepb_wep_pinv(const nepb_wep* h, const double* coef, const double* x, double* y);
+/* Y[:, ycol] = (A(lambda) X + X B + K .* X) - C1 Pinv(lambda, C2T x) for blocks with nx*nz rows; sinv = 1 ./ [sM; sP] */
+int nepb_wep_schur_matvec_block(const nepb_wep* h, const double* lambda, const double* sinv, const nepb_block* X, int xcol,
+                                nepb_block* Y, int ycol);
+/* algorithmic HBM bytes of one nepb_wep_mlincomb_block call */
+int64_t nepb_wep_mlincomb_bytes(const nepb_wep* h, int na);
+
 /* ---- deterministic synthetic data (bench / tests): Middle-Square-Weyl stream ------------------- */
 /* state = {x_lo,x_hi,w_lo,w_hi,s_lo,s_hi}; fills out[count] with uniform doubles in [0,1) exactly as
  * gen_rng_float of src/gallery_extra/basic_random_examples.jl:86-95 and advances the state. */

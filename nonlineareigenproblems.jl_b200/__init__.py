@@ -24,4 +24,6 @@ from .nleigs import (nleigs, nleigs_backslash, backslash_coefficients, DeviceLin
                      lowrank_backslash, LowRankStructure)
 from .deflation import (DeflatedGenericNEP, deflate_eigpair, get_deflated_eigpairs, normalize_schur_pair,  # noqa: F401
                         DeflatedNEPLinSolver, DeflatedNEPLinSolverCreator)
+from .wep import (WEP_FD, nep_gallery_WEP, WEPLinSolverCreator, WEPFactorizedLinSolver, WEPBackslashLinSolver,  # noqa: F401
+                  WEPGMRESLinSolver, SchurMatVec, construct_WEP_schur_complement, SqrtQuadratic)
 from . import rk_helper  # noqa: F401

@@ -110,6 +110,13 @@ SIGNATURES = {
     "nepb_iar_expand": (c_int, [vp, c_int, c_i64, c_int, vp, c_int, c_int]),
     "nepb_iar_pack": (c_int, [vp, c_int, c_int, c_i64, vp, c_int]),
     "nepb_block_colnorms": (c_int, [vp, c_int, c_int, c_i64, vp]),
+    "nepb_wep_create": (c_int, [c_int, c_int, c_dbl, c_dbl, vp, vp, vp, P(vp)]),
+    "nepb_wep_destroy": (c_int, [vp]),
+    "nepb_wep_info": (c_int, [vp, P(c_int), P(c_int), P(c_i64)]),
+    "nepb_wep_mlincomb_block": (c_int, [vp, vp, vp, c_int, c_int, vp, vp, vp, c_int]),
+    "nepb_wep_pinv": (c_int, [vp, vp, vp, vp]),
+    "nepb_wep_schur_matvec_block": (c_int, [vp, vp, vp, vp, c_int, vp, c_int]),
+    "nepb_wep_mlincomb_bytes": (c_i64, [vp, c_int]),
     "nepb_msws_init": (c_int, [C.c_uint64, C.c_uint64, vp]),
     "nepb_msws_fill": (c_int, [vp, c_i64, vp]),
 }

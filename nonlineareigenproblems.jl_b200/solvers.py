@@ -65,7 +65,8 @@ class StandardSPMFErrmeasure:
 
 
 def DefaultErrmeasure(nep):
-    return StandardSPMFErrmeasure(nep)
+    """errmeasure.jl:91-101: StandardSPMFErrmeasure for an AbstractSPMF, the plain residual otherwise (e.g. WEP_FD)."""
+    return StandardSPMFErrmeasure(nep) if hasattr(nep, "get_Av") else ResidualErrmeasure(nep)
 
 
 def _errs(errmeasure, lams, Q):
