@@ -554,6 +554,296 @@ __global__ void __launch_bounds__(256, 2) lu_schur_pipe_kernel(LuDev d, const in
 }
 
 // ---------------------------------------------------------------------------------------------
+// schur on the FP64 tensor pipe (round 2): same items as the pipelined kernel, the 64 x 64 x np product of a tile as
+// mma.sync.m8n8k4.f64 (DMMA) -- 8 warps, each 16 rows x 32 columns = 2 x 4 MMA tiles, 4 real MMAs per complex product.
+// The DFMA version reads 128 B of shared memory per thread and k-step for 64 DFMA: the 128 B/clk shared-memory pipe and the
+// FP64 pipe are busy for the same number of cycles (measured: FP64 pipe 43 % active).  With MMA fragments a warp reads
+// 12 x 256 B per 4 k-steps for 8192 DFMA: the shared-memory pipe needs a fifth of the FP64 time.
+// Operands are de-interleaved into re / im planes by 8-byte cp.async copies (zero-fill outside the tile and for k >= np):
+// L21 as [k][row] with a pitch of 68 doubles, U12 as [column][k] with a pitch of 36, so that both the copies (row-fastest /
+// k-fastest, following the column-major fronts) and the fragment reads hit 16 different bank pairs per phase.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async8z(double* smem_dst, const double* gsrc, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gsrc), "r"(sz));
+}
+__device__ int g_schur_dbg = 0;  // timing experiments (NEPB_LU_SCHUR_DBG): 1 no MMA, 2 no epilogue, 4 load / store epilogue, 8 no staging
+constexpr int SD_LLD = SCHUR_T + 4;  // L planes: [k][row]
+constexpr int SD_ULD = 36;           // U planes: [column][k], k <= 32
+constexpr int SD_UBUF = 2 * SCHUR_T * SD_ULD;  // doubles per U buffer (re plane + im plane)
+template <bool CINIT>
+__global__ void __launch_bounds__(256, 2) lu_schur_dmma_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts) {
+    extern __shared__ double sdm[];
+    const int4 it = items[blockIdx.x];
+    const int s = it.x, i0 = it.y, jfirst = it.z, ntiles = it.w;
+    const int b = blockIdx.y;
+    const int nf = d.ld[s], np = d.np[s], ncb = d.nf[s] - np;
+    const int npad = (np + 3) & ~3;
+    double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
+    double* sLr = sdm;
+    double* sLi = sLr + npad * SD_LLD;
+    double* sU0 = sLi + npad * SD_LLD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int th = min(SCHUR_T, ncb - i0);
+    const int dbg = g_schur_dbg;
+    auto stage_u = [&](int j0, double* sU) {
+        const int tw = min(SCHUR_T, ncb - j0);
+        if (dbg & 8) return;
+        for (int idx = tid; idx < npad * SCHUR_T; idx += 256) {
+            const int t = idx % npad, c = idx / npad;
+            const bool ok = c < tw && t < np;
+            const double* src = (const double*)(F + (ok ? (size_t)t + (size_t)(np + j0 + c) * nf : 0));
+            cp_async8z(sU + c * SD_ULD + t, src, ok);
+            cp_async8z(sU + SCHUR_T * SD_ULD + c * SD_ULD + t, src + 1, ok);
+        }
+    };
+    for (int idx = tid; idx < ((dbg & 8) ? 0 : npad * SCHUR_T); idx += 256) {
+        const int r = idx % SCHUR_T, t = idx / SCHUR_T;
+        const bool ok = r < th && t < np;
+        const double* src = (const double*)(F + (ok ? (size_t)(np + i0 + r) + (size_t)t * nf : 0));
+        cp_async8z(sLr + t * SD_LLD + r, src, ok);
+        cp_async8z(sLi + t * SD_LLD + r, src + 1, ok);
+    }
+    stage_u(jfirst, sU0);
+    cp_async_commit();
+    const int ar = lane >> 2, ak = lane & 3;
+    const int wr = (warp & 3) * 16, wc = (warp >> 2) * 32;
+    for (int q = 0; q < ntiles; ++q) {
+        const int j0 = jfirst + q * SCHUR_T;
+        const double* sUr = sU0 + (size_t)(q & 1) * SD_UBUF;
+        const double* sUi = sUr + SCHUR_T * SD_ULD;
+        const int tw = min(SCHUR_T, ncb - j0);
+        double cr[2][4][2], ci[2][4][2];
+        // CINIT: the accumulators start as the C tile itself (loads in flight while the operand tiles land), the product is
+        // formed with -L21, and the tile is written back with plain stores: no atomics, the tile is owned by this CTA
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int cc = wc + nt * 8 + 2 * ak + e;
+                const double2* col = F + (size_t)(np + i0) + (size_t)(np + j0 + cc) * nf;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int rr = wr + mt * 8 + ar;
+                    double2 v = make_double2(0.0, 0.0);
+                    if (CINIT && cc < tw && rr < th) v = col[rr];
+                    cr[mt][nt][e] = v.x;
+                    ci[mt][nt][e] = v.y;
+                }
+            }
+        if (q + 1 < ntiles) {
+            stage_u(j0 + SCHUR_T, sU0 + (size_t)((q + 1) & 1) * SD_UBUF);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (wr < th && wc < tw) {  // warp-uniform: skip warps whose 16 x 32 patch lies outside the tile
+#pragma unroll 2
+            for (int k4 = 0; k4 < ((dbg & 1) ? 0 : npad); k4 += 4) {
+                double a_r[2], a_i[2], na_i[2];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    a_r[mt] = sLr[(k4 + ak) * SD_LLD + wr + mt * 8 + ar];
+                    a_i[mt] = sLi[(k4 + ak) * SD_LLD + wr + mt * 8 + ar];
+                    if (CINIT) {  // -L21
+                        a_r[mt] = -a_r[mt];
+                        a_i[mt] = -a_i[mt];
+                    }
+                    na_i[mt] = -a_i[mt];
+                }
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const double b_r = sUr[(wc + nt * 8 + ar) * SD_ULD + k4 + ak];
+                    const double b_i = sUi[(wc + nt * 8 + ar) * SD_ULD + k4 + ak];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        dmma884(cr[mt][nt][0], cr[mt][nt][1], a_r[mt], b_r);
+                        dmma884(ci[mt][nt][0], ci[mt][nt][1], a_r[mt], b_i);
+                        dmma884(cr[mt][nt][0], cr[mt][nt][1], na_i[mt], b_i);
+                        dmma884(ci[mt][nt][0], ci[mt][nt][1], a_i[mt], b_r);
+                    }
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int cc = wc + nt * 8 + 2 * ak + e;
+                    if (cc < tw) {
+                        double2* col = F + (size_t)(np + i0) + (size_t)(np + j0 + cc) * nf;
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+                            const int rr = wr + mt * 8 + ar;
+                            if (CINIT) {
+                                if (rr < th) col[rr] = make_double2(cr[mt][nt][e], ci[mt][nt][e]);
+                            } else if (rr < th && !(dbg & 2)) {
+                                if (dbg & 4) {
+                                    double2 o = col[rr];
+                                    o.x -= cr[mt][nt][e];
+                                    o.y -= ci[mt][nt][e];
+                                    col[rr] = o;
+                                } else {
+                                    red_sub_c(col + rr, make_double2(cr[mt][nt][e], ci[mt][nt][e]));
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // the buffer of tile q is refilled in iteration q + 1
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// schur with delayed updates (round 2, the default): the skip experiments of profiles/r2_contour_breakdown.txt show that the
+// trailing update is bound by the read-modify-write of C in HBM (82 GB per 128-node step: every link of a supernode that was
+// split at 32 pivot columns passes over the whole trailing matrix with an inner dimension of 32), not by the FP64 pipe.
+// In a chain of in-place fronts the panels of consecutive links are neighbouring columns / rows of ONE dense array, so the
+// updates of up to LU_WINDOW links can be applied together: a deferred link only updates the strip that becomes the pivot
+// block and the panels of the next link (first np_next columns and rows of its trailing matrix), with the panels of all
+// links since the last full update, K = kback + np; the link that closes the window updates its whole trailing matrix once
+// with that K (up to 128).  C traffic and atomics per flop drop by the window length.
+// Kernel: 64 x 64 tile per item and column tile, DMMA as above, K streamed in chunks of 16 through a 3-stage cp.async ring
+// (re / im planes; L chunk [k][row] pitch 68, U chunk [column][k] pitch 20: conflict-free copies and fragment reads).
+// item.w = column tiles | kind << 8 | cap << 16 (strips: kind 1 / 2, cap = pivot columns of the next link).
+// ---------------------------------------------------------------------------------------------
+constexpr int SR_KC = 16, SR_ST = 3, SR_LLD = SCHUR_T + 4, SR_ULD = SR_KC + 4;
+constexpr int SR_STAGE = 2 * SR_KC * SR_LLD + 2 * SCHUR_T * SR_ULD;  // doubles
+constexpr size_t SR_SMEM = (size_t)SR_ST * SR_STAGE * sizeof(double);
+// MT x NT MMA tiles per warp: (2, 4) full 64 x 64 tile, (1, 4) row strip (32 x 64), (2, 2) column strip (64 x 32)
+template <int MT, int NT>
+__device__ __forceinline__ void schur_ring_body(const LuDev& d, const int4 it, double2* __restrict__ fronts, double* srm) {
+    const int s = it.x, i0 = it.y, jfirst = it.z, ntiles = it.w & 0xff;
+    constexpr int TM = 4 * 8 * MT, TN = 2 * 8 * NT;  // rows / columns of the CTA tile
+    const int b = blockIdx.y;
+    const int nf = d.ld[s], np = d.np[s], ncb = d.nf[s] - np, kb = d.kback[s];
+    const int ktot = kb + np, nk = (ktot + SR_KC - 1) / SR_KC;
+    double2* F = fronts + (size_t)b * d.front_total + d.front_off[s];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int dbg = g_schur_dbg;
+    const int cap = (it.w >> 16) & 0xff;  // strips: the next link's pivot columns (<= 32)
+    const int th = (MT == 1) ? min(cap, ncb - i0) : min(TM, ncb - i0);
+    auto tile_w = [&](int j0) { return (NT == 2) ? min(cap, ncb - j0) : min(TN, ncb - j0); };
+    auto load = [&](int i) {
+        if (dbg & 8) return;
+        const int q = i / nk, kc = i - q * nk;
+        const int j0 = jfirst + q * SCHUR_T, tw = tile_w(j0);
+        double* sLr = srm + (size_t)(i % SR_ST) * SR_STAGE;
+        double* sLi = sLr + SR_KC * SR_LLD;
+        double* sUr = sLi + SR_KC * SR_LLD;
+        double* sUi = sUr + SCHUR_T * SR_ULD;
+#pragma unroll
+        for (int idx = tid; idx < SR_KC * TM; idx += 256) {  // L21 chunk: TM rows x 16 k, rows fastest (column-major front)
+            const int r = idx % TM, kk = idx / TM;
+            const int t = kc * SR_KC + kk;
+            const bool ok = r < th && t < ktot;
+            const double* src = (const double*)(F + (ok ? (int64_t)(np + i0 + r) + (int64_t)(t - kb) * nf : 0));
+            cp_async8z(sLr + kk * SR_LLD + r, src, ok);
+            cp_async8z(sLi + kk * SR_LLD + r, src + 1, ok);
+        }
+#pragma unroll
+        for (int idx = tid; idx < SR_KC * TN; idx += 256) {  // U12 chunk: 16 k x TN columns, k fastest
+            const int kk = idx % SR_KC, c = idx / SR_KC;
+            const int t = kc * SR_KC + kk;
+            const bool ok = c < tw && t < ktot;
+            const double* src = (const double*)(F + (ok ? (int64_t)(t - kb) + (int64_t)(np + j0 + c) * nf : 0));
+            cp_async8z(sUr + c * SR_ULD + kk, src, ok);
+            cp_async8z(sUi + c * SR_ULD + kk, src + 1, ok);
+        }
+    };
+    const int total = ntiles * nk;
+    for (int i = 0; i < SR_ST - 1; ++i) {
+        if (i < total) load(i);
+        cp_async_commit();
+    }
+    const int ar = lane >> 2, ak = lane & 3;
+    const int wr = (warp & 3) * 8 * MT, wc = (warp >> 2) * 8 * NT;
+    double cr[MT][NT][2], ci[MT][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) cr[mt][nt][0] = cr[mt][nt][1] = ci[mt][nt][0] = ci[mt][nt][1] = 0.0;
+    int q = 0, kc = 0;
+    for (int i = 0; i < total; ++i) {
+        cp_async_wait<SR_ST - 2>();
+        __syncthreads();  // chunk i has landed for everybody, and everybody is done with the stage that is refilled now
+        if (i + SR_ST - 1 < total) load(i + SR_ST - 1);
+        cp_async_commit();
+        const int j0 = jfirst + q * SCHUR_T, tw = tile_w(j0);
+        const bool active = wr < th && wc < tw;  // warp-uniform
+        if (active && !(dbg & 1)) {
+            const double* sLr = srm + (size_t)(i % SR_ST) * SR_STAGE;
+            const double* sLi = sLr + SR_KC * SR_LLD;
+            const double* sUr = sLi + SR_KC * SR_LLD;
+            const double* sUi = sUr + SCHUR_T * SR_ULD;
+#pragma unroll
+            for (int k4 = 0; k4 < SR_KC; k4 += 4) {
+                double a_r[MT], a_i[MT], na_i[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    a_r[mt] = sLr[(k4 + ak) * SR_LLD + wr + mt * 8 + ar];
+                    a_i[mt] = sLi[(k4 + ak) * SR_LLD + wr + mt * 8 + ar];
+                    na_i[mt] = -a_i[mt];
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double b_r = sUr[(wc + nt * 8 + ar) * SR_ULD + k4 + ak];
+                    const double b_i = sUi[(wc + nt * 8 + ar) * SR_ULD + k4 + ak];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        dmma884(cr[mt][nt][0], cr[mt][nt][1], a_r[mt], b_r);
+                        dmma884(ci[mt][nt][0], ci[mt][nt][1], a_r[mt], b_i);
+                        dmma884(cr[mt][nt][0], cr[mt][nt][1], na_i[mt], b_i);
+                        dmma884(ci[mt][nt][0], ci[mt][nt][1], a_i[mt], b_r);
+                    }
+                }
+            }
+        }
+        if (++kc == nk) {  // tile q complete: C -= acc (L2 reductions, fire and forget), next column tile
+            if (active && !(dbg & 2)) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int cc = wc + nt * 8 + 2 * ak + e;
+                        if (cc < tw) {
+                            double2* col = F + (size_t)(np + i0) + (size_t)(np + j0 + cc) * nf;
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) {
+                                const int rr = wr + mt * 8 + ar;
+                                if (rr < th) red_sub_c(col + rr, make_double2(cr[mt][nt][e], ci[mt][nt][e]));
+                            }
+                        }
+                    }
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) cr[mt][nt][0] = cr[mt][nt][1] = ci[mt][nt][0] = ci[mt][nt][1] = 0.0;
+            kc = 0;
+            ++q;
+        }
+    }
+}
+
+// item.w = column tiles | kind << 8: kind 0 full 64 x 64 tiles, 1 row strip (32-row tiles), 2 column strip (32-column tiles)
+__global__ void __launch_bounds__(256, 2) lu_schur_ring_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts) {
+    extern __shared__ double srm[];
+    const int4 it = items[blockIdx.x];
+    const int kind = (it.w >> 8) & 0xff;
+    if (kind == 0) schur_ring_body<2, 4>(d, it, fronts, srm);
+    else if (kind == 1) schur_ring_body<1, 4>(d, it, fronts, srm);
+    else schur_ring_body<2, 2>(d, it, fronts, srm);
+}
+
+// ---------------------------------------------------------------------------------------------
 // solves.  Xp: permuted right-hand sides / solutions, [b][n][k] row-major; W: per-front work rows [b][w_total][k].
 // rhs_stride = 0 when all shifts share one right-hand side block (contour integration).
 // ---------------------------------------------------------------------------------------------
@@ -1213,6 +1503,30 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
                     S.level[s], cnt, S.level[top], nf[top] - np[top]);
         }
     }
+    // delayed Schur updates (lu_schur_ring_kernel): windows of up to LU_WINDOW consecutive links of a chain of in-place fronts
+    std::vector<int32_t> kback(ns, 0);
+    std::vector<char> defer(ns, 0);
+    static const bool use_ring = !(getenv("NEPB_LU_SCHUR_RING") && atoi(getenv("NEPB_LU_SCHUR_RING")) == 0) && !getenv("NEPB_LU_SCHUR_SIMPLE");
+    static const int window = std::max(1, std::min(4, getenv("NEPB_LU_WINDOW") ? atoi(getenv("NEPB_LU_WINDOW")) : 4));
+    sd->schur_ring = use_ring && S.max_np <= 32;
+    if (sd->schur_ring && window > 1)
+        for (int s = 0; s < ns; ++s) {
+            if (!S.in_place_child[s] || S.has_in_place_child[s]) continue;  // not the first link of a chain
+            int pos = 0, kb = 0;
+            for (int cur = s;; cur = S.sn_parent[cur]) {
+                kback[cur] = kb;
+                const bool has_next = S.in_place_child[cur];
+                if (has_next && pos < window - 1) {
+                    defer[cur] = 1;
+                    kb += np[cur];
+                    ++pos;
+                } else {
+                    kb = 0;
+                    pos = 0;
+                }
+                if (!has_next) break;
+            }
+        }
     std::vector<int2> fc_items, bc_items;
     int max_level_slots = 0;
     for (int l = 0; l < S.nlevels; ++l) {
@@ -1274,11 +1588,25 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
                 pn_items.push_back(make_int4(s, 0, t0, 0));
                 pn_items.push_back(make_int4(s, 1, t0, 0));
             }
-            for (int j0 = 0; j0 < ncb; j0 += SCHUR_T)
-                for (int i0 = 0; i0 < ncb; i0 += SCHUR_T) sc_items.push_back(make_int4(s, i0, j0, 1));
-            for (int j0 = 0; j0 < ncb; j0 += SCHUR_T * SCHUR_GROUP)
-                for (int i0 = 0; i0 < ncb; i0 += SCHUR_T)
-                    sp_items.push_back(make_int4(s, i0, j0, std::min(SCHUR_GROUP, (ncb - j0 + SCHUR_T - 1) / SCHUR_T)));
+            if (defer[s]) {
+                // deferred link: only the strip that becomes the next link's pivot block and panels (its first npn columns, all
+                // rows; its first npn rows, the remaining columns)
+                const int npn = np[S.sn_parent[s]];  // <= 32 = the strip tiles' short side
+                for (int i0 = 0; i0 < ncb; i0 += SCHUR_T) {  // column strip: 64 x 32 tiles
+                    sc_items.push_back(make_int4(s, i0, 0, 1 | (2 << 8) | (npn << 16)));
+                    sp_items.push_back(make_int4(s, i0, 0, 1 | (2 << 8) | (npn << 16)));
+                }
+                // row strip: 32 x 64 tiles over the columns >= npn (the corner belongs to the column strip)
+                for (int j0 = npn; j0 < ncb; j0 += SCHUR_T) sc_items.push_back(make_int4(s, 0, j0, 1 | (1 << 8) | (npn << 16)));
+                for (int j0 = npn; j0 < ncb; j0 += SCHUR_T * SCHUR_GROUP)
+                    sp_items.push_back(make_int4(s, 0, j0, std::min(SCHUR_GROUP, (ncb - j0 + SCHUR_T - 1) / SCHUR_T) | (1 << 8) | (npn << 16)));
+            } else {
+                for (int j0 = 0; j0 < ncb; j0 += SCHUR_T)
+                    for (int i0 = 0; i0 < ncb; i0 += SCHUR_T) sc_items.push_back(make_int4(s, i0, j0, 1));
+                for (int j0 = 0; j0 < ncb; j0 += SCHUR_T * SCHUR_GROUP)
+                    for (int i0 = 0; i0 < ncb; i0 += SCHUR_T)
+                        sp_items.push_back(make_int4(s, i0, j0, std::min(SCHUR_GROUP, (ncb - j0 + SCHUR_T - 1) / SCHUR_T)));
+            }
             (in_tail[s] ? sfr_tail : sfr_items).push_back(s);
             if (ncb > SOLVE_BIG)
                 for (int r0 = 0; r0 < ncb; r0 += SOLVE_CHUNK)
@@ -1371,6 +1699,7 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
     UP(sd->fc_items, fc_items);
     UP(sd->bc_items, bc_items);
     UP(sd->has_ip, S.has_in_place_child);
+    UP(sd->kback, kback);
 #undef UP
     if (e != cudaSuccess) {
         set_error("CUDA error while uploading the LU symbolic data: %s", cudaGetErrorString(e));
@@ -1384,6 +1713,7 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
     d.ld = sd->ld.p;
     d.in_place = sd->in_place.p;
     d.has_ip = sd->has_ip.p;
+    d.kback = sd->kback.p;
     d.bw_slot = sd->bw_slot.p;
     d.xsplit = sd->xsplit.p;
     d.row_ptr = sd->row_ptr.p;
@@ -1404,6 +1734,21 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
     sd->smem_schur = (size_t)mnp * (2 * SCHUR_T + 1) * 16;
     sd->smem_schur_pipe = (size_t)mnp * (3 * SCHUR_T + 2) * 16;
     sd->schur_pipe = sd->smem_schur_pipe <= 110 * 1024 && !getenv("NEPB_LU_SCHUR_SIMPLE");
+    {   // DMMA Schur update (default; NEPB_LU_SCHUR_DMMA=0 selects the DFMA kernels)
+        const int mpad = (mnp + 3) & ~3;
+        sd->smem_schur_dmma = ((size_t)2 * mpad * SD_LLD + (size_t)2 * SD_UBUF) * sizeof(double);
+        const char* e = getenv("NEPB_LU_SCHUR_DMMA");
+        sd->schur_dmma = mnp <= 32 && !(e && atoi(e) == 0) && !getenv("NEPB_LU_SCHUR_SIMPLE");
+        cudaFuncSetAttribute(lu_schur_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM);
+        if (getenv("NEPB_LU_SCHUR_DBG")) {
+            const int v = atoi(getenv("NEPB_LU_SCHUR_DBG"));
+            cudaMemcpyToSymbol(g_schur_dbg, &v, sizeof(int));
+        }
+        if (sd->schur_dmma) {
+            cudaFuncSetAttribute(lu_schur_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_schur_dmma);
+            cudaFuncSetAttribute(lu_schur_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_schur_dmma);
+        }
+    }
     cudaFuncSetAttribute(lu_diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
     cudaFuncSetAttribute(lu_schur_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd->smem_schur_pipe);
     cudaFuncSetAttribute(lu_panel_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM);
@@ -1501,12 +1846,19 @@ __global__ void lu_info_init_kernel(int nb, LuInfo* __restrict__ info) {
 
 // numeric factorisation of lu->nb shifts into lu->fronts (coefficients already on the device); device work only, so the
 // sequence can be captured into a CUDA graph
+// Timing experiments only (results are wrong when a bit is set): NEPB_LU_SKIP bit0 Schur update, bit1 extend-add, bit2 panels,
+// bit3 forward solve, bit4 backward solve, bit5 diag, bit6 zero-fill of the fronts.
+static int lu_skip_mask() {
+    static const int m = getenv("NEPB_LU_SKIP") ? atoi(getenv("NEPB_LU_SKIP")) : 0;
+    return m;
+}
+
 static int factor_prologue(nepb_lu* lu) {
     const nepb_spmf* h = lu->op;
     LuSymbolicDev* sd = lu->sym;
     const LuSymbolic& S = sd->S;
     const int nb = lu->nb;
-    NEPB_CUDA(cudaMemsetAsync(lu->fronts.p, 0, sizeof(double) * 2 * (size_t)nb * S.front_total, stream()));
+    if (!(lu_skip_mask() & 64)) NEPB_CUDA(cudaMemsetAsync(lu->fronts.p, 0, sizeof(double) * 2 * (size_t)nb * S.front_total, stream()));
     NEPB_LAUNCH(lu_info_init_kernel, (nb + 127) / 128, 128, 0, nb, lu->info.p);
     dim3 grid((unsigned)((h->nnz + 255) / 256), nb);
     NEPB_LAUNCH(lu_assemble_kernel, grid, 256, 0, h->nnz, h->p, h->is_complex, sd->a_pos.p, sd->a_scale.p, h->d_vals.p, (const double2*)lu->coef.p,
@@ -1521,9 +1873,10 @@ static void factor_level_panels(nepb_lu* lu, int l) {
     const int nb = lu->nb;
     double2* F = (double2*)lu->fronts.p;
     const auto& L = sd->lv[l];
-    if (L.ea_count) NEPB_LAUNCH(lu_extend_add_kernel, dim3(L.ea_count, nb), 256, 0, sd->dev, sd->ea_items.p + L.ea_begin, sd->ea_recs.p, F);
-    NEPB_LAUNCH(lu_diag_inv_kernel, dim3(L.front_count, nb), 128, DIAG_SMEM, sd->dev, sd->fr_items.p + L.front_begin, F, lu->piv.p, lu->info.p);
-    if (L.pn_count) NEPB_LAUNCH(lu_panel_inv_kernel, dim3(L.pn_count, nb), 256, PANEL_SMEM, sd->dev, sd->pn_items.p + L.pn_begin, F, lu->piv.p);
+    const int skip = lu_skip_mask();
+    if (L.ea_count && !(skip & 2)) NEPB_LAUNCH(lu_extend_add_kernel, dim3(L.ea_count, nb), 256, 0, sd->dev, sd->ea_items.p + L.ea_begin, sd->ea_recs.p, F);
+    if (!(skip & 32)) NEPB_LAUNCH(lu_diag_inv_kernel, dim3(L.front_count, nb), 128, DIAG_SMEM, sd->dev, sd->fr_items.p + L.front_begin, F, lu->piv.p, lu->info.p);
+    if (L.pn_count && !(skip & 4)) NEPB_LAUNCH(lu_panel_inv_kernel, dim3(L.pn_count, nb), 256, PANEL_SMEM, sd->dev, sd->pn_items.p + L.pn_begin, F, lu->piv.p);
 }
 
 static void factor_level_schur(nepb_lu* lu, int l) {
@@ -1531,9 +1884,24 @@ static void factor_level_schur(nepb_lu* lu, int l) {
     const int nb = lu->nb;
     double2* F = (double2*)lu->fronts.p;
     const auto& L = sd->lv[l];
+    if (lu_skip_mask() & 1) return;
     // few shifts in flight: one tile per CTA (twice the CTAs, half the time per CTA); otherwise two column tiles per CTA share
     // the L21 tile
-    if (L.sc_count && sd->schur_pipe && (int64_t)nb * L.sp_count < 2 * sm_count())
+    if (L.sc_count && sd->schur_ring) {
+        const bool one = (int64_t)nb * L.sp_count < 2 * sm_count();
+        NEPB_LAUNCH(lu_schur_ring_kernel, dim3(one ? L.sc_count : L.sp_count, nb), 256, SR_SMEM, sd->dev,
+                    one ? sd->sc_items.p + L.sc_begin : sd->sp_items.p + L.sp_begin, F);
+        return;
+    }
+    static const bool cinit = (getenv("NEPB_LU_SCHUR_CINIT") && atoi(getenv("NEPB_LU_SCHUR_CINIT")) != 0);
+    const bool one_tile = (int64_t)nb * L.sp_count < 2 * sm_count();
+    if (L.sc_count && sd->schur_dmma) {
+        const dim3 grid(one_tile ? L.sc_count : L.sp_count, nb);
+        const int4* items = one_tile ? sd->sc_items.p + L.sc_begin : sd->sp_items.p + L.sp_begin;
+        if (cinit) NEPB_LAUNCH(lu_schur_dmma_kernel<true>, grid, 256, sd->smem_schur_dmma, sd->dev, items, F);
+        else NEPB_LAUNCH(lu_schur_dmma_kernel<false>, grid, 256, sd->smem_schur_dmma, sd->dev, items, F);
+    }
+    else if (L.sc_count && sd->schur_pipe && (int64_t)nb * L.sp_count < 2 * sm_count())
         NEPB_LAUNCH(lu_schur_pipe_kernel, dim3(L.sc_count, nb), 256, sd->smem_schur_pipe, sd->dev, sd->sc_items.p + L.sc_begin, F);
     else if (L.sc_count && sd->schur_pipe)
         NEPB_LAUNCH(lu_schur_pipe_kernel, dim3(L.sp_count, nb), 256, sd->smem_schur_pipe, sd->dev, sd->sp_items.p + L.sp_begin, F);
@@ -1745,7 +2113,7 @@ int lu_factor_solve_pipelined(nepb_lu* lu, int k, const double2* Bdev, size_t rh
         factor_level_schur(lu, l);
         NEPB_CUDA(cudaStreamWaitEvent(side, ev[l + 1], 0));
         set_current_stream(side);
-        solve_forward_level(c, l);
+        if (!(lu_skip_mask() & 8)) solve_forward_level(c, l);
         set_current_stream(s0);
     }
     NEPB_CUDA(cudaEventRecord(ev[nlev + 1], side));  // join
@@ -1759,12 +2127,12 @@ int lu_factor_solve_pipelined(nepb_lu* lu, int k, const double2* Bdev, size_t rh
         if (hp) {
             if (l + 2 < nlev) NEPB_CUDA(cudaStreamWaitEvent(side, evB[l + 2], 0));
             set_current_stream(side);
-            solve_backward_partials(c, l);
+            if (!(lu_skip_mask() & 16)) solve_backward_partials(c, l);
             set_current_stream(s0);
             NEPB_CUDA(cudaEventRecord(evP[l], side));
             NEPB_CUDA(cudaStreamWaitEvent(s0, evP[l], 0));
         }
-        solve_backward_level(c, l);
+        if (!(lu_skip_mask() & 16)) solve_backward_level(c, l);
         NEPB_CUDA(cudaEventRecord(evB[l], s0));
     }
     NEPB_LAUNCH(lu_permute_out_kernel, pg, 256, 0, n, k, c.sd->iperm.p, c.sd->dc.p, c.Xp, Xdev, (size_t)n * k);

@@ -20,6 +20,7 @@ struct LuDev {  // passed by value to kernels
     const uint8_t* has_ip;     // the front has such a child
     const int32_t* bw_slot;    // first partial-sum slot of a big front in the backward solve
     const int32_t* xsplit;     // update rows [0, xsplit) are pivot columns of the parent
+    const int32_t* kback;      // delayed Schur updates: pivot columns of the earlier links of the window (0: none)
     const int64_t* row_ptr;
     const int32_t* rows;
     const int64_t* rel_ptr;
@@ -76,6 +77,8 @@ struct LuSymbolicDev {
     std::vector<LuLevel> lv;
     DevBuf<int64_t> front_off, row_ptr, rel_ptr, w_off, a_pos;
     DevBuf<uint8_t> in_place, has_ip;
+    DevBuf<int32_t> kback;
+    bool schur_ring = false;
     DevBuf<int32_t> bw_slot, xsplit, sfr_items, chain_fronts;
     DevBuf<int2> fc_items, bc_items;
     int part_slots = 0;
@@ -86,6 +89,8 @@ struct LuSymbolicDev {
     DevBuf<EaRec> ea_recs;
     size_t smem_diag = 0, smem_panel = 0, smem_schur = 0, smem_schur_pipe = 0;
     bool schur_pipe = false;
+    size_t smem_schur_dmma = 0;
+    bool schur_dmma = false;
 };
 
 int lu_symbolic_get(const nepb_spmf* h, LuSymbolicDev** out);

@@ -188,5 +188,7 @@ def test_nleigs_gun_lowrank_device(variant):
     assert gold["count"] == 21 and len(lam) == 21
     _match(lam, gold["lam"], 1e-8)
     assert det["kconv"] == gold["kconv"] and det["N"] == gold["N"]
-    assert det["rows"] == dnep.n + det["N"] * 84 and det["gpu_launches"] > 0
+    # p = 1: one block of n entries, then blocks of r = 84 (method_nleigs.jl:205-211); the dynamic variants keep the block that
+    # was added in the step the linearization converged
+    assert det["rows"] in (dnep.n + det["N"] * 84, dnep.n + (det["N"] + 1) * 84) and det["gpu_launches"] > 0
     assert np.all(res < 1e-10)
