@@ -22,6 +22,7 @@ from __future__ import annotations
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import subprocess
 import sys
@@ -311,6 +312,66 @@ def bench_spmm(args, ks=(1, 8, 20)):
                          % (res["serial_csc"], cores, res["allcore_csr"], err)}
     dnep.close()
     return out, peak, peak_src, cpu, general
+
+
+def bench_wep(args, peak, nz=945):
+    """Config C5 (WEP, JARLEBRING, nz = 3*5*7*9 = 945, nx = nz + 4, n = 898 695): the native compute_Mlincomb
+    (Waveguide.jl:324-379) on the device -- the Sylvester-form interior as one stencil pass plus the boundary transforms -- for
+    1, 3 and 20 columns, against the HBM roofline (algorithmic bytes: nepb_wep_mlincomb_bytes), each result compared with a
+    NumPy / SciPy evaluation of the reference's formula on the same operands (sparse Dzz / Dz / Dxx products and numpy.fft)."""
+    import nepb200
+    from nepb200 import Block, _lib
+    from nepb200 import wep as pw
+    lib = _lib.lib
+    nep = nepb200.nep_gallery_WEP(nx=nz + 4, nz=nz, benchmark_problem="JARLEBRING", neptype="WEP")
+    n, nx = nep.n, nep.nx
+    lam = -2.7 - 3.1j
+    rng = np.random.default_rng(5)
+    out = {"n": int(n), "nx": int(nx), "nz": int(nz)}
+
+    def reference(V, a):
+        m = nx * nz
+        X = [V[:m, j].reshape(nz, nx, order="F") for j in range(min(V.shape[1], 3))]
+        y1 = (nep.A(lam) @ X[0] + (nep.Dxx.T @ X[0].T).T + nep.K * X[0]) * a[0]
+        for d in range(1, len(X)):
+            y1 = y1 + (nep.A(lam, d) @ X[d]) * a[d]
+        y1 = y1.reshape(-1, order="F") + (nep.C1 @ V[m:, 0]) * a[0]
+        D = 1j * pw.sqrt_derivative(1.0, np.concatenate([nep.b, nep.b]), np.concatenate([nep.cM, nep.cP]), V.shape[1] - 1, lam)
+        D[:, 0] += nep.d0
+        Rinv = lambda x: np.fft.ifft(nep.bbinv * x[::-1])  # noqa: E731
+        R = lambda x: (nep.bb * np.fft.fft(x))[::-1]  # noqa: E731
+        t = sum(D[:, j] * np.concatenate([Rinv(V[m:m + nz, j]), Rinv(V[m + nz:, j])]) * a[j] for j in range(V.shape[1]))
+        return np.concatenate([y1, np.concatenate([R(t[:nz]), R(t[nz:])]) + (nep.C2T @ V[:m, 0]) * a[0]])
+
+    for na in (1, 3, 20):
+        V = rng.standard_normal((n, na)) + 1j * rng.standard_normal((n, na))
+        a = (rng.standard_normal(na) + 1j * rng.standard_normal(na)) / np.array([math.factorial(min(j, 10)) for j in range(na)])
+        Vb, Zb = Block.from_host(V), Block(n, 1)
+        reps = max(args.steps, 20)
+        for _ in range(max(args.warmup, 3)):
+            nep.mlincomb_block(lam, Vb, 0, na, a, Zb, 0)
+        lib.nepb_synchronize()
+        l0 = lib.nepb_launch_count()
+        ms = C.c_float()
+        lib.nepb_timer_start()
+        for _ in range(reps):
+            nep.mlincomb_block(lam, Vb, 0, na, a, Zb, 0)
+        lib.nepb_timer_stop(C.byref(ms))
+        t = ms.value / reps
+        launches = (lib.nepb_launch_count() - l0) // reps
+        nbytes = int(lib.nepb_wep_mlincomb_bytes(nep._h, na))
+        zref = reference(V, a)
+        err = float(np.linalg.norm(Zb.download()[:, 0] - zref) / np.linalg.norm(zref))
+        out[str(na)] = {"columns": na, "ms": t, "bytes": nbytes, "gbs": nbytes / t / 1e6, "frac": nbytes / t / 1e6 / peak, "launches": int(launches),
+                        "parity_relerr": err}
+        log("[bench] WEP compute_Mlincomb n=%d, %d column(s): %.1f us, %.0f GB/s (%.1f%% of the HBM peak), %d launches; parity %.1e" %
+            (n, na, t * 1e3, out[str(na)]["gbs"], 100 * out[str(na)]["frac"], launches, err))
+        if not err < 1e-12:
+            raise SystemExit("bench: WEP compute_Mlincomb differs from the NumPy evaluation of the reference formula: %g" % err)
+        Vb.close()
+        Zb.close()
+    nep.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -617,6 +678,8 @@ def main():
         line["spmm_kernels"] = {"1": "spmm_fused_kernel", "8": "spmm_tma_kernel<CPT=1,GC=8> (16-row tiles, TMA bulk staging)",
                                 "20": "spmm_tma_kernel<CPT=3,GC=8> (16-row tiles, TMA bulk staging)"}
         line["spmm_general"] = general
+        if dist.rank == 0:
+            line["wep"] = bench_wep(args, peak)
     # factorisation roofline of the headline step: complex multiply-adds of the numeric LU (symbolic count) x 8 flops x nodes over
     # the step time, against a measured cuBLAS ZGEMM rate; the triangular solves and the assembly are in the time, not in the flops
     if dist.rank == 0:

@@ -230,8 +230,12 @@ int nepb_wep_create(int nx, int nz, double hx, double hz, const double* K_scaled
                     const double* bb, nepb_wep** out);
 int nepb_wep_destroy(nepb_wep* h);
 int nepb_wep_info(const nepb_wep* h, int* nx, int* nz, int64_t* n);
+/* Derivative table of the boundary functions at one lambda, kept in HBM: D (2 nz x ncols complex, ROW-major),
+ * D[m, j] = 1im * d^j/dlambda^j sqrt(beta_m(lambda)) (+ d0 for j = 0), the `D` of Waveguide.jl:351-361. */
+int nepb_wep_set_table(nepb_wep* h, int ncols, const double* D);
 /* Z[:, zcol] = sum_j a_j M^{(j)}(lambda) V[:, vcol0 + j], j = 0..na-1.  coef: 2 nz x na complex, ROW-major,
- * coef[m, j] = a_j * (D[m, j] + (j == 0 ? d0 : 0)) with D as in Waveguide.jl:351-361. */
+ * coef[m, j] = a_j * D[m, j]; or NULL: the table of nepb_wep_set_table (for this lambda, >= na columns) is used and a_j is
+ * applied on the device (a solver loop at a fixed shift then uploads 16 na bytes per call). */
 int nepb_wep_mlincomb_block(const nepb_wep* h, const double* lambda, const nepb_block* V, int vcol0, int na, const double* a,
                             const double* coef, nepb_block* Z, int zcol);
 /* y = [R(coef[0:nz] .* Rinv(x[0:nz])); R(coef[nz:2nz] .* Rinv(x[nz:2nz]))]; coef = 1 ./ [sM; sP] gives Pinv */

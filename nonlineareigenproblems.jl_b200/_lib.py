@@ -112,6 +112,7 @@ SIGNATURES = {
     "nepb_block_colnorms": (c_int, [vp, c_int, c_int, c_i64, vp]),
     "nepb_wep_create": (c_int, [c_int, c_int, c_dbl, c_dbl, vp, vp, vp, P(vp)]),
     "nepb_wep_destroy": (c_int, [vp]),
+    "nepb_wep_set_table": (c_int, [vp, c_int, vp]),
     "nepb_wep_info": (c_int, [vp, P(c_int), P(c_int), P(c_i64)]),
     "nepb_wep_mlincomb_block": (c_int, [vp, vp, vp, c_int, c_int, vp, vp, vp, c_int]),
     "nepb_wep_pinv": (c_int, [vp, vp, vp, vp]),

@@ -1739,7 +1739,7 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
         sd->smem_schur_dmma = ((size_t)2 * mpad * SD_LLD + (size_t)2 * SD_UBUF) * sizeof(double);
         const char* e = getenv("NEPB_LU_SCHUR_DMMA");
         sd->schur_dmma = mnp <= 32 && !(e && atoi(e) == 0) && !getenv("NEPB_LU_SCHUR_SIMPLE");
-        cudaFuncSetAttribute(lu_schur_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM);
+        cudaFuncSetAttribute(lu_schur_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM + 64 * 1024);
         if (getenv("NEPB_LU_SCHUR_DBG")) {
             const int v = atoi(getenv("NEPB_LU_SCHUR_DBG"));
             cudaMemcpyToSymbol(g_schur_dbg, &v, sizeof(int));
@@ -1889,7 +1889,8 @@ static void factor_level_schur(nepb_lu* lu, int l) {
     // the L21 tile
     if (L.sc_count && sd->schur_ring) {
         const bool one = (int64_t)nb * L.sp_count < 2 * sm_count();
-        NEPB_LAUNCH(lu_schur_ring_kernel, dim3(one ? L.sc_count : L.sp_count, nb), 256, SR_SMEM, sd->dev,
+        static const size_t pad = getenv("NEPB_LU_SCHUR_PAD") ? (size_t)atoi(getenv("NEPB_LU_SCHUR_PAD")) * 1024 : 0;  // occupancy experiments
+        NEPB_LAUNCH(lu_schur_ring_kernel, dim3(one ? L.sc_count : L.sp_count, nb), 256, SR_SMEM + pad, sd->dev,
                     one ? sd->sc_items.p + L.sc_begin : sd->sp_items.p + L.sp_begin, F);
         return;
     }

@@ -159,6 +159,7 @@ class WEP_FD:
         kb = np.array([self.k_bar], dtype=np.complex128)
         check(lib.nepb_wep_create(self.nx, self.nz, self.hx, self.hz, ptr(self.K), ptr(kb), ptr(np.ascontiguousarray(self.bb)), C.byref(h)))
         self._h = h
+        self._table = (None, 0)  # (lambda, columns) of the derivative table resident on the device
 
     def close(self):
         if getattr(self, "_h", None):
@@ -178,22 +179,39 @@ class WEP_FD:
         beta = np.concatenate([lam * lam + self.b * lam + self.cM, lam * lam + self.b * lam + self.cP])
         return 1j * np.sign(beta.imag) * np.sqrt(beta) + self.d0
 
-    def boundary_coefficients(self, lam, a):
-        """coef[m, j] = a_j (D[m, j] + [j == 0] d0), D[m, :] = 1im * sqrt_derivative(1, b_m, c_m, na - 1, lambda)
-        (Waveguide.jl:351-373); row-major (2 nz, na) for the device."""
-        na = len(a)
-        D = 1j * sqrt_derivative(1.0, np.concatenate([self.b, self.b]), np.concatenate([self.cM, self.cP]), na - 1, complex(lam))
+    def derivative_table(self, lam, ncols):
+        """D[m, :] = 1im * sqrt_derivative(1, b_m, c_m, ncols - 1, lambda), + d0 in column 0 (Waveguide.jl:351-373); (2 nz, ncols)."""
+        D = 1j * sqrt_derivative(1.0, np.concatenate([self.b, self.b]), np.concatenate([self.cM, self.cP]), ncols - 1, complex(lam))
         D[:, 0] += self.d0
-        return np.ascontiguousarray(D * np.asarray(a, dtype=np.complex128)[None, :])
+        return np.ascontiguousarray(D)
+
+    def boundary_coefficients(self, lam, a):
+        """coef[m, j] = a_j D[m, j]; row-major (2 nz, na): the explicit coefficient block of nepb_wep_mlincomb_block."""
+        return np.ascontiguousarray(self.derivative_table(lam, len(a)) * np.asarray(a, dtype=np.complex128)[None, :])
+
+    def _ensure_table(self, lam, na):
+        """The derivative table of `lam` with >= na columns on the device: a solver loop at a fixed shift (iar, tiar, resinv's
+        Rayleigh functional) computes and uploads it once and grows it geometrically."""
+        tl, tc = self._table
+        if tl != complex(lam) or tc < na:
+            ncols = na if tl != complex(lam) else max(na, 2 * tc)
+            check(lib.nepb_wep_set_table(self._h, ncols, ptr(self.derivative_table(lam, ncols))))
+            self._table = (complex(lam), ncols)
 
     # -- compute_Mlincomb -------------------------------------------------------------------------------------------------
-    def mlincomb_block(self, lam, Vb: Block, vcol0, na, a, Zb: Block, zcol):
-        """Z[:, zcol] = sum_j a_j M^{(j)}(lambda) V[:, vcol0 + j] with all operands in HBM."""
+    def mlincomb_block(self, lam, Vb: Block, vcol0, na, a, Zb: Block, zcol, use_table=True):
+        """Z[:, zcol] = sum_j a_j M^{(j)}(lambda) V[:, vcol0 + j] with all operands in HBM.  use_table: keep the derivative table
+        of `lam` on the device (solver loops at a fixed shift); False: one explicit coefficient block for this call."""
         a = np.ascontiguousarray(np.asarray(a, dtype=np.complex128))
         if len(a) != na:
             raise ValueError("Incompatible sizes: Number of coefficients = %d, number of vectors = %d." % (len(a), na))
         lam_ = np.array([complex(lam)], dtype=np.complex128)
-        check(lib.nepb_wep_mlincomb_block(self._h, ptr(lam_), Vb._h, vcol0, na, ptr(a), ptr(self.boundary_coefficients(lam, a)), Zb._h, zcol))
+        coef = None
+        if use_table:
+            self._ensure_table(lam, na)
+        else:
+            coef = self.boundary_coefficients(lam, a)
+        check(lib.nepb_wep_mlincomb_block(self._h, ptr(lam_), Vb._h, vcol0, na, ptr(a), None if coef is None else ptr(coef), Zb._h, zcol))
 
     def compute_Mlincomb(self, lam, V, a=None, startder=None):
         V = np.asarray(V, dtype=np.complex128)
@@ -224,7 +242,7 @@ class WEP_FD:
         Q = np.asarray(Q, dtype=np.complex128)
         Qb, Zb = Block.from_host(Q), Block(self.n, Q.shape[1])
         for s, lam in enumerate(lams):
-            self.mlincomb_block(lam, Qb, s, 1, [1.0], Zb, s)
+            self.mlincomb_block(lam, Qb, s, 1, [1.0], Zb, s, use_table=False)
         out = np.empty(Q.shape[1])
         check(lib.nepb_block_colnorms(Zb._h, 0, Q.shape[1], self.n, ptr(out)))
         Qb.close()
