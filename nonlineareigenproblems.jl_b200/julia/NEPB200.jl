@@ -247,6 +247,85 @@ integrate_interval(::Type{PrecomputedIntegral}, ::Type{T}, f, gv, a, b, N, logge
     task_local_storage(:nepb200_precomputed_integral)::Array{CF,3}
 
 # ------------------------------------------------------------------------------------------------
+# (f)3 WEP-native path: new methods for the reference's own WEP_FD type (GalleryWaveguide), src/gallery_extra/waveguide/Waveguide.jl
+#   compute_Mlincomb(nep::WEP_FD, λ, V, a)  :324-379   SchurMatVec * v  :393-402   Pinv  :160-163
+# The device handle is created once per problem and kept beside it (WeakKeyDict: it dies with the nep).  The reference's
+# WEP linear solvers (WEPLinSolverCreator, lin_solve :555-567) run unchanged on top: they only call Pinv, SchurMatVec and a
+# factorisation of the Schur complement, for which `B200FactorizeLinSolver` on the assembled matrix is the drop-in.
+# ------------------------------------------------------------------------------------------------
+# dense n x k block resident in HBM (nepb_block_*): upload / download transpose between Julia's column-major and the device layout
+mutable struct B200Block
+    h::Ptr{Cvoid}; n::Int; k::Int
+    function B200Block(n::Integer, k::Integer)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        chk(ccall(sym(:nepb_block_create), Cint, (Int64, Cint, Ptr{Ptr{Cvoid}}), n, k, h))
+        b = new(h[], n, k)
+        finalizer(x -> ccall(sym(:nepb_block_destroy), Cint, (Ptr{Cvoid},), x.h), b)
+        return b
+    end
+end
+function B200Block(V::Matrix{CF})
+    b = B200Block(size(V, 1), size(V, 2))
+    chk(ccall(sym(:nepb_block_upload), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{CF}, Int64), b.h, 0, b.k, V, b.n))
+    return b
+end
+function download(b::B200Block)
+    V = Matrix{CF}(undef, b.n, b.k)
+    chk(ccall(sym(:nepb_block_download), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{CF}, Int64), b.h, 0, b.k, V, b.n))
+    return V
+end
+
+mutable struct B200WEP
+    h::Ptr{Cvoid}
+    table_λ::Union{Nothing,CF}; table_cols::Int
+end
+const WEP_HANDLES = WeakKeyDict{Any,B200WEP}()
+function b200_wep(nep)   # nep::GalleryWaveguide.WEP_FD
+    get!(WEP_HANDLES, nep) do
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        K = Matrix{CF}(nep.K); kb = CF[nep.k_bar]; bb = Vector{CF}(nep.bb)
+        chk(ccall(sym(:nepb_wep_create), Cint, (Cint, Cint, Cdouble, Cdouble, Ptr{CF}, Ptr{CF}, Ptr{CF}, Ptr{Ptr{Cvoid}}),
+                  nep.nx, nep.nz, nep.hx, nep.hz, K, kb, bb, h))
+        w = B200WEP(h[], nothing, 0)
+        finalizer(x -> ccall(sym(:nepb_wep_destroy), Cint, (Ptr{Cvoid},), x.h), w)
+        w
+    end
+end
+# D[m, j] = 1im * d^j/dλ^j sqrt(β_m(λ)) (+ d0 for j = 0) with the reference's own sqrt_derivative (:574-616); row-major for C
+function wep_table(nep, λ, ncols::Integer)
+    nz = nep.nz; cMP = vcat(nep.cM, nep.cP)
+    D = Matrix{CF}(undef, ncols, 2nz)                       # column m of the Julia array = row m of the C array
+    for m = 1:2nz
+        D[:, m] .= 1im .* GalleryWaveguide.sqrt_derivative(1, nep.b[rem(m - 1, nz) + 1], cMP[m], ncols - 1, λ)
+    end
+    D[1, :] .+= nep.d0
+    return D
+end
+function b200_wep_mlincomb(nep, λ::Number, V::AbstractVecOrMat, a::Vector=ones(CF, size(V, 2)))
+    w = b200_wep(nep); n = size(nep, 1); na = size(V, 2)
+    size(V, 1) == n || error("Incompatible sizes: Length of vectors = ", size(V, 1), ", size of NEP = ", n, ".")
+    length(a) == na || error("Incompatible sizes: Number of coefficients = ", length(a), ", number of vectors = ", na, ".")
+    if w.table_λ != CF(λ) || w.table_cols < na          # a solver loop at a fixed shift uploads the table once
+        chk(ccall(sym(:nepb_wep_set_table), Cint, (Ptr{Cvoid}, Cint, Ptr{CF}), w.h, na, wep_table(nep, λ, na)))
+        w.table_λ, w.table_cols = CF(λ), na
+    end
+    Vb = B200Block(Matrix{CF}(reshape(V, n, na))); Zb = B200Block(n, 1)
+    chk(ccall(sym(:nepb_wep_mlincomb_block), Cint, (Ptr{Cvoid}, Ptr{CF}, Ptr{Cvoid}, Cint, Cint, Ptr{CF}, Ptr{CF}, Ptr{Cvoid}, Cint),
+              w.h, CF[λ], Vb.h, 0, na, Vector{CF}(a), C_NULL, Zb.h, 0))
+    return vec(download(Zb))
+end
+function b200_wep_pinv(nep, λ::Number, x::Vector)
+    w = b200_wep(nep); y = similar(x, CF)
+    coef = 1 ./ vcat(GalleryWaveguide.sM(nep, λ), GalleryWaveguide.sP(nep, λ))
+    chk(ccall(sym(:nepb_wep_pinv), Cint, (Ptr{Cvoid}, Ptr{CF}, Ptr{CF}, Ptr{CF}), w.h, Vector{CF}(coef), Vector{CF}(x), y))
+    return y
+end
+# To activate for the reference's type (needs `using GalleryWaveguide`, an optional sub-package of NEP-PACK):
+#   NonlinearEigenproblems.compute_Mlincomb(nep::GalleryWaveguide.WEP_FD, λ::Number, V::AbstractVecOrMat, a::Vector=ones(CF, size(V, 2))) =
+#       NEPB200.b200_wep_mlincomb(nep, λ, V, a)
+#   GalleryWaveguide.Pinv(nep::GalleryWaveguide.WEP_FD, λ, x) = NEPB200.b200_wep_pinv(nep, λ, x)
+
+# ------------------------------------------------------------------------------------------------
 # multi-GPU plumbing: one Julia worker per GPU (`julia -p 8`), NCCL id shipped with Distributed
 # ------------------------------------------------------------------------------------------------
 function b200_comm_unique_id()
