@@ -117,6 +117,22 @@ struct nepb_spmf {
         nepb::DevBuf<int2> runs;  // runs of consecutive columns of every tile: (first column, position in the tile | length << 16)
     };
     mutable TileSet tiling[2];  // [0]: 32-row tiles, [1]: 16-row tiles
+    // two-dimensional tiles (spmf.cu, round 2): a tile is S segments of <= R consecutive rows, one segment per "grid line" (rows
+    // a dominant column offset apart), so that the tile's rows share most of their columns and far fewer rows of V are staged
+    // per matrix row.  desc: (2 + S) int4 per tile: (first entry of cols, distinct columns, first run, runs),
+    // (first entry of lidx, nonzeros, segments, -), then per segment (first row, rows, first nonzero, nonzeros).
+    // lidx is stored tile by tile (padded to 8 entries) so that a tile's indices are one aligned bulk copy.
+    struct TileSet2D {
+        int state = 0;  // 0 = not built, 1 = ready, -1 = not applicable
+        int S = 0, R = 0, line = 0;
+        int64_t ntiles = 0;
+        int max_cols = 0, max_nnz = 0;
+        nepb::DevBuf<int4> desc;
+        nepb::DevBuf<int32_t> cols;
+        nepb::DevBuf<uint16_t> lidx;
+        nepb::DevBuf<int2> runs;
+    };
+    mutable TileSet2D tiling2d;
     void* lu_symbolic = nullptr;  // owned by lu.cu (lazy)
     std::vector<void*> lu_matched;   // analyses of row-permuted patterns (static pivoting), newest last; owned by lu.cu
     bool lu_prefer_matched = false;  // a factorisation on the plain pattern met zero / tiny pivots

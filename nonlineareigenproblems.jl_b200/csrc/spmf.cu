@@ -368,6 +368,7 @@ __host__ __device__ inline TmaSmem tma_smem_layout(int max_cols, int max_nnz, in
     return L;
 }
 
+__device__ int g_spmm_dbg = 0;  // timing experiments (NEPB_SPMM_DBG; wrong results): 1 no third V piece, 2 term values read once per trip, 4 no V loads
 template <int VW, bool CA, bool DIAG, int CPT, int GC>
 __global__ void __launch_bounds__(256) spmm_tma_kernel(int kt, int ldv, int ldz, int max_cols, int max_nnz, int tile_rows,
                                                        const int4* __restrict__ tiles, const int2* __restrict__ runs,
@@ -510,6 +511,7 @@ __global__ void __launch_bounds__(256) spmm_tma_kernel(int kt, int ldv, int ldz,
     // Two consecutive nonzeros share ONE third load: lanes 0-3 take columns 16..19 of the first, lanes 4-7 those of the second
     // (separate accumulator, folded into lanes 0-3 at the end): 2.5 instead of 3 wavefronts per nonzero for the V rows.
     const bool pair = GC == 8 && CPT == 3 && !DIAG && kt <= 20;
+    const int dbg = g_spmm_dbg;
     double2 acc3 = make_double2(0.0, 0.0);
     constexpr int UN = CPT >= 3 ? 2 : 4;
     int base = start;
@@ -520,10 +522,16 @@ __global__ void __launch_bounds__(256) spmm_tma_kernel(int kt, int ldv, int ldz,
             double va[VW], vb[VW];
             double2 xa[CPT], xb[CPT];
             load_vals_s(base, va);
-            load_vals_s(base + 1, vb);
-            load_x(la, xa, 2);
-            load_x(lb, xb, 2);
-            const double2 x3 = sV[((gc < 4) ? la : lb) * kt + 16 + (gc & 3)];
+            if (!(dbg & 2)) load_vals_s(base + 1, vb);
+            else
+                for (int t = 0; t < VW; ++t) vb[t] = va[t];
+            if (!(dbg & 4)) {
+                load_x(la, xa, 2);
+                load_x(lb, xb, 2);
+            } else {
+                xa[0] = xa[1] = xb[0] = xb[1] = make_double2(1.0, (double)la + lb);
+            }
+            const double2 x3 = (dbg & 1) ? make_double2(1.0, 2.0) : sV[((gc < 4) ? la : lb) * kt + 16 + (gc & 3)];
             const double2 ma = combine<VW, CA>(va, [&](int i) { return cp.c[i]; });
             const double2 mb = combine<VW, CA>(vb, [&](int i) { return cp.c[i]; });
 #pragma unroll
@@ -1180,12 +1188,422 @@ static int launch_tma_vw(const nepb_spmf* h, const nepb_spmf::TileSet& T, int ti
     return 1;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Two-dimensional tiles (round 2).  Measured (profiles/r2_spmm_2d.txt): with the row products' shared-memory reads switched
+// off the 16-row kernel above still takes 404 of 430 us at k = 20 -- the product is bound by the bytes that travel from L2
+// into the SMs (~6 TB/s for every variant), and a strip of 16 consecutive rows of a five-line stencil stages 5.6 rows of V per
+// matrix row.  A tile of S = 4 segments x R = 8 rows, the segments one dominant column offset ("grid line") apart, shares
+// its lines: 8 lines x 12 columns for 32 rows = 3.0 rows of V per matrix row (1.9 -> 1.0 GB of staging at k = 20).
+// The line length is found from the pattern (most frequent |column - row| >= 32); patterns without one keep the 1D tiles.
+// SCALAR mode, real term values with an even count (16-byte aligned slices); everything else as in spmm_tma_kernel.
+// ---------------------------------------------------------------------------------------------
+template <int VW, int CPT, bool PRE>
+__global__ void __launch_bounds__(256) spmm_tma2d_kernel(int kt, int ldv, int ldz, int max_cols, int max_nnz, int S, int R,
+                                                         const int4* __restrict__ desc, const int2* __restrict__ runs,
+                                                         const int* __restrict__ tile_cols, const int* __restrict__ rowptr,
+                                                         const uint16_t* __restrict__ lidx, const double* __restrict__ vals,
+                                                         const double2* __restrict__ V, double2* __restrict__ Z, const CoefP cp) {
+    constexpr int GC = 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned oA = (unsigned)max_cols * kt * 16, oL = oA + (unsigned)max_nnz * VW * 8, oB = oL + (((unsigned)max_nnz + 7) & ~7u) * 2;
+    double2* sV = (double2*)smem_raw;
+    const double* sA = (const double*)(smem_raw + oA);
+    const uint16_t* sL = (const uint16_t*)(smem_raw + oL);
+    const int4* d = desc + (size_t)blockIdx.x * (2 + S);
+    const int4 h0 = d[0], h1 = d[1];
+    const int ncols = h0.y, run0 = h0.z, nruns = h0.w, nnz = h1.y, nseg = h1.z;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(smem_raw + oB);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned lbytes = (((unsigned)nnz + 7) & ~7u) * 2;
+        const unsigned total = (unsigned)ncols * kt * 16 + (unsigned)nnz * VW * 8 + lbytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(total) : "memory");
+        unsigned off = 0;
+        for (int s = 0; s < nseg; ++s) {  // the segments' value slices, back to back
+            const int4 sg = d[2 + s];
+            if (sg.w > 0) bulk_g2s((unsigned)__cvta_generic_to_shared(smem_raw + oA) + off, vals + (size_t)sg.z * VW, (unsigned)sg.w * VW * 8, bar_s);
+            off += (unsigned)sg.w * VW * 8;
+        }
+        if (lbytes) bulk_g2s((unsigned)__cvta_generic_to_shared(smem_raw + oL), lidx + h1.x, lbytes, bar_s);
+    }
+    if (ldv == kt) {
+        for (int r = tid; r < nruns; r += nth) {
+            const int2 rn = runs[run0 + r];
+            const int dst_row = rn.y & 0xffff, len = rn.y >> 16;
+            bulk_g2s((unsigned)__cvta_generic_to_shared(sV + (size_t)dst_row * kt), V + (size_t)rn.x * ldv, (unsigned)len * kt * 16, bar_s);
+        }
+    } else {
+        const int* cols = tile_cols + h0.x;
+        for (int dcol = tid; dcol < ncols; dcol += nth)
+            bulk_g2s((unsigned)__cvta_generic_to_shared(sV + (size_t)dcol * kt), V + (size_t)cols[dcol] * ldv, (unsigned)kt * 16, bar_s);
+    }
+    const int gc = tid % GC, t = tid / GC;
+    const int sgi = t / R, ri = t - sgi * R;
+    int start = 0, end = 0, zrow = -1;
+    if (sgi < nseg) {
+        int off = 0;
+        for (int s = 0; s < sgi; ++s) off += d[2 + s].w;
+        const int4 sg = d[2 + sgi];
+        if (ri < sg.y) {
+            zrow = sg.x + ri;
+            start = off + rowptr[zrow] - sg.z;
+            end = off + rowptr[zrow + 1] - sg.z;
+        }
+    }
+    {
+        unsigned done = 0, spins = 0;
+        while (!done) {
+            if (++spins > (1u << 26)) asm volatile("trap;");
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done)
+                         : "r"(bar_s), "r"(0)
+                         : "memory");
+        }
+    }
+    double2 acc[2][CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[0][j] = acc[1][j] = make_double2(0.0, 0.0);
+    if constexpr (PRE) {
+        // combine the raw term values ONCE per nonzero (the 8 lanes of a row would each repeat these 2 p DFMA): every thread
+        // takes up to 4 nonzeros into registers, then the coefficients c = sum_i c_i a_i are written over the front of the slice
+        double2 m[4];
+        int cnt = 0;
+        for (int e = tid; e < nnz && cnt < 4; e += nth, ++cnt) {
+            double v[VW];
+#pragma unroll
+            for (int u = 0; u < VW; u += 2) {
+                const double2 w = *(const double2*)(sA + (size_t)e * VW + u);
+                v[u] = w.x;
+                v[u + 1] = w.y;
+            }
+            m[cnt] = combine<VW, false>(v, [&](int i) { return cp.c[i]; });
+        }
+        __syncthreads();
+        cnt = 0;
+        for (int e = tid; e < nnz && cnt < 4; e += nth, ++cnt) ((double2*)(smem_raw + oA))[e] = m[cnt];
+        __syncthreads();
+    }
+    auto load_vals_s = [&](int idx, double (&v)[VW]) {
+        if constexpr (PRE) {
+            const double2 w = ((const double2*)sA)[idx];
+            v[0] = w.x;
+            v[1] = w.y;
+        } else {
+            const double* vp = sA + (size_t)idx * VW;
+#pragma unroll
+            for (int u = 0; u < VW; u += 2) {
+                const double2 w = *(const double2*)(vp + u);
+                v[u] = w.x;
+                v[u + 1] = w.y;
+            }
+        }
+    };
+    auto coef_of = [&](const double (&v)[VW]) {
+        if constexpr (PRE) return make_double2(v[0], v[1]);
+        else return combine<VW, false>(v, [&](int i) { return cp.c[i]; });
+    };
+    auto load_x = [&](int li, double2 (&x)[CPT], int ncp) {
+        const double2* xr = sV + li * kt + gc;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+            if (j < ncp) x[j] = xr[j * GC];
+    };
+    auto fma_one = [&](const double (&v)[VW], const double2 (&x)[CPT], double2 (&ac)[CPT], int ncp) {
+        const double2 m = coef_of(v);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+            if (j < ncp) cfma(ac[j], m, x[j]);
+    };
+    const bool pair = CPT == 3 && kt <= 20;  // two consecutive nonzeros share the half-empty third piece of their V rows
+    double2 acc3 = make_double2(0.0, 0.0);
+    constexpr int UN = CPT >= 3 ? 2 : 4;
+    int base = start;
+    if (pair) {
+#pragma unroll 2
+        for (; base + 2 <= end; base += 2) {
+            const int la = (int)sL[base], lb = (int)sL[base + 1];
+            double va[VW], vb[VW];
+            double2 xa[CPT], xb[CPT];
+            load_vals_s(base, va);
+            load_vals_s(base + 1, vb);
+            load_x(la, xa, 2);
+            load_x(lb, xb, 2);
+            const double2 x3 = sV[((gc < 4) ? la : lb) * kt + 16 + (gc & 3)];
+            const double2 ma = coef_of(va), mb = coef_of(vb);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                cfma(acc[0][j], ma, xa[j]);
+                cfma(acc[1][j], mb, xb[j]);
+            }
+            cfma(acc3, (gc < 4) ? ma : mb, x3);
+        }
+    } else {
+        for (; base + UN <= end; base += UN) {
+            int li[UN];
+            double v[UN][VW];
+            double2 x[UN][CPT];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) li[u] = (int)sL[base + u];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                load_vals_s(base + u, v[u]);
+                load_x(li[u], x[u], CPT);
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) fma_one(v[u], x[u], acc[u & 1], CPT);
+        }
+    }
+    for (; base < end; ++base) {
+        double v[VW];
+        double2 x[CPT];
+        load_vals_s(base, v);
+        load_x((int)sL[base], x, CPT);
+        fma_one(v, x, acc[0], CPT);
+    }
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        acc[0][j].x += acc[1][j].x;
+        acc[0][j].y += acc[1][j].y;
+    }
+    if (pair) {
+        const double tx = __shfl_down_sync(0xffffffffu, acc3.x, 4), ty = __shfl_down_sync(0xffffffffu, acc3.y, 4);
+        if (gc < 4) {
+            acc[0][2].x += acc3.x + tx;
+            acc[0][2].y += acc3.y + ty;
+        }
+    }
+    if (zrow >= 0) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int c = gc + j * GC;
+            if (c < kt) Z[(size_t)zrow * ldz + c] = acc[0][j];
+        }
+    }
+}
+
+// Host side of the two-dimensional tiles: line length from the pattern, tiles = S segments x R rows, per tile the sorted distinct
+// columns (runs of consecutive columns = bulk copies), tile-local 16-bit indices stored tile by tile.
+static int spmf_build_tiles2d(const nepb_spmf* h) {
+    nepb_spmf::TileSet2D& T = h->tiling2d;
+    if (T.state) return T.state;
+    T.state = -1;
+    const int64_t n = h->n;
+    const int32_t* rp = h->h_rowptr;
+    const int32_t* ci = h->h_colind;
+    const int S = std::max(1, std::min(8, getenv("NEPB_SPMM_2D_S") ? atoi(getenv("NEPB_SPMM_2D_S")) : 4));
+    const int R = std::max(1, std::min(32, getenv("NEPB_SPMM_2D_R") ? atoi(getenv("NEPB_SPMM_2D_R")) : 8));
+    if (S * R * 8 > 256 || n < 64) return -1;
+    // dominant column offset ("grid line length") from a sample of rows
+    int64_t line = 0;
+    {
+        std::vector<std::pair<int64_t, int64_t>> offs;
+        const int64_t step = std::max<int64_t>(1, n / 4096);
+        int64_t total = 0;
+        std::vector<int64_t> d;
+        for (int64_t r = 0; r < n; r += step)
+            for (int32_t e = rp[r]; e < rp[r + 1]; ++e) {
+                ++total;
+                const int64_t a = std::llabs((long long)ci[e] - (long long)r);
+                if (a >= 32) d.push_back(a);
+            }
+        std::sort(d.begin(), d.end());
+        int64_t best = 0;
+        for (size_t i = 0; i < d.size();) {
+            size_t j = i;
+            while (j < d.size() && d[j] == d[i]) ++j;
+            if ((int64_t)(j - i) > best) {
+                best = (int64_t)(j - i);
+                line = d[i];
+            }
+            i = j;
+        }
+        if (getenv("NEPB_SPMM_2D_LINE")) line = atoll(getenv("NEPB_SPMM_2D_LINE"));
+        else if (best * 25 < total) return -1;  // no offset carries >= 4 % of the nonzeros (a 21-point stencil: 9.5 %): keep the 1D tiles
+        if (line < 2 * R || line * S > n) return -1;
+    }
+    // tiles: whole super-blocks of S lines first, the remaining rows as S consecutive segments
+    struct Seg {
+        int64_t row0;
+        int rows;
+    };
+    std::vector<Seg> segs;  // S per tile (rows = 0: unused)
+    const int64_t sb = (int64_t)S * line, nsb = n / sb;
+    for (int64_t b = 0; b < nsb; ++b)
+        for (int64_t i0 = 0; i0 < line; i0 += R)
+            for (int s = 0; s < S; ++s) segs.push_back({b * sb + s * line + i0, (int)std::min<int64_t>(R, line - i0)});
+    for (int64_t r = nsb * sb; r < n; r += (int64_t)S * R)
+        for (int s = 0; s < S; ++s) {
+            const int64_t r0 = r + (int64_t)s * R;
+            segs.push_back({std::min(r0, n), (int)std::max<int64_t>(0, std::min<int64_t>(R, n - r0))});
+        }
+    const int64_t ntiles = (int64_t)segs.size() / S;
+    if (ntiles >= (int64_t)1 << 30) return -1;
+    const int DS = 2 + S;
+    std::vector<int4> desc((size_t)ntiles * DS);
+    constexpr int64_t CHUNK = 512;
+    const int64_t nchunks = (ntiles + CHUNK - 1) / CHUNK;
+    std::vector<std::vector<int32_t>> ccols(nchunks);
+    std::vector<std::vector<int2>> cruns(nchunks);
+    std::vector<std::vector<uint16_t>> clidx(nchunks);
+    int bad = 0, maxc = 0, maxz = 0;
+#pragma omp parallel
+    {
+        std::vector<int32_t> stamp((size_t)n, -1), local((size_t)n, 0), cur;
+#pragma omp for schedule(dynamic, 1) reduction(| : bad) reduction(max : maxc) reduction(max : maxz)
+        for (int64_t ch = 0; ch < nchunks; ++ch) {
+            for (int64_t t = ch * CHUNK; t < std::min(ntiles, (ch + 1) * CHUNK); ++t) {
+                cur.clear();
+                int nnz = 0, nseg = 0;
+                for (int s = 0; s < S; ++s) {
+                    const Seg& g = segs[(size_t)t * S + s];
+                    if (g.rows > 0) nseg = s + 1;
+                    for (int64_t r = g.row0; r < g.row0 + g.rows; ++r)
+                        for (int32_t e = rp[r]; e < rp[r + 1]; ++e) {
+                            ++nnz;
+                            if (stamp[ci[e]] != (int32_t)t) {
+                                stamp[ci[e]] = (int32_t)t;
+                                cur.push_back(ci[e]);
+                            }
+                        }
+                }
+                if (cur.size() > 4096) bad |= 1;
+                std::sort(cur.begin(), cur.end());
+                for (size_t u = 0; u < cur.size(); ++u) local[cur[u]] = (int32_t)u;
+                const int run_first = (int)cruns[ch].size();
+                for (size_t u = 0; u < cur.size();) {
+                    size_t v = u + 1;
+                    while (v < cur.size() && cur[v] == cur[v - 1] + 1 && v - u < 32767) ++v;
+                    cruns[ch].push_back(make_int2(cur[u], (int)u | ((int)(v - u) << 16)));
+                    u = v;
+                }
+                int4* dd = desc.data() + (size_t)t * DS;
+                dd[0] = make_int4((int)ccols[ch].size(), (int)cur.size(), run_first, (int)cruns[ch].size() - run_first);
+                dd[1] = make_int4((int)clidx[ch].size(), nnz, nseg, 0);
+                for (int s = 0; s < S; ++s) {
+                    const Seg& g = segs[(size_t)t * S + s];
+                    dd[2 + s] = make_int4((int)g.row0, g.rows, g.rows ? rp[g.row0] : 0, g.rows ? rp[g.row0 + g.rows] - rp[g.row0] : 0);
+                    for (int64_t r = g.row0; r < g.row0 + g.rows; ++r)
+                        for (int32_t e = rp[r]; e < rp[r + 1]; ++e) clidx[ch].push_back((uint16_t)local[ci[e]]);
+                }
+                while (clidx[ch].size() % 8) clidx[ch].push_back(0);
+                ccols[ch].insert(ccols[ch].end(), cur.begin(), cur.end());
+                maxc = std::max(maxc, (int)cur.size());
+                maxz = std::max(maxz, nnz);
+            }
+        }
+    }
+    if (bad) return -1;
+    std::vector<int32_t> cols;
+    std::vector<int2> runs;
+    std::vector<uint16_t> lidx;
+    for (int64_t ch = 0; ch < nchunks; ++ch) {
+        const int coff = (int)cols.size(), roff = (int)runs.size();
+        const size_t loff = lidx.size();
+        if (loff + clidx[ch].size() >= (size_t)std::numeric_limits<int32_t>::max() || cols.size() + ccols[ch].size() >= (size_t)std::numeric_limits<int32_t>::max())
+            return -1;
+        for (int64_t t = ch * CHUNK; t < std::min(ntiles, (ch + 1) * CHUNK); ++t) {
+            desc[(size_t)t * DS].x += coff;
+            desc[(size_t)t * DS].z += roff;
+            desc[(size_t)t * DS + 1].x += (int)loff;
+        }
+        cols.insert(cols.end(), ccols[ch].begin(), ccols[ch].end());
+        runs.insert(runs.end(), cruns[ch].begin(), cruns[ch].end());
+        lidx.insert(lidx.end(), clidx[ch].begin(), clidx[ch].end());
+    }
+    auto up = [&](auto& buf, const auto& vec) {
+        cudaError_t e = buf.alloc(std::max<size_t>(vec.size(), 1));
+        if (e == cudaSuccess && !vec.empty()) e = cudaMemcpy(buf.p, vec.data(), sizeof(vec[0]) * vec.size(), cudaMemcpyHostToDevice);
+        return e;
+    };
+    cudaError_t e = up(T.desc, desc);
+    if (e == cudaSuccess) e = up(T.cols, cols);
+    if (e == cudaSuccess) e = up(T.lidx, lidx);
+    if (e == cudaSuccess) e = up(T.runs, runs);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        T.desc.release();
+        T.cols.release();
+        T.lidx.release();
+        T.runs.release();
+        return -1;
+    }
+    T.S = S;
+    T.R = R;
+    T.line = (int)line;
+    T.ntiles = ntiles;
+    T.max_cols = maxc;
+    T.max_nnz = maxz;
+    T.state = 1;
+    return 1;
+}
+
+static size_t tma2d_smem_bytes(const nepb_spmf::TileSet2D& T, int kt, int vw) {
+    return (size_t)T.max_cols * kt * 16 + (size_t)T.max_nnz * vw * 8 + (size_t)((T.max_nnz + 7) & ~7) * 2 + 16;
+}
+
+// returns 1 when the product was launched on the two-dimensional tiles
+template <int VW>
+static int launch_tma2d_vw(const nepb_spmf* h, const nepb_spmf::TileSet2D& T, int kt, int ldv, int ldz, const double2* V, double2* Z, const CoefP& cp) {
+    const size_t smem = tma2d_smem_bytes(T, kt, VW);
+    // one combine pass per tile instead of 8 redundant ones per nonzero: measured slower at every width (k = 20: 421 vs 373 us,
+    // profiles/r2_spmm_2d.txt), kept selectable (NEPB_SPMM_2D_PRE=1)
+    const bool pre = getenv("NEPB_SPMM_2D_PRE") && atoi(getenv("NEPB_SPMM_2D_PRE")) != 0 && T.max_nnz <= 4 * T.S * T.R * 8;
+#define NEPB_TMA2D(CPT_)                                                                                                              \
+    do {                                                                                                                              \
+        static size_t attr_done[16] = {0};                                                                                            \
+        int dev = 0;                                                                                                                  \
+        cudaGetDevice(&dev);                                                                                                          \
+        if (smem > 48 * 1024 && smem > attr_done[dev & 15]) {                                                                         \
+            NEPB_CUDA(cudaFuncSetAttribute(spmm_tma2d_kernel<VW, CPT_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            NEPB_CUDA(cudaFuncSetAttribute(spmm_tma2d_kernel<VW, CPT_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_done[dev & 15] = smem;                                                                                               \
+        }                                                                                                                             \
+        if (pre)                                                                                                                      \
+            NEPB_LAUNCH((spmm_tma2d_kernel<VW, CPT_, true>), (unsigned)T.ntiles, T.S * T.R * 8, smem, kt, ldv, ldz, T.max_cols, T.max_nnz, T.S, \
+                        T.R, T.desc.p, T.runs.p, T.cols.p, h->d_rowptr.p, T.lidx.p, h->d_vals.p, V, Z, cp);                            \
+        else                                                                                                                          \
+            NEPB_LAUNCH((spmm_tma2d_kernel<VW, CPT_, false>), (unsigned)T.ntiles, T.S * T.R * 8, smem, kt, ldv, ldz, T.max_cols, T.max_nnz, T.S, \
+                        T.R, T.desc.p, T.runs.p, T.cols.p, h->d_rowptr.p, T.lidx.p, h->d_vals.p, V, Z, cp);                            \
+    } while (0)
+    if (kt <= 8) NEPB_TMA2D(1);
+    else if (kt <= 16) NEPB_TMA2D(2);
+    else if (kt <= 24) NEPB_TMA2D(3);
+    else NEPB_TMA2D(4);
+#undef NEPB_TMA2D
+    return 1;
+}
+
 // the TMA-staged tiled product (default for 5..32 columns when the operands allow bulk copies); 0 = does not apply
 static int launch_tma(const nepb_spmf* h, bool diag, int kt, int ldv, int ldz, const double2* V, double2* Z, const CoefP& cp,
                       const double2* cdiag) {
     const bool enabled = !(getenv("NEPB_SPMM_TMA") && atoi(getenv("NEPB_SPMM_TMA")) == 0);  // read per call: tests / tools toggle it
     if (!enabled || kt < 5 || getenv("NEPB_SPMM_CFG") || getenv("NEPB_SPMM_BULK")) return 0;
+    {
+        const int v = getenv("NEPB_SPMM_DBG") ? atoi(getenv("NEPB_SPMM_DBG")) : 0;  // read per call (tools toggle it)
+        static int last = 0;
+        if (v != last) {
+            cudaMemcpyToSymbol(g_spmm_dbg, &v, sizeof(int));
+            last = v;
+        }
+    }
     if (((uintptr_t)V & 15) != 0) return 0;  // bulk copies need 16-byte aligned sources (rows are ldv*16 bytes apart)
+    // two-dimensional tiles when the pattern has a dominant line length (SCALAR mode, real values, even term count)
+    const bool want2d = !(getenv("NEPB_SPMM_2D") && atoi(getenv("NEPB_SPMM_2D")) == 0);  // read per call: tests / tools toggle it
+    if (want2d && !diag && !h->is_complex && (h->vw == 2 || h->vw == 4) && !getenv("NEPB_SPMM_TILE_ROWS") && !getenv("NEPB_SPMM_GC") &&
+        spmf_build_tiles2d(h) == 1 && tma2d_smem_bytes(h->tiling2d, kt, h->vw) <= 200 * 1024) {
+        const int rc2 = h->vw == 2 ? launch_tma2d_vw<2>(h, h->tiling2d, kt, ldv, ldz, V, Z, cp) : launch_tma2d_vw<4>(h, h->tiling2d, kt, ldv, ldz, V, Z, cp);
+        if (rc2 == 1) {
+            NEPB_LAUNCH_CHECK();
+            return 1;
+        }
+        if (rc2 < 0) return rc2;
+    }
     // measured on C4 (profiles/r2_spmm_variants.txt): 16-row tiles (twice the resident CTAs = pipeline stages) beat 32-row
     // tiles at every width, and 8 lanes per row beat 4 (fewer wavefronts, but too few warps to hide the latencies)
     int which = 1;
