@@ -714,14 +714,17 @@ __global__ void __launch_bounds__(256, 2) lu_schur_dmma_kernel(LuDev d, const in
 // (re / im planes; L chunk [k][row] pitch 68, U chunk [column][k] pitch 20: conflict-free copies and fragment reads).
 // item.w = column tiles | kind << 8 | cap << 16 (strips: kind 1 / 2, cap = pivot columns of the next link).
 // ---------------------------------------------------------------------------------------------
-constexpr int SR_KC = 16, SR_ST = 3, SR_LLD = SCHUR_T + 4, SR_ULD = SR_KC + 4;
-constexpr int SR_STAGE = 2 * SR_KC * SR_LLD + 2 * SCHUR_T * SR_ULD;  // doubles
-constexpr size_t SR_SMEM = (size_t)SR_ST * SR_STAGE * sizeof(double);
-// MT x NT MMA tiles per warp: (2, 4) full 64 x 64 tile, (1, 4) row strip (32 x 64), (2, 2) column strip (64 x 32)
-template <int MT, int NT>
+constexpr int SR_KC = 16, SR_LLD = SCHUR_T + 4, SR_ULD = SR_KC + 4;
+__host__ __device__ constexpr int sr_stage_doubles(int tn) { return 2 * SR_KC * SR_LLD + 2 * tn * SR_ULD; }
+constexpr size_t sr_smem(int tn, int st) { return (size_t)st * sr_stage_doubles(tn) * sizeof(double); }
+// MT x NT MMA tiles per warp, WM x WN warps, ST ring stages, TNS = column-tile step of the items.
+// 256 threads (4 x 2 warps), 3 stages: (2, 4) full 64 x 64 tile, (1, 4) row strip (32 x 64), (2, 2) column strip (64 x 32).
+// 128 threads (4 x 1 warps), 2 stages, 4 CTAs per SM: (2, 4) 64 x 32 tile (full and column strip), (1, 4) row strip (32 x 32).
+template <int MT, int NT, int WM, int WN, int ST, int TNS>
 __device__ __forceinline__ void schur_ring_body(const LuDev& d, const int4 it, double2* __restrict__ fronts, double* srm) {
     const int s = it.x, i0 = it.y, jfirst = it.z, ntiles = it.w & 0xff;
-    constexpr int TM = 4 * 8 * MT, TN = 2 * 8 * NT;  // rows / columns of the CTA tile
+    constexpr int TM = WM * 8 * MT, TN = WN * 8 * NT;  // rows / columns of the CTA tile
+    constexpr int NTH = 32 * WM * WN, SR_ST = ST, SR_STAGE = sr_stage_doubles(TNS);
     const int b = blockIdx.y;
     const int nf = d.ld[s], np = d.np[s], ncb = d.nf[s] - np, kb = d.kback[s];
     const int ktot = kb + np, nk = (ktot + SR_KC - 1) / SR_KC;
@@ -730,17 +733,17 @@ __device__ __forceinline__ void schur_ring_body(const LuDev& d, const int4 it, d
     const int dbg = g_schur_dbg;
     const int cap = (it.w >> 16) & 0xff;  // strips: the next link's pivot columns (<= 32)
     const int th = (MT == 1) ? min(cap, ncb - i0) : min(TM, ncb - i0);
-    auto tile_w = [&](int j0) { return (NT == 2) ? min(cap, ncb - j0) : min(TN, ncb - j0); };
+    auto tile_w = [&](int j0) { return (((it.w >> 8) & 0xff) == 2) ? min(cap, ncb - j0) : min(TN, ncb - j0); };
     auto load = [&](int i) {
         if (dbg & 8) return;
         const int q = i / nk, kc = i - q * nk;
-        const int j0 = jfirst + q * SCHUR_T, tw = tile_w(j0);
+        const int j0 = jfirst + q * TNS, tw = tile_w(j0);
         double* sLr = srm + (size_t)(i % SR_ST) * SR_STAGE;
         double* sLi = sLr + SR_KC * SR_LLD;
         double* sUr = sLi + SR_KC * SR_LLD;
-        double* sUi = sUr + SCHUR_T * SR_ULD;
+        double* sUi = sUr + TNS * SR_ULD;
 #pragma unroll
-        for (int idx = tid; idx < SR_KC * TM; idx += 256) {  // L21 chunk: TM rows x 16 k, rows fastest (column-major front)
+        for (int idx = tid; idx < SR_KC * TM; idx += NTH) {  // L21 chunk: TM rows x 16 k, rows fastest (column-major front)
             const int r = idx % TM, kk = idx / TM;
             const int t = kc * SR_KC + kk;
             const bool ok = r < th && t < ktot;
@@ -749,7 +752,7 @@ __device__ __forceinline__ void schur_ring_body(const LuDev& d, const int4 it, d
             cp_async8z(sLi + kk * SR_LLD + r, src + 1, ok);
         }
 #pragma unroll
-        for (int idx = tid; idx < SR_KC * TN; idx += 256) {  // U12 chunk: 16 k x TN columns, k fastest
+        for (int idx = tid; idx < SR_KC * TN; idx += NTH) {  // U12 chunk: 16 k x TN columns, k fastest
             const int kk = idx % SR_KC, c = idx / SR_KC;
             const int t = kc * SR_KC + kk;
             const bool ok = c < tw && t < ktot;
@@ -764,7 +767,7 @@ __device__ __forceinline__ void schur_ring_body(const LuDev& d, const int4 it, d
         cp_async_commit();
     }
     const int ar = lane >> 2, ak = lane & 3;
-    const int wr = (warp & 3) * 8 * MT, wc = (warp >> 2) * 8 * NT;
+    const int wr = (warp % WM) * 8 * MT, wc = (warp / WM) * 8 * NT;
     double cr[MT][NT][2], ci[MT][NT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
@@ -776,13 +779,13 @@ __device__ __forceinline__ void schur_ring_body(const LuDev& d, const int4 it, d
         __syncthreads();  // chunk i has landed for everybody, and everybody is done with the stage that is refilled now
         if (i + SR_ST - 1 < total) load(i + SR_ST - 1);
         cp_async_commit();
-        const int j0 = jfirst + q * SCHUR_T, tw = tile_w(j0);
+        const int j0 = jfirst + q * TNS, tw = tile_w(j0);
         const bool active = wr < th && wc < tw;  // warp-uniform
         if (active && !(dbg & 1)) {
             const double* sLr = srm + (size_t)(i % SR_ST) * SR_STAGE;
             const double* sLi = sLr + SR_KC * SR_LLD;
             const double* sUr = sLi + SR_KC * SR_LLD;
-            const double* sUi = sUr + SCHUR_T * SR_ULD;
+            const double* sUi = sUr + TNS * SR_ULD;
 #pragma unroll
             for (int k4 = 0; k4 < SR_KC; k4 += 4) {
                 double a_r[MT], a_i[MT], na_i[MT];
@@ -833,14 +836,23 @@ __device__ __forceinline__ void schur_ring_body(const LuDev& d, const int4 it, d
     }
 }
 
-// item.w = column tiles | kind << 8: kind 0 full 64 x 64 tiles, 1 row strip (32-row tiles), 2 column strip (32-column tiles)
+// item.w = column tiles | kind << 8 | cap << 16: kind 0 full tiles, 1 row strip (32-row tiles), 2 column strip (<= 32 columns)
 __global__ void __launch_bounds__(256, 2) lu_schur_ring_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts) {
     extern __shared__ double srm[];
     const int4 it = items[blockIdx.x];
     const int kind = (it.w >> 8) & 0xff;
-    if (kind == 0) schur_ring_body<2, 4>(d, it, fronts, srm);
-    else if (kind == 1) schur_ring_body<1, 4>(d, it, fronts, srm);
-    else schur_ring_body<2, 2>(d, it, fronts, srm);
+    if (kind == 0) schur_ring_body<2, 4, 4, 2, 3, 64>(d, it, fronts, srm);
+    else if (kind == 1) schur_ring_body<1, 4, 4, 2, 3, 64>(d, it, fronts, srm);
+    else schur_ring_body<2, 2, 4, 2, 3, 64>(d, it, fronts, srm);
+}
+// 128 threads, 64 x 32 tiles, two stages: four CTAs per SM, so that the operand loads / epilogues of three CTAs run under the
+// MMA phase of the fourth
+__global__ void __launch_bounds__(128, 4) lu_schur_ring32_kernel(LuDev d, const int4* __restrict__ items, double2* __restrict__ fronts) {
+    extern __shared__ double srm[];
+    const int4 it = items[blockIdx.x];
+    const int kind = (it.w >> 8) & 0xff;
+    if (kind == 1) schur_ring_body<1, 4, 4, 1, 2, 32>(d, it, fronts, srm);
+    else schur_ring_body<2, 4, 4, 1, 2, 32>(d, it, fronts, srm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1509,6 +1521,8 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
     static const bool use_ring = !(getenv("NEPB_LU_SCHUR_RING") && atoi(getenv("NEPB_LU_SCHUR_RING")) == 0) && !getenv("NEPB_LU_SCHUR_SIMPLE");
     static const int window = std::max(1, std::min(4, getenv("NEPB_LU_WINDOW") ? atoi(getenv("NEPB_LU_WINDOW")) : 4));
     sd->schur_ring = use_ring && S.max_np <= 32;
+    static const int ring_tn = (getenv("NEPB_LU_SCHUR_TN") && atoi(getenv("NEPB_LU_SCHUR_TN")) == 64) ? 64 : 32;
+    sd->schur_tn = sd->schur_ring ? ring_tn : SCHUR_T;
     if (sd->schur_ring && window > 1)
         for (int s = 0; s < ns; ++s) {
             if (!S.in_place_child[s] || S.has_in_place_child[s]) continue;  // not the first link of a chain
@@ -1588,6 +1602,7 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
                 pn_items.push_back(make_int4(s, 0, t0, 0));
                 pn_items.push_back(make_int4(s, 1, t0, 0));
             }
+            const int tn = sd->schur_tn;  // column-tile step of the Schur items
             if (defer[s]) {
                 // deferred link: only the strip that becomes the next link's pivot block and panels (its first npn columns, all
                 // rows; its first npn rows, the remaining columns)
@@ -1597,15 +1612,17 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
                     sp_items.push_back(make_int4(s, i0, 0, 1 | (2 << 8) | (npn << 16)));
                 }
                 // row strip: 32 x 64 tiles over the columns >= npn (the corner belongs to the column strip)
-                for (int j0 = npn; j0 < ncb; j0 += SCHUR_T) sc_items.push_back(make_int4(s, 0, j0, 1 | (1 << 8) | (npn << 16)));
-                for (int j0 = npn; j0 < ncb; j0 += SCHUR_T * SCHUR_GROUP)
-                    sp_items.push_back(make_int4(s, 0, j0, std::min(SCHUR_GROUP, (ncb - j0 + SCHUR_T - 1) / SCHUR_T) | (1 << 8) | (npn << 16)));
+                const int grp = SCHUR_GROUP * (SCHUR_T / tn);  // column tiles per grouped item: the same 128 columns for both widths
+                for (int j0 = npn; j0 < ncb; j0 += tn) sc_items.push_back(make_int4(s, 0, j0, 1 | (1 << 8) | (npn << 16)));
+                for (int j0 = npn; j0 < ncb; j0 += tn * grp)
+                    sp_items.push_back(make_int4(s, 0, j0, std::min(grp, (ncb - j0 + tn - 1) / tn) | (1 << 8) | (npn << 16)));
             } else {
-                for (int j0 = 0; j0 < ncb; j0 += SCHUR_T)
+                const int grp = SCHUR_GROUP * (SCHUR_T / tn);
+                for (int j0 = 0; j0 < ncb; j0 += tn)
                     for (int i0 = 0; i0 < ncb; i0 += SCHUR_T) sc_items.push_back(make_int4(s, i0, j0, 1));
-                for (int j0 = 0; j0 < ncb; j0 += SCHUR_T * SCHUR_GROUP)
+                for (int j0 = 0; j0 < ncb; j0 += tn * grp)
                     for (int i0 = 0; i0 < ncb; i0 += SCHUR_T)
-                        sp_items.push_back(make_int4(s, i0, j0, std::min(SCHUR_GROUP, (ncb - j0 + SCHUR_T - 1) / SCHUR_T)));
+                        sp_items.push_back(make_int4(s, i0, j0, std::min(grp, (ncb - j0 + tn - 1) / tn)));
             }
             (in_tail[s] ? sfr_tail : sfr_items).push_back(s);
             if (ncb > SOLVE_BIG)
@@ -1739,7 +1756,8 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
         sd->smem_schur_dmma = ((size_t)2 * mpad * SD_LLD + (size_t)2 * SD_UBUF) * sizeof(double);
         const char* e = getenv("NEPB_LU_SCHUR_DMMA");
         sd->schur_dmma = mnp <= 32 && !(e && atoi(e) == 0) && !getenv("NEPB_LU_SCHUR_SIMPLE");
-        cudaFuncSetAttribute(lu_schur_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM + 64 * 1024);
+        cudaFuncSetAttribute(lu_schur_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sr_smem(64, 3) + 64 * 1024);
+        cudaFuncSetAttribute(lu_schur_ring32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sr_smem(32, 2) + 64 * 1024);
         if (getenv("NEPB_LU_SCHUR_DBG")) {
             const int v = atoi(getenv("NEPB_LU_SCHUR_DBG"));
             cudaMemcpyToSymbol(g_schur_dbg, &v, sizeof(int));
@@ -1888,10 +1906,15 @@ static void factor_level_schur(nepb_lu* lu, int l) {
     // few shifts in flight: one tile per CTA (twice the CTAs, half the time per CTA); otherwise two column tiles per CTA share
     // the L21 tile
     if (L.sc_count && sd->schur_ring) {
-        const bool one = (int64_t)nb * L.sp_count < 2 * sm_count();
+        static const int force_one = getenv("NEPB_LU_SCHUR_ONE") ? atoi(getenv("NEPB_LU_SCHUR_ONE")) : -1;
+        const bool one = force_one >= 0 ? force_one != 0 : (int64_t)nb * L.sp_count < 2 * sm_count();
         static const size_t pad = getenv("NEPB_LU_SCHUR_PAD") ? (size_t)atoi(getenv("NEPB_LU_SCHUR_PAD")) * 1024 : 0;  // occupancy experiments
-        NEPB_LAUNCH(lu_schur_ring_kernel, dim3(one ? L.sc_count : L.sp_count, nb), 256, SR_SMEM + pad, sd->dev,
-                    one ? sd->sc_items.p + L.sc_begin : sd->sp_items.p + L.sp_begin, F);
+        if (sd->schur_tn == 32)
+            NEPB_LAUNCH(lu_schur_ring32_kernel, dim3(one ? L.sc_count : L.sp_count, nb), 128, sr_smem(32, 2) + pad, sd->dev,
+                        one ? sd->sc_items.p + L.sc_begin : sd->sp_items.p + L.sp_begin, F);
+        else
+            NEPB_LAUNCH(lu_schur_ring_kernel, dim3(one ? L.sc_count : L.sp_count, nb), 256, sr_smem(64, 3) + pad, sd->dev,
+                        one ? sd->sc_items.p + L.sc_begin : sd->sp_items.p + L.sp_begin, F);
         return;
     }
     static const bool cinit = (getenv("NEPB_LU_SCHUR_CINIT") && atoi(getenv("NEPB_LU_SCHUR_CINIT")) != 0);

@@ -79,6 +79,7 @@ struct LuSymbolicDev {
     DevBuf<uint8_t> in_place, has_ip;
     DevBuf<int32_t> kback;
     bool schur_ring = false;
+    int schur_tn = 64;  // column-tile step of the Schur items
     DevBuf<int32_t> bw_slot, xsplit, sfr_items, chain_fronts;
     DevBuf<int2> fc_items, bc_items;
     int part_slots = 0;
