@@ -675,8 +675,8 @@ def main():
                             "peak_source": peak_src, "kernel": kernel_name,
                             "algorithmic_bytes_per_launch": head["bytes"], "us_per_launch": head["ms"] * 1e3}
         line["spmm"] = {str(k): {kk: v[kk] for kk in ("ms", "gbs", "frac", "bytes", "e2e_ms", "parity_relerr")} for k, v in spmm.items()}
-        line["spmm_kernels"] = {"1": "spmm_fused_kernel", "8": "spmm_tma_kernel<CPT=1,GC=8> (16-row tiles, TMA bulk staging)",
-                                "20": "spmm_tma_kernel<CPT=3,GC=8> (16-row tiles, TMA bulk staging)"}
+        line["spmm_kernels"] = {"1": "spmm_fused_kernel", "8": "spmm_tma2d_kernel<CPT=1> (2D tiles of 4 x 8 rows, TMA bulk staging)",
+                                "20": "spmm_tma2d_kernel<CPT=3> (2D tiles of 4 x 8 rows, TMA bulk staging)"}
         line["spmm_general"] = general
         if dist.rank == 0:
             line["wep"] = bench_wep(args, peak)
