@@ -239,10 +239,10 @@ __global__ void __launch_bounds__(128) block_gemm_dmma_kernel(int64_t rows, int 
 // (B) doubles so that the 16 lanes of a 64-bit shared-memory phase hit 16 different bank pairs.  Out-of-range rows / columns /
 // k are zero-filled by the copy itself; column tiles that lie completely beyond q are skipped (CTA-uniform).
 // ---------------------------------------------------------------------------------------------
-constexpr int ZT_M = 128, ZT_NT = 7, ZT_N = 8 * ZT_NT, ZT_K = 16, ZT_ST = 3;
+constexpr int ZT_NT = 7, ZT_N = 8 * ZT_NT, ZT_K = 16, ZT_ST = 3;
 constexpr int ZA_LD = ZT_K + 4, ZB_LD = 64 + 4;
-constexpr int ZT_STAGE_DOUBLES = 2 * ZT_M * ZA_LD + 2 * ZT_K * ZB_LD;
-constexpr size_t ZT_SMEM = (size_t)ZT_ST * ZT_STAGE_DOUBLES * 8;
+__host__ __device__ constexpr int zt_stage_doubles(int zm) { return 2 * zm * ZA_LD + 2 * ZT_K * ZB_LD; }
+__host__ __device__ constexpr size_t zt_smem(int zm) { return (size_t)ZT_ST * zt_stage_doubles(zm) * 8; }
 
 __device__ __forceinline__ void cp_async_8z(double* smem_dst, const double* gsrc, bool valid) {
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -250,7 +250,10 @@ __device__ __forceinline__ void cp_async_8z(double* smem_dst, const double* gsrc
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gsrc), "r"(sz));
 }
 
-__global__ void __launch_bounds__(256, 1) block_gemm_dmma2_kernel(int64_t rows, int ka, int q, int cols_per_cta, const double2* __restrict__ A,
+// ZT_M rows per CTA = 16 per warp: 128 (8 warps, one CTA per SM) or 64 (4 warps, two CTAs per SM: the ring waits / barriers of
+// one CTA run under the MMAs of the other)
+template <int ZT_M>
+__global__ void __launch_bounds__(2 * ZT_M, 128 / ZT_M) block_gemm_dmma2_kernel(int64_t rows, int ka, int q, int cols_per_cta, const double2* __restrict__ A,
                                                                   int lda, const double2* __restrict__ C /* row-major ka x q */,
                                                                   double2* __restrict__ Y, int ldy) {
     extern __shared__ double zsm[];
@@ -260,6 +263,7 @@ __global__ void __launch_bounds__(256, 1) block_gemm_dmma2_kernel(int64_t rows, 
     const int ncols = min(cols_per_cta, q - col0);  // columns of this CTA (<= 56)
     const int nt_act = (ncols + 7) / 8;
     const int nk = (ka + ZT_K - 1) / ZT_K;
+    constexpr int ZT_STAGE_DOUBLES = zt_stage_doubles(ZT_M), NTH = 2 * ZT_M;
     auto stage_ptr = [&](int st) { return zsm + (size_t)st * ZT_STAGE_DOUBLES; };
     auto load_chunk = [&](int kc, int st) {
         double* sAr = stage_ptr(st);
@@ -267,14 +271,14 @@ __global__ void __launch_bounds__(256, 1) block_gemm_dmma2_kernel(int64_t rows, 
         double* sBr = sAi + ZT_M * ZA_LD;
         double* sBi = sBr + ZT_K * ZB_LD;
         const int k0 = kc * ZT_K;
-        for (int idx = tid; idx < ZT_M * ZT_K; idx += 256) {  // A tile: 128 rows x 16 k, 256 contiguous bytes per row
+        for (int idx = tid; idx < ZT_M * ZT_K; idx += NTH) {  // A tile: 128 rows x 16 k, 256 contiguous bytes per row
             const int r = idx / ZT_K, kk = idx % ZT_K;
             const bool ok = row0 + r < rows && k0 + kk < ka;
             const double* src = (const double*)(A + (ok ? (size_t)(row0 + r) * lda + k0 + kk : 0));
             cp_async_8z(sAr + r * ZA_LD + kk, src, ok);
             cp_async_8z(sAi + r * ZA_LD + kk, src + 1, ok);
         }
-        for (int idx = tid; idx < ZT_K * ZT_N; idx += 256) {  // B tile: 16 k x 56 columns of the small matrix
+        for (int idx = tid; idx < ZT_K * ZT_N; idx += NTH) {  // B tile: 16 k x 56 columns of the small matrix
             const int kk = idx / ZT_N, c = idx % ZT_N;
             const bool ok = k0 + kk < ka && c < ncols;
             const double* src = (const double*)(C + (ok ? (size_t)(k0 + kk) * q + col0 + c : 0));
@@ -835,17 +839,23 @@ int nepb_block_gemm(const nepb_block* A, int acol0, int ka, const double* C, int
         int dev = 0;
         cudaGetDevice(&dev);
         if (!attr[dev & 15]) {
-            NEPB_CUDA(cudaFuncSetAttribute(block_gemm_dmma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZT_SMEM));
+            NEPB_CUDA(cudaFuncSetAttribute(block_gemm_dmma2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zt_smem(128)));
+            NEPB_CUDA(cudaFuncSetAttribute(block_gemm_dmma2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zt_smem(64)));
             attr[dev & 15] = true;
         }
+        static const int zm = (getenv("NEPB_GEMM_ZM") && atoi(getenv("NEPB_GEMM_ZM")) == 64) ? 64 : 128;  // 64-row CTAs (two per SM) measured slower: 22.2 vs 25.6 TFLOP/s at k = 200
         // column tiles of equal width (a multiple of 8, at most 56): 50 -> 56, 100 -> 56 + 48, 200 -> 4 x 48 + 8 ... the tiles that
         // remain partly empty skip their empty 8-column blocks
         const int ntiles8 = (q + 7) / 8;
         const int nct = (ntiles8 + ZT_NT - 1) / ZT_NT;
         const int cols_per_cta = 8 * ((ntiles8 + nct - 1) / nct);
-        dim3 grid((unsigned)((rows + ZT_M - 1) / ZT_M), (unsigned)nct);
-        NEPB_LAUNCH(block_gemm_dmma2_kernel, grid, 256, ZT_SMEM, rows, ka, q, cols_per_cta, (const double2*)A->d.p + acol0, A->k,
-                    (const double2*)g_gemm_c.p, (double2*)Y->d.p + ycol0, Y->k);
+        dim3 grid((unsigned)((rows + zm - 1) / zm), (unsigned)nct);
+        if (zm == 128)
+            NEPB_LAUNCH(block_gemm_dmma2_kernel<128>, grid, 256, zt_smem(128), rows, ka, q, cols_per_cta, (const double2*)A->d.p + acol0, A->k,
+                        (const double2*)g_gemm_c.p, (double2*)Y->d.p + ycol0, Y->k);
+        else
+            NEPB_LAUNCH(block_gemm_dmma2_kernel<64>, grid, 128, zt_smem(64), rows, ka, q, cols_per_cta, (const double2*)A->d.p + acol0, A->k,
+                        (const double2*)g_gemm_c.p, (double2*)Y->d.p + ycol0, Y->k);
     }
     NEPB_LAUNCH_CHECK();
     return NEPB_OK;
