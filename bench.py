@@ -587,6 +587,12 @@ def main():
     reduce = 1 if dist.world > 1 else 0
     reduce_e2e = 2 if dist.world > 1 else 0  # only rank 0 extracts (method_beyncontour.jl:114-184): the other ranks skip the download
     _lib.check(lib.nepb_contour_set_probe(integ._h, _lib.ptr(Vf), n))
+    # the probe and the moment array are passed again every step: page-lock them once (nepb_host_register, the documented option
+    # for buffers a caller re-uses) so that their transfers are direct DMA from / to pinned host memory
+    pinned = []
+    for arr in (Vf, S):
+        if lib.nepb_host_register(_lib.ptr(arr), arr.nbytes) == 0:
+            pinned.append(arr)
 
     def step_dev():
         _lib.check(lib.nepb_contour_integrate_dev(integ._h, len(mine), _lib.ptr(coef), _lib.ptr(Wm), reduce))
@@ -634,6 +640,8 @@ def main():
         log("[bench] contour: %.2f ms/step -> %.1f solves/s on %d GPU(s); e2e %.2f ms; eigenvalues inside: %s (p=%d)" %
             (t_step, value, dist.world, te, lam_found, info["p"]))
     sym = nepb200.symbolic_info(dnep)
+    for arr in pinned:
+        lib.nepb_host_unregister(_lib.ptr(arr))
     integ.close()
     dnep.close()
 
@@ -653,7 +661,7 @@ def main():
                    "lu": sym},
         "e2e": {"value": GUN_N / (te * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": int(n * GUN_K * 16 + coef.nbytes + Wm.nbytes),
                 "d2h_bytes_per_step": int(n * GUN_K * 2 * 16), "ms_per_step": te,
-                "note": "per rank: probe + coefficients up every step; the moment block comes back on rank 0 only (reduce = 2)"},
+                "note": "per rank: probe + coefficients up every step from page-locked host arrays (nepb_host_register); the moment block comes back on rank 0 only (reduce = 2)"},
         "gpu_launches": launches_total,
         "clocks": clocks,
         "eigenvalues_from_timed_moments": [[x.real, x.imag] for x in lam_found] if lam_found else None,
