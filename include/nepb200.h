@@ -113,6 +113,9 @@ int nepb_spmf_apply_block_ex(const nepb_spmf* h, int mode, const nepb_block* V, 
  * columns (<= 192) are staged in shared memory; *distinct_total = sum over tiles = rows of V gathered per product
  * (vs nnz_union without tiling); all zero when the operator has a row with more than 192 nonzeros (untiled kernels) */
 int nepb_spmf_tiles_info(const nepb_spmf* h, int64_t* ntiles, int64_t* distinct_total, int* max_distinct);
+/* the two-dimensional tiles of the multi-column product (5..32 columns): line = dominant column offset found in the pattern
+ * (0: none, the one-dimensional tiles are used), segments x seg_rows rows per tile, staged rows of V summed over the tiles */
+int nepb_spmf_tiles2d_info(const nepb_spmf* h, int* line, int* segments, int* seg_rows, int64_t* ntiles, int64_t* distinct_total);
 /* algorithmic HBM bytes of one nepb_spmf_apply_block call (SURVEY.md 8(d) formula) */
 int64_t nepb_spmf_apply_bytes(const nepb_spmf* h, int mode, int k, int q);
 

@@ -81,6 +81,7 @@ SIGNATURES = {
     "nepb_spmf_apply_block": (c_int, [vp, c_int, vp, c_int, vp, vp]),
     "nepb_spmf_apply_bytes": (c_i64, [vp, c_int, c_int, c_int]),
     "nepb_spmf_tiles_info": (c_int, [vp, P(c_i64), P(c_i64), P(c_int)]),
+    "nepb_spmf_tiles2d_info": (c_int, [vp, P(c_int), P(c_int), P(c_int), P(c_i64), P(c_i64)]),
     "nepb_lu_set_options": (c_int, [vp, c_int, c_int, c_int, vp]),
     "nepb_lu_symbolic_info": (c_int, [vp, P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_int), P(c_dbl)]),
     "nepb_lu_symbolic_get": (c_int, [vp, vp, vp, vp, vp, vp, vp]),

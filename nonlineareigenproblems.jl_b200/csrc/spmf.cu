@@ -1943,6 +1943,20 @@ int nepb_spmf_tiles_info(const nepb_spmf* h, int64_t* ntiles, int64_t* distinct_
     return NEPB_OK;
 }
 
+// two-dimensional tiles of the multi-column product: line length found in the pattern (0: none, the 1D tiles are used), segments
+// per tile, rows per segment, tiles, staged rows of V in total (distinct columns summed over the tiles)
+int nepb_spmf_tiles2d_info(const nepb_spmf* h, int* line, int* segments, int* seg_rows, int64_t* ntiles, int64_t* distinct_total) {
+    NEPB_CHECK_ARG(h, "handle is NULL");
+    const bool ok = spmf_build_tiles2d(h) == 1;
+    const nepb_spmf::TileSet2D& T = h->tiling2d;
+    if (line) *line = ok ? T.line : 0;
+    if (segments) *segments = ok ? T.S : 0;
+    if (seg_rows) *seg_rows = ok ? T.R : 0;
+    if (ntiles) *ntiles = ok ? T.ntiles : 0;
+    if (distinct_total) *distinct_total = ok ? (int64_t)(T.cols.n) : 0;
+    return NEPB_OK;
+}
+
 int nepb_spmf_pattern(const nepb_spmf* h, int64_t* colptr, int64_t* rowval) {
     NEPB_CHECK_ARG(h && colptr && rowval, "NULL argument");
     for (int64_t j = 0; j <= h->n; ++j) colptr[j] = h->h_colptr[j] + h->index_base;

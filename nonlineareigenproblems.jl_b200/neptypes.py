@@ -272,6 +272,12 @@ class B200SPMF:
         Cblk = np.ascontiguousarray(Cblk, dtype=np.complex128)
         check(lib.nepb_spmf_apply_block(self._h, mode, Vb._h, Zb.k, ptr(Cblk), Zb._h))
 
+    def tiles2d_info(self):
+        """(line, segments, rows per segment, tiles, staged V rows in total) of the two-dimensional tiles; line = 0: not applicable."""
+        ln, sg, sr, nt, tot = C.c_int(), C.c_int(), C.c_int(), C.c_int64(), C.c_int64()
+        check(lib.nepb_spmf_tiles2d_info(self._h, C.byref(ln), C.byref(sg), C.byref(sr), C.byref(nt), C.byref(tot)))
+        return ln.value, sg.value, sr.value, nt.value, tot.value
+
     def tiles_info(self):
         """Row tiles of the multi-column kernel: (tiles, V rows staged per product, largest tile)."""
         nt, tot, mx = C.c_int64(), C.c_int64(), C.c_int()

@@ -324,3 +324,49 @@ def test_host_buffer_pipeline_roundtrip():
             _lib.check(_lib.lib.nepb_host_unregister(_lib.ptr(buf)))
             _lib.check(_lib.lib.nepb_host_unregister(_lib.ptr(out)))
         b.close()
+
+
+def test_two_dimensional_tiles_of_the_multicolumn_kernel():
+    """The 2D tiles (S segments x R rows, segments one grid line apart; csrc/spmf.cu:spmf_build_tiles2d) depend on host integer
+    work: the line length is found from the pattern, every row belongs to exactly one tile, the remainder rows and the short
+    last segments of a line are handled.  Grid sides that are / are not multiples of the segment height, with / without a
+    remainder of rows behind the last super-block; every width class of the kernel (1..4 pieces of 8 columns); against the
+    oracle's products.  A pattern without a dominant line (random, gun) keeps the 1D tiles."""
+    import os
+    rng = np.random.default_rng(21)
+    for grid in (37, 40, 50):
+        mats, _ = g.stencil_pep(grid)
+        Av = [m.tocsc() for m in mats]
+        dnep = B200SPMF(Av, [Monomial(i) for i in range(4)])
+        line, S, R, ntiles, staged = dnep.tiles2d_info()
+        n = grid * grid
+        assert (line, S, R) == (grid, 4, 8)
+        nsb = n // (4 * grid)
+        expect = nsb * -(-grid // 8) + -(-(n - nsb * 4 * grid) // 32)
+        assert ntiles == expect
+        _, staged1d, _ = dnep.tiles_info()
+        assert staged < staged1d  # fewer staged rows of V than the 32-row strips
+        lam = 0.3 + 0.2j
+        Mo = sum(A * lam ** i for i, A in enumerate(Av))
+        for k in (5, 8, 9, 16, 17, 20, 24, 25, 32):
+            V = rng.standard_normal((n, k)) + 1j * rng.standard_normal((n, k))
+            Z = dnep.compute_MM(lam * np.eye(k), V)
+            assert relerr(Z, Mo @ V) < RTOL
+            os.environ["NEPB_SPMM_2D"] = "0"   # the 1D tiles give the same product
+            try:
+                assert relerr(dnep.compute_MM(lam * np.eye(k), V), Mo @ V) < RTOL
+            finally:
+                del os.environ["NEPB_SPMM_2D"]
+            assert np.array_equal(Z, dnep.compute_MM(lam * np.eye(k), V))  # bitwise reproducible
+        # a column window of a wider block (rows of V not adjacent in memory: one bulk copy per staged row)
+        from nepb200 import Block
+        Vw = rng.standard_normal((n, 24)) + 1j * rng.standard_normal((n, 24))
+        Vb, Zb = Block.from_host(Vw), Block(n, 24)
+        from nepb200 import _lib
+        cf = np.ascontiguousarray(dnep.coefficients(lam), dtype=np.complex128)
+        _lib.check(_lib.lib.nepb_spmf_apply_block_ex(dnep._h, 0, Vb._h, 3, 12, 12, _lib.ptr(cf), Zb._h, 5))
+        assert relerr(Zb.download()[:, 5:17], Mo @ Vw[:, 3:15]) < RTOL
+    A = sp.random(2000, 2000, 0.01, random_state=3, format="csc")
+    assert B200SPMF([A], [ONE]).tiles2d_info()[0] == 0
+    K, M, W1, W2 = g.load_gun_matrices()
+    assert B200SPMF([K, -M, W1, W2], [ONE, IDENTITY, ONE, ONE]).tiles2d_info()[0] == 0
