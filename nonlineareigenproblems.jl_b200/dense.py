@@ -64,6 +64,8 @@ def solve_block(solver, Bb: Block, bcol0: int, nrhs: int, Xb: Block, xcol0: int,
 
 def mlincomb_block(nep: B200SPMF, lam, Vb: Block, vcol0: int, k: int, a, Zb: Block, zcol0: int):
     """compute_Mlincomb!(nep, lam, V[:, vcol0:vcol0+k], a) -> Z[:, zcol0], operands in HBM."""
+    if hasattr(nep, "mlincomb_block"):  # a NEP type with its own device product (WEP_FD, Waveguide.jl:324-379)
+        return nep.mlincomb_block(lam, Vb, vcol0, k, a, Zb, zcol0)
     Cm, _ = nep.lincomb_coefficients(lam, np.asarray(a, dtype=np.complex128))
     Cm = np.ascontiguousarray(Cm.reshape(nep.p, k))
     check(lib.nepb_spmf_apply_block_ex(nep._h, _lib.COEF_GENERAL, Vb._h, vcol0, k, 1, ptr(Cm), Zb._h, zcol0))
@@ -72,6 +74,8 @@ def mlincomb_block(nep: B200SPMF, lam, Vb: Block, vcol0: int, k: int, a, Zb: Blo
 def residual_errors(nep: B200SPMF, errmeasure, lams, Qb: Block, k: int, Rb: Block):
     """estimate_error for all k Ritz pairs at once: one multi-lambda SpMM + column norms, everything in HBM."""
     lams = np.asarray(lams, dtype=np.complex128)
+    if hasattr(nep, "residual_block"):  # not an SPMF: one product per Ritz value (WEP_FD)
+        return nep.residual_block(lams, Qb, k, Rb)
     Cd = np.empty((nep.p, k), dtype=np.complex128)
     for i, f in enumerate(nep.fi):
         Cd[i, :] = [complex(f(complex(s))) for s in lams]

@@ -249,6 +249,15 @@ class WEP_FD:
         Zb.close()
         return out / np.linalg.norm(Q, axis=0)
 
+    def residual_block(self, lams, Qb: Block, k, Rb: Block):
+        """The same with Q already in HBM (the device-resident iar / tiar loops)."""
+        for s, lam in enumerate(lams[:k]):
+            self.mlincomb_block(lam, Qb, s, 1, [1.0], Rb, s, use_table=False)
+        num, den = np.empty(k), np.empty(k)
+        check(lib.nepb_block_colnorms(Rb._h, 0, k, self.n, ptr(num)))
+        check(lib.nepb_block_colnorms(Qb._h, 0, k, self.n, ptr(den)))
+        return num / den
+
     # -- boundary operator and Schur complement ----------------------------------------------------------------------------
     def Pinv(self, lam, x):
         """[R(Rinv(x1) ./ sM); R(Rinv(x2) ./ sP)] (Waveguide.jl:160-163) on the device."""

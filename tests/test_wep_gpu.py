@@ -123,3 +123,9 @@ def test_resinv_and_iar_reach_the_reference_eigenvalue():
     assert np.linalg.norm(nep.compute_Mlincomb(lam, v)) / np.linalg.norm(v) < 1e-10
     lams, V = nepb200.iar(nep, sigma=-3 - 3.5j, neigs=3, maxit=100, v=v0, tol=1e-8, linsolvercreator=creator)[:2]
     assert len(lams) == 3 and np.min(np.abs(LAMREF - lams)) < 1e-10
+    # tiar with the basis in HBM (config C5 of BASELINE.json in small): the same three eigenvalues (iar == tiar, test/tiar.jl)
+    lt, Qt = nepb200.tiar_device(nep, sigma=-3 - 3.5j, neigs=3, maxit=100, v=v0, tol=1e-8, linsolvercreator=creator)[:2]
+    assert len(lt) == 3 and np.min(np.abs(LAMREF - lt)) < 1e-10
+    assert max(np.min(np.abs(lams - x)) for x in lt) < 1e-8
+    for i in range(3):
+        assert np.linalg.norm(nep.compute_Mlincomb(lt[i], Qt[:, i])) / np.linalg.norm(Qt[:, i]) < 1e-8
