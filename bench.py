@@ -370,6 +370,34 @@ def bench_wep(args, peak, nz=945):
             raise SystemExit("bench: WEP compute_Mlincomb differs from the NumPy evaluation of the reference formula: %g" % err)
         Vb.close()
         Zb.close()
+    # C5 end to end: tiar with the basis in HBM (src/method_tiar.jl) on this problem, Schur-complement solver (Waveguide.jl:476-567)
+    # on the device multifrontal LU.  Reported, never fatal for the headline line.
+    try:
+        sigma = -3 - 3.5j
+        t0 = time.perf_counter()
+        solver = nepb200.WEPLinSolverCreator(solver_type="factorized").create_linsolver(nep, sigma)
+        lib.nepb_synchronize()
+        t_fact = time.perf_counter() - t0
+
+        class _Creator:
+            def create_linsolver(self, nep_, lam_):
+                return solver
+        l0 = lib.nepb_launch_count()
+        t0 = time.perf_counter()
+        lams, Q, _, _ = nepb200.tiar_device(nep, sigma=sigma, neigs=3, maxit=60, v=np.ones(n) / np.sqrt(n), tol=1e-8, linsolvercreator=_Creator())
+        lib.nepb_synchronize()
+        t_tiar = time.perf_counter() - t0
+        res = [float(np.linalg.norm(nep.compute_Mlincomb(lams[i], Q[:, i])) / np.linalg.norm(Q[:, i])) for i in range(len(lams))]
+        out["tiar_c5"] = {"schur_unknowns": int(nx * nz), "schur_lu": nepb200.symbolic_info(solver.schur), "assembly_analysis_factorisation_s": t_fact,
+                          "tiar_s": t_tiar, "gpu_launches": int(lib.nepb_launch_count() - l0), "eigenvalues": [[float(x.real), float(x.imag)] for x in lams],
+                          "residuals": res}
+        log("[bench] C5 tiar on WEP n=%d: Schur-complement LU %.2f s, tiar %.2f s, %d eigenvalues, max residual %.1e" %
+            (n, t_fact, t_tiar, len(lams), max(res) if res else float("nan")))
+        solver.fact.lu.close()
+        solver.schur.close()
+    except Exception as exc:  # noqa: BLE001
+        out["tiar_c5"] = {"error": repr(exc)}
+        log("[bench] C5 tiar on WEP failed: %r" % (exc,))
     nep.close()
     return out
 
