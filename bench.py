@@ -701,7 +701,7 @@ def main():
         try:
             # dram read+write per launch of THIS kernel from the committed ncu --set full capture; the file names the kernel it
             # was taken from, and a capture of another kernel is not reported
-            with open(os.path.join(ROOT, "profiles", "r1_spmm_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2_spmm_traffic.json")) as f:
                 tj = json.load(f)
             if "spmm_fused_kernel" in tj.get("kernel", "spmm_fused_kernel"):
                 traffic = tj["traffic_bytes_per_launch"]
