@@ -314,3 +314,154 @@ def nep_gallery_wep(nx=3 * 5 * 7, nz=3 * 5 * 7, benchmark_problem="TAUSCH", nept
     if neptype == "WEP":
         return WEP_FD(nx, nz, hx, hz, Dxx, Dzz, Dz, C1, C2T, K, Km, Kp)
     raise ValueError("The NEP-type '%s' is not supported for the waveguide eigenvalue problem." % neptype)
+
+
+# ---- Sylvester-SMW preconditioner (waveguide_preconditioner.jl) -----------------------------------------------------------
+# Test infrastructure only: the product ships the matrix-free Schur-complement product and a GMRES solver that takes any left
+# preconditioner as a callable (`Pl`, as IterativeSolvers' gmres); this restatement is what the GPU test hands to it, and it is
+# pinned to test/wep_small.jl:28-31 (with as many domains as grid lines the preconditioner is the exact inverse, 1e-14).
+def _F(v, n1):
+    """F (:190-199): zero-padded FFT of length 2 (n1 + 1) along the first axis, rows 2..n of the result."""
+    n = n1 + 1
+    pad = np.zeros((2 * n, v.shape[1]), dtype=np.complex128)
+    pad[1:n, :] = v
+    return np.fft.fft(pad, axis=0)[1:n, :]
+
+
+def _Fh(v, n1):
+    """Fh (:201-211)."""
+    n = n1 + 1
+    pad = np.zeros((2 * n, v.shape[1]), dtype=np.complex128)
+    pad[1:n, :] = v
+    return np.fft.ifft(pad, axis=0)[1:n, :] * 2 * n
+
+
+def _W(X):
+    """W = Wh (:160-187): the (real, symmetric) sine-transform matrix of the eigenvectors of Dxx, through two FFTs."""
+    n1 = X.shape[0]
+    return (_F(X, n1) - _Fh(X, n1)) * ((1j / 2) / math.sqrt((n1 + 1) / 2.0))
+
+
+def solve_wg_sylvester_fft(C, lam, k_bar, hx, hz):
+    """solve_wg_sylvester_fft! (:114-158): A X + X B = C with A = Dzz + 2 lam Dz + (lam^2 + k_bar) I (circulant) and B = Dxx."""
+    C = np.array(C, dtype=np.complex128)
+    nz, nx = C.shape
+    alpha = lam ** 2 + k_bar
+    v = np.zeros(nz, dtype=np.complex128)
+    v[0], v[1], v[nz - 1] = -2, 1, 1
+    v = v / hz ** 2
+    w = np.zeros(nz, dtype=np.complex128)
+    w[1], w[nz - 1] = 1, -1
+    w = w * (lam / hz)
+    D = np.fft.fft(v + w) + alpha
+    S = -(4 / hx ** 2) * np.sin(math.pi * np.arange(1, nx + 1) / (2 * (nx + 1))) ** 2
+    T = C.conj().T
+    C = _W(T).conj().T
+    C = np.fft.ifft(C, axis=0) * math.sqrt(nx)   # Vh! (:170-175)
+    Z = C / (D[:, None] + S[None, :])
+    T = Z.conj().T
+    C = _W(T).conj().T
+    return np.fft.fft(C, axis=0) / math.sqrt(nx)  # V! (:163-168)
+
+
+class WEPPreconditioner:
+    """wep_generate_preconditioner / generate_smw_matrix / solve_smw / ldiv! (:9-111, 218-421) for a WEP_FD with nx = nz + 4
+    and N domains in the z direction (nz / N an integer)."""
+
+    def __init__(self, nep, N, sigma):
+        import scipy.linalg as sl
+        if nep.nz + 4 != nep.nx:
+            raise ValueError("This implementation requires nx = nz + 4. Provided NEP has nz = %d and nx = %d" % (nep.nz, nep.nx))
+        if nep.nz % N:
+            raise ValueError("This implementation is uniform in the blocking and therefore requires nz/N to be an integer.")
+        self.nep, self.N, self.sigma = nep, int(N), complex(sigma)
+        n = nep.nz
+        self.L = n // self.N
+        self.dd1, self.dd2 = nep.d1 / nep.hx ** 2, nep.d2 / nep.hx ** 2
+        mm = self.N ** 2 + 4 * self.N
+        M = np.zeros((mm, mm), dtype=np.complex128)
+        for k in range(1, mm + 1):
+            E = self._Ek(k, 1.0, np.zeros((n, nep.nx), dtype=np.complex128))
+            Fk = self._Linv(E)
+            M[:, k - 1] = self._functionals(Fk)
+        self.lu = sl.lu_factor(M + np.eye(mm))
+
+    # index helpers (:236-255); 1-based i, j as in the reference
+    def _II(self, i):
+        return slice((i - 1) * self.L, i * self.L)
+
+    def _JJ(self, j):
+        return slice((j - 3) * self.L + 2, (j - 2) * self.L + 2)
+
+    def _JJ2(self, j):
+        n, N = self.nep.nz, self.N
+        return {1: 0, 2: 1, N + 3: n + 2, N + 4: n + 3}[j]
+
+    def _k2ij(self, k):
+        N = self.N
+        j = k % (N + 4) + (k % (N + 4) == 0) * (N + 4)
+        return (k - j) // (N + 4) + 1, j
+
+    def _Linv(self, rhs):
+        nep = self.nep
+        return solve_wg_sylvester_fft(rhs, self.sigma, nep.k_bar, nep.hx, nep.hz)
+
+    def _Pm(self, v):
+        nep = self.nep
+        return -nep.R(nep.Rinv(v) / nep.sM(self.sigma))
+
+    def _Pp(self, v):
+        nep = self.nep
+        return -nep.R(nep.Rinv(v) / nep.sP(self.sigma))
+
+    def _Ek(self, k, a, Y, quirk=False):
+        """Adds a * E~_k to Y (:265-293 with a = 1; :376-404 in solve_smw, whose j == 2 branch reads
+        `Y[II(i), 2] += Y[II(i), 2] + alpha[k]*K[II(i), 2]`, i.e. it doubles what is already there: kept, quirk=True)."""
+        nep, N = self.nep, self.N
+        n, nx, K = nep.nz, nep.nx, nep.K
+        i, j = self._k2ij(k)
+        II = self._II(i)
+        ek = np.zeros(n, dtype=np.complex128)
+        if j in (1, 2, N + 3, N + 4):
+            c = self._JJ2(j)
+            if quirk and j == 2:
+                Y[II, c] += Y[II, c] + a * K[II, c]
+            else:
+                Y[II, c] += a * K[II, c]
+            ek[II] = self.dd1 if j in (1, N + 4) else self.dd2
+            if j <= 2:
+                Y[:, 0] += a * self._Pm(ek)
+            else:
+                Y[:, nx - 1] += a * self._Pp(ek)
+        else:
+            JJ = self._JJ(j)
+            Y[II, JJ] += a * K[II, JJ]
+        return Y
+
+    def _functionals(self, X):
+        mm, N, L = self.N ** 2 + 4 * self.N, self.N, self.L
+        b = np.zeros(mm, dtype=np.complex128)
+        for k in range(1, mm + 1):
+            i, j = self._k2ij(k)
+            if j in (1, 2, N + 3, N + 4):
+                b[k - 1] = X[self._II(i), self._JJ2(j)].sum() / L
+            else:
+                b[k - 1] = X[self._II(i), self._JJ(j)].sum() / (L * L)
+        return b
+
+    def ldiv(self, B):
+        """ldiv!(precond, B) (:27-30): B <- vec(solve_smw(reshape(B, nz, nx)))."""
+        import scipy.linalg as sl
+        nep = self.nep
+        C = self._Linv(np.asarray(B, dtype=np.complex128).reshape(nep.nz, nep.nx, order="F"))
+        alpha = sl.lu_solve(self.lu, self._functionals(C))
+        Y = np.zeros((nep.nz, nep.nx), dtype=np.complex128)
+        for k in range(1, len(alpha) + 1):
+            self._Ek(k, alpha[k - 1], Y, quirk=True)
+        return (C - self._Linv(Y)).reshape(-1, order="F")
+
+    __call__ = ldiv
+
+
+def wep_generate_preconditioner(nep, N, sigma):
+    return WEPPreconditioner(nep, N, sigma)

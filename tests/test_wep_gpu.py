@@ -129,3 +129,24 @@ def test_resinv_and_iar_reach_the_reference_eigenvalue():
     assert max(np.min(np.abs(lams - x)) for x in lt) < 1e-8
     for i in range(3):
         assert np.linalg.norm(nep.compute_Mlincomb(lt[i], Qt[:, i])) / np.linalg.norm(Qt[:, i]) < 1e-8
+
+
+def test_resinv_with_gmres_and_the_sylvester_preconditioner():
+    """test/wep_small.jl:55-61: resinv with WEPLinSolverCreator(solver_type = :gmres, kwargs = ((:Pl, precond), (:reltol, 1e-7)))
+    and precond = wep_generate_preconditioner(nep, 3*7, lambda0).  The Schur-complement products of GMRES run on the device; the
+    preconditioner is the oracle's restatement of waveguide_preconditioner.jl, handed over as the `Pl` callable (the product
+    ships the solver, not this preconditioner)."""
+    nep = nepb200.nep_gallery_WEP(nx=3 * 5 * 7 + 4, nz=3 * 5 * 7, benchmark_problem="JARLEBRING", neptype="WEP")
+    onep = ow.nep_gallery_wep(nx=3 * 5 * 7 + 4, nz=3 * 5 * 7, benchmark_problem="JARLEBRING", neptype="WEP")
+    lam0 = -3 - 3.5j
+    precond = ow.wep_generate_preconditioner(onep, 3 * 7, lam0)
+    n = nep.n
+    v0 = np.ones(n) / np.sqrt(n)
+
+    class RefErr:
+        def estimate_error(self, lam, v):
+            return abs(lam - LAMREF) / abs(lam)
+    creator = nepb200.WEPLinSolverCreator(solver_type="gmres", kwargs=(("Pl", precond), ("reltol", 1e-7)))
+    lam, v = nepb200.resinv(nep, lam=lam0, v=v0, tol=1e-12, errmeasure=RefErr(), linsolvercreator=creator)
+    assert abs(lam - LAMREF) < 1e-11 * abs(lam)
+    assert np.linalg.norm(nep.compute_Mlincomb(lam, v)) / np.linalg.norm(v) < 1e-10

@@ -67,3 +67,24 @@ def test_resinv_reaches_the_reference_eigenvalue():
     lam, v = osol.resinv(nep, lam=-3 - 3.5j, v=v0, tol=1e-12, errmeasure=err, linsolvercreator=ow.WEPLinSolverCreator())
     assert abs(lam - LAMREF) < 1e-11 * abs(lam)
     assert np.linalg.norm(o.compute_Mlincomb(nep, lam, v)) / np.linalg.norm(v) < 1e-10
+
+
+def test_sylvester_smw_preconditioner_literal():
+    """test/wep_small.jl:28-31: with N = nz domains the Sylvester-SMW preconditioner (waveguide_preconditioner.jl) inverts the
+    Schur complement: ldiv!(precond, SchurMatVec * b1) == b1 to 1e-14; and its Sylvester solver solves A X + X B = C."""
+    nx, nz = 11, 7
+    nep = ow.nep_gallery_wep(nx=nx, nz=nz, benchmark_problem="TAUSCH", neptype="WEP")
+    lam = -1.3 - 0.31j
+    rng = np.random.default_rng(0)
+    C = rng.standard_normal((nz, nx)) + 1j * rng.standard_normal((nz, nx))
+    X = ow.solve_wg_sylvester_fft(C, lam, nep.k_bar, nep.hx, nep.hz)
+    assert np.linalg.norm(nep.A(lam) @ X + X @ nep.Dxx.toarray() - C) < 1e-13 * np.linalg.norm(C)
+    precond = ow.wep_generate_preconditioner(nep, nz, lam)
+    b1 = rng.random(nx * nz) + 1j * rng.random(nx * nz)
+    b2 = precond.ldiv(ow.schur_matvec(nep, lam, b1))
+    assert np.linalg.norm(b1 - b2) / np.linalg.norm(b1) < 1e-14
+    import pytest
+    with pytest.raises(ValueError):
+        ow.wep_generate_preconditioner(ow.nep_gallery_wep(nx=12, nz=7, neptype="WEP"), 7, lam)   # nx != nz + 4
+    with pytest.raises(ValueError):
+        ow.wep_generate_preconditioner(nep, 3, lam)   # nz / N not an integer
