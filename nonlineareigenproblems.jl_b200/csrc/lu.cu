@@ -1519,7 +1519,7 @@ static int lu_symbolic_build(const nepb_spmf* h, const int32_t* rowmap, const do
     std::vector<int32_t> kback(ns, 0);
     std::vector<char> defer(ns, 0);
     static const bool use_ring = !(getenv("NEPB_LU_SCHUR_RING") && atoi(getenv("NEPB_LU_SCHUR_RING")) == 0) && !getenv("NEPB_LU_SCHUR_SIMPLE");
-    static const int window = std::max(1, std::min(4, getenv("NEPB_LU_WINDOW") ? atoi(getenv("NEPB_LU_WINDOW")) : 4));
+    static const int window = std::max(1, std::min(7, getenv("NEPB_LU_WINDOW") ? atoi(getenv("NEPB_LU_WINDOW")) : 4));  // kback + np <= 224: the strip caps are 8-bit
     sd->schur_ring = use_ring && S.max_np <= 32;
     static const int ring_tn = (getenv("NEPB_LU_SCHUR_TN") && atoi(getenv("NEPB_LU_SCHUR_TN")) == 64) ? 64 : 32;
     sd->schur_tn = sd->schur_ring ? ring_tn : SCHUR_T;
