@@ -243,30 +243,67 @@ __global__ void __launch_bounds__(512) wep_czt_inv_kernel(int nz, int na, int fl
     }
 }
 
+// t[m] = chirp[mm] * sum_jj coef[m, jj] (a_jj) G[m, jj], m = h nz + mm: one warp per output, lanes along the columns (both rows are
+// contiguous), fixed-order shuffle tree.  Used for more than 4 columns: inside the two CTAs of the forward transform the same sums
+// are a chain of dependent L2 round trips (measured 30 us at 20 columns, 120 us at 60).
+__global__ void __launch_bounds__(256) wep_combine_kernel(int nz, int na, const double* __restrict__ chirp, const double* __restrict__ coef, int ldc,
+                                                          const double* __restrict__ avec, const double* __restrict__ G, double* __restrict__ t) {
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= 2 * nz) return;
+    const double* cf = coef + 2 * (int64_t)m * ldc;
+    const double* g = G + 2 * (int64_t)m * na;
+    c2 acc{0, 0};
+    for (int jj = lane; jj < na; jj += 32) acc = fma2(avec ? mul(ld(cf + 2 * jj), ld(avec + 2 * jj)) : ld(cf + 2 * jj), ld(g + 2 * jj), acc);
+    for (int o = 16; o; o >>= 1) {
+        acc.re += __shfl_xor_sync(0xffffffffu, acc.re, o);
+        acc.im += __shfl_xor_sync(0xffffffffu, acc.im, o);
+    }
+    if (lane == 0) st(t + 2 * m, mul(acc, ld(chirp + 2 * (m % nz))));
+}
+
 // y[h nz + nz-1-j] = bb[j] * DFT( t )[j] (+ C2T rows), t[m] = sum_jj coef[m, jj] (a_jj) G[m, jj]:  block h
 __global__ void __launch_bounds__(512) wep_czt_fwd_kernel(int nx, int nz, int na, int fl, const double* __restrict__ ftw,
                                                           const double* __restrict__ chirp, const double* __restrict__ filt,
                                                           const double* __restrict__ bb, const double* __restrict__ coef, int ldc,
                                                           const double* __restrict__ avec, const double* __restrict__ G,
-                                                          const double* __restrict__ V1, int64_t ldv, c2 cd1, c2 cd2, double* __restrict__ y,
-                                                          int64_t ldy) {
+                                                          const double* __restrict__ tvec, const double* __restrict__ V1, int64_t ldv, c2 cd1,
+                                                          c2 cd2, double* __restrict__ y, int64_t ldy) {
     extern __shared__ double2 czt_sm[];
     c2* sm = reinterpret_cast<c2*>(czt_sm);
     const int h = blockIdx.x;
-    // t[m] = sum_jj coef[m, jj] G[m, jj]: 8 lanes per m (lane l takes jj = l, l + 8, ...), folded in a fixed order
-    for (int m0 = 0; m0 < fl; m0 += blockDim.x / 8) {
-        const int m = m0 + threadIdx.x / 8, l = threadIdx.x % 8;
-        c2 t{0, 0};
-        if (m < nz) {
-            const double* cf = coef + 2 * (int64_t)(h * nz + m) * ldc;
-            const double* g = G + 2 * (int64_t)(h * nz + m) * na;
-            for (int jj = l; jj < na; jj += 8) t = fma2(avec ? mul(ld(cf + 2 * jj), ld(avec + 2 * jj)) : ld(cf + 2 * jj), ld(g + 2 * jj), t);
+    if (tvec) {  // combined (and chirped) by wep_combine_kernel
+        for (int m = threadIdx.x; m < fl; m += blockDim.x) sm[m] = (m < nz) ? ld(tvec + 2 * (h * nz + m)) : c2{0, 0};
+    } else if (na <= 4) {  // few columns: one thread per m
+        for (int m = threadIdx.x; m < fl; m += blockDim.x) {
+            c2 t{0, 0};
+            if (m < nz) {
+                const double* cf = coef + 2 * (int64_t)(h * nz + m) * ldc;
+                const double* g = G + 2 * (int64_t)(h * nz + m) * na;
+                for (int jj = 0; jj < na; ++jj) t = fma2(avec ? mul(ld(cf + 2 * jj), ld(avec + 2 * jj)) : ld(cf + 2 * jj), ld(g + 2 * jj), t);
+                t = mul(t, ld(chirp + 2 * m));
+            }
+            sm[m] = t;
         }
-        for (int o = 4; o; o >>= 1) {
-            t.re += __shfl_xor_sync(0xffffffffu, t.re, o);
-            t.im += __shfl_xor_sync(0xffffffffu, t.im, o);
+    } else {
+        // t[m] = sum_jj coef[m, jj] G[m, jj]: 8 lanes per m (lane l takes jj = l, l + 8, ...), folded in a fixed order; the
+        // padding m >= nz is zeroed separately so that the loop (whose loads are dependent L2 round trips) only covers nz outputs
+        for (int m = nz + threadIdx.x; m < fl; m += blockDim.x) sm[m] = c2{0, 0};
+        const int per = blockDim.x / 8, l = threadIdx.x % 8, mo = threadIdx.x / 8;
+#pragma unroll 4
+        for (int m0 = 0; m0 < nz; m0 += per) {
+            const int m = m0 + mo;
+            c2 t{0, 0};
+            if (m < nz) {
+                const double* cf = coef + 2 * (int64_t)(h * nz + m) * ldc;
+                const double* g = G + 2 * (int64_t)(h * nz + m) * na;
+                for (int jj = l; jj < na; jj += 8) t = fma2(avec ? mul(ld(cf + 2 * jj), ld(avec + 2 * jj)) : ld(cf + 2 * jj), ld(g + 2 * jj), t);
+            }
+            for (int o = 4; o; o >>= 1) {
+                t.re += __shfl_xor_sync(0xffffffffu, t.re, o);
+                t.im += __shfl_xor_sync(0xffffffffu, t.im, o);
+            }
+            if (l == 0 && m < nz) sm[m] = mul(t, ld(chirp + 2 * m));
         }
-        if (l == 0 && m < fl) sm[m] = (m < nz) ? mul(t, ld(chirp + 2 * m)) : c2{0, 0};
     }
     fft_convolve(sm, fl, ftw, filt);
     const double sc = 1.0 / (double)fl;
@@ -302,8 +339,14 @@ int boundary(const nepb_wep* h, int na, const double* d_coef, int ldc, const dou
         NEPB_CUDA(h->G.reserve((size_t)4 * h->nz * na));
         const size_t smem = (size_t)h->fl * 32;  // data + per-stage twiddle runs
         NEPB_LAUNCH(wep_czt_inv_kernel, dim3(na, 2), 512, smem, h->nz, na, h->fl, h->ftw.p, h->chirp.p, h->filt_i.p, h->bb.p, d_v2, ldv2, h->G.p);
+        const double* tvec = nullptr;
+        if (na > 4) {
+            NEPB_CUDA(h->t.reserve((size_t)4 * h->nz));
+            NEPB_LAUNCH(wep_combine_kernel, (2 * h->nz + 7) / 8, 256, 0, h->nz, na, h->chirp.p, d_coef, ldc, d_avec, h->G.p, h->t.p);
+            tvec = h->t.p;
+        }
         NEPB_LAUNCH(wep_czt_fwd_kernel, 2, 512, smem, h->nx, h->nz, na, h->fl, h->ftw.p, h->chirp.p, h->filt_f.p, h->bb.p, d_coef, ldc, d_avec,
-                    h->G.p, d_V1, ldv, cd1, cd2, d_y, ldy);
+                    h->G.p, tvec, d_V1, ldv, cd1, cd2, d_y, ldy);
         NEPB_LAUNCH_CHECK();
         return NEPB_OK;
     }
