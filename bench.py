@@ -213,7 +213,7 @@ def build_c4(grid):
 # ------------------------------------------------------------------------------------------------
 # workload: fused SPMF SpMM on config C4 (roofline)
 # ------------------------------------------------------------------------------------------------
-def bench_spmm(args, ks=(1, 8, 20)):
+def bench_spmm(args, ks=(1, 8, 20), with_cpu=True):
     """Config C4.  SCALAR mode (M(lambda) V, the north-star formula) for k = 1, 8, 20; GENERAL mode as the solver loops call it
     (compute_Mlincomb with k = 20 / 100 basis columns, NEPTypes.jl:972-1011, and the nleigs stacked product with N = 7 blocks,
     method_nleigs.jl:456-472).  Every timed product is compared with a SciPy CSR product on the same V (parity at the stated
@@ -287,7 +287,7 @@ def bench_spmm(args, ks=(1, 8, 20)):
         Vb.close()
         Zb.close()
     cpu = None
-    if not args.no_cpu_baseline:
+    if with_cpu and not args.no_cpu_baseline:
         # CPU side: the C restatement of the reference's compute_MM loop (oracle/csrc/spmf_mm.c) -- once in the reference's own
         # serial form (CSC, one thread) and once row-parallel over all host cores
         from oracle.cspmf import CSpmf
@@ -676,7 +676,7 @@ def main():
     # ---- SpMM roofline (every rank runs its own replica; rank 0 reports) -------------------------------------
     spmm, peak, peak_src, cpu_spmm, general = (None, None, None, None, None)
     if not args.no_spmm:
-        spmm, peak, peak_src, cpu_spmm, general = bench_spmm(args)
+        spmm, peak, peak_src, cpu_spmm, general = bench_spmm(args, with_cpu=(dist.rank == 0 and dist.world == 1))
 
     line = {
         "metric": "contour_beyn quadrature-point solves/sec (gun, N=128, k=20)",
@@ -714,7 +714,7 @@ def main():
         line["spmm_kernels"] = {"1": "spmm_fused_kernel", "8": "spmm_tma2d_kernel<CPT=1> (2D tiles of 4 x 8 rows, TMA bulk staging)",
                                 "20": "spmm_tma2d_kernel<CPT=3> (2D tiles of 4 x 8 rows, TMA bulk staging)"}
         line["spmm_general"] = general
-        if dist.rank == 0:
+        if dist.rank == 0 and dist.world == 1:  # auxiliary section: single-GPU runs only
             line["wep"] = bench_wep(args, peak)
     # factorisation roofline of the headline step: complex multiply-adds of the numeric LU (symbolic count) x 8 flops x nodes over
     # the step time, against a measured cuBLAS ZGEMM rate; the triangular solves and the assembly are in the time, not in the flops
@@ -726,7 +726,7 @@ def main():
                                     "frac": fl / (t_step * 1e-3) / 1e12 / (zpeak * dist.world), "peak_source": zsrc,
                                     "flops_per_step": fl, "factor_bytes_streamed_by_the_solves_per_step": solve_bytes,
                                     "note": "whole step time (factor + forward/backward solves + accumulate) against the factorisation flops only"}
-    if dist.rank == 0 and not args.no_cpu_baseline:
+    if dist.rank == 0 and dist.world == 1 and not args.no_cpu_baseline:  # the CPU baseline is timed at N = 1 only
         cores = max(1, min(host_cores(), 64))
         cpu = CpuContour(cores)
         import tempfile
